@@ -1,0 +1,96 @@
+"""Seeded synthetic weights with the tensor names of the real checkpoints.
+
+Names and shapes follow the HF ``Wav2Vec2BertModel`` state dict that the reference loads
+(``audiotoken/encoder.py:129``; shapes listed in SURVEY.md A.3), the VQ ``state_dict``
+layout the reference reads (``_codebook.embed`` ``[1, K, D]``, ``audiotoken/utils.py:331-339``)
+and, for the acoustic path, the HF ``EncodecModel`` encoder/quantizer names
+(SURVEY.md A.7).  A real checkpoint with the same names loads through the same code.
+
+All tensors are drawn on the CPU from one ``torch.Generator`` in a fixed order, so the GPU
+box and the build container produce bit-identical weights for a given seed.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+W2VBERT = dict(hidden=1024, heads=16, head_dim=64, ffn=4096, feat_in=160,
+               conv_kernel=31, left=64, right=8, ln_eps=1e-5)
+
+
+def _randn(g, *shape, std=1.0, mean=0.0):
+    return torch.randn(*shape, generator=g, dtype=torch.float32) * std + mean
+
+
+def synthetic_w2vbert_state_dict(n_layers: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """HF-named fp32 tensors for `n_layers` conformer layers + the feature projection.
+
+    Scales follow HF's default init (Linear N(0, 0.02), distance embedding N(0, 1),
+    pointwise conv ~N(0, 0.044), depthwise ~N(0, 0.25)); LayerNorm gains/biases and Linear
+    biases are perturbed away from 1/0 so that parity tests exercise them.
+    """
+    g = torch.Generator().manual_seed(seed)
+    H, F, D = W2VBERT['hidden'], W2VBERT['ffn'], W2VBERT['feat_in']
+    sd: Dict[str, torch.Tensor] = {}
+
+    def ln(prefix, n):
+        sd[prefix + '.weight'] = _randn(g, n, std=0.1, mean=1.0)
+        sd[prefix + '.bias'] = _randn(g, n, std=0.1)
+
+    def lin(prefix, n_out, n_in, std=0.02, bias=True):
+        sd[prefix + '.weight'] = _randn(g, n_out, n_in, std=std)
+        if bias:
+            sd[prefix + '.bias'] = _randn(g, n_out, std=0.02)
+
+    ln('feature_projection.layer_norm', D)
+    lin('feature_projection.projection', H, D, std=0.045)
+    for i in range(n_layers):
+        p = f'encoder.layers.{i}.'
+        ln(p + 'ffn1_layer_norm', H)
+        lin(p + 'ffn1.intermediate_dense', F, H)
+        lin(p + 'ffn1.output_dense', H, F)
+        ln(p + 'self_attn_layer_norm', H)
+        for nm in ('linear_q', 'linear_k', 'linear_v', 'linear_out'):
+            lin(p + 'self_attn.' + nm, H, H)
+        sd[p + 'self_attn.distance_embedding.weight'] = _randn(
+            g, W2VBERT['left'] + W2VBERT['right'] + 1, W2VBERT['head_dim'], std=1.0)
+        ln(p + 'conv_module.layer_norm', H)
+        sd[p + 'conv_module.pointwise_conv1.weight'] = _randn(g, 2 * H, H, 1, std=0.044)
+        sd[p + 'conv_module.depthwise_conv.weight'] = _randn(g, H, 1, W2VBERT['conv_kernel'], std=0.25)
+        ln(p + 'conv_module.depthwise_layer_norm', H)
+        sd[p + 'conv_module.pointwise_conv2.weight'] = _randn(g, H, H, 1, std=0.044)
+        ln(p + 'ffn2_layer_norm', H)
+        lin(p + 'ffn2.intermediate_dense', F, H)
+        lin(p + 'ffn2.output_dense', H, F)
+        ln(p + 'final_layer_norm', H)
+    return sd
+
+
+def synthetic_codebook(codebook_size: int, dim: int, seed: int = 4) -> torch.Tensor:
+    """`[K, D]` fp32 centroids ~ N(0, 1) (BASELINE config 5 recipe)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(codebook_size, dim, generator=g, dtype=torch.float32)
+
+
+def data_derived_codebook(embeddings: torch.Tensor, codebook_size: int, seed: int = 2,
+                          noise: float = 0.3) -> torch.Tensor:
+    """Centroids sampled from LayerNormed embeddings + noise (random N(0,1)
+    centroids collapse to ~140 used codes; data-derived ones give realistic margins)."""
+    g = torch.Generator().manual_seed(seed)
+    e = embeddings.reshape(-1, embeddings.shape[-1]).float().cpu()
+    idx = torch.randint(0, e.shape[0], (codebook_size,), generator=g)
+    return e[idx] + noise * torch.randn(codebook_size, e.shape[1], generator=g)
+
+
+def synthetic_waveform(index: int, num_samples: int, sample_rate: int) -> torch.Tensor:
+    """Clip `index` of the synthetic corpus: noise + 3 sinusoids, in [-1, 1]."""
+    g = torch.Generator().manual_seed(1000 + index)
+    t = torch.arange(num_samples, dtype=torch.float64) / sample_rate
+    x = 0.1 * torch.randn(num_samples, generator=g, dtype=torch.float32)
+    f = torch.rand(3, generator=g) * (4000.0 - 80.0) + 80.0
+    a = torch.rand(3, generator=g) * (0.2 - 0.05) + 0.05
+    ph = torch.rand(3, generator=g) * 2 * torch.pi
+    for k in range(3):
+        x = x + (a[k].double() * torch.sin(2 * torch.pi * f[k].double() * t + ph[k].double())).float()
+    return x.clamp_(-1.0, 1.0)
