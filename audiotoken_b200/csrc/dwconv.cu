@@ -1,0 +1,136 @@
+// Conformer convolution-module middle (HF modeling_wav2vec2_bert.py:213-221):
+//   causal depthwise conv1d (k=31, left pad 30 zeros, per clip) -> LayerNorm(1024) -> swish.
+// Work item = (clip, 16-row time tile); 512 threads, each owns a channel pair for all 16 rows:
+// 31x2 weights and 16x2 accumulators live in registers, the 46 input rows are streamed once
+// (coalesced 2 KB rows, re-reads between neighbouring tiles hit L2).  The LayerNorm needs the whole
+// 1024-channel row, so row statistics go through a two-level (warp shuffle, shared memory) reduction.
+// HBM-bound: 2 KB (bf16) read + 2 KB written per row.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kC = 1024, kK = 31, kTT = 16, kThreads = 512;
+
+template <typename T> B2T_DEVICE float2 ld2(const T* p);
+template <> B2T_DEVICE float2 ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> B2T_DEVICE float2 ld2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T> B2T_DEVICE void st2(T* p, float a, float b);
+template <> B2T_DEVICE void st2<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> B2T_DEVICE void st2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename T, bool kBF16>
+__global__ void __launch_bounds__(kThreads)
+dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
+                       const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                       const int32_t* __restrict__ row_off, const int32_t* __restrict__ ctile_clip,
+                       const int32_t* __restrict__ ctile_t0, T* __restrict__ out) {
+  __shared__ float s_red[16][kTT];
+  __shared__ float s_stat[kTT];
+  const int clip = ctile_clip[blockIdx.x], t0 = ctile_t0[blockIdx.x];
+  const int r0 = row_off[clip], rows = row_off[clip + 1] - r0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = tid * 2;
+
+  float w0[kK], w1[kK];
+#pragma unroll
+  for (int k = 0; k < kK; ++k) {
+    w0[k] = r16<kBF16>(__ldg(w_dw + (size_t)c * kK + k));
+    w1[k] = r16<kBF16>(__ldg(w_dw + (size_t)(c + 1) * kK + k));
+  }
+  float a0[kTT], a1[kTT];
+#pragma unroll
+  for (int t = 0; t < kTT; ++t) { a0[t] = 0.f; a1[t] = 0.f; }
+
+  // input row (t0 - 30 + j), j = 0..45, contributes to output t with tap k = j - t  (0 <= k <= 30)
+#pragma unroll
+  for (int j = 0; j < kTT + kK - 1; ++j) {
+    const int tr = t0 - (kK - 1) + j;
+    float2 v = make_float2(0.f, 0.f);
+    if (tr >= 0 && tr < rows) v = ld2<T>(x + (size_t)(r0 + tr) * kC + c);
+#pragma unroll
+    for (int t = 0; t < kTT; ++t) {
+      const int k = j - t;
+      if (k >= 0 && k < kK) {
+        a0[t] = fmaf(w0[k], v.x, a0[t]);
+        a1[t] = fmaf(w1[k], v.y, a1[t]);
+      }
+    }
+  }
+  // LayerNorm over channels, all 16 rows at once
+  float part[kTT];
+#pragma unroll
+  for (int t = 0; t < kTT; ++t) {
+    a0[t] = r16<kBF16>(a0[t]);
+    a1[t] = r16<kBF16>(a1[t]);
+    part[t] = warp_sum(a0[t] + a1[t]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < kTT; ++t) s_red[warp][t] = part[t];
+  }
+  __syncthreads();
+  if (tid < kTT) {
+    float s = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 16; ++wi) s += s_red[wi][tid];
+    s_stat[tid] = s * (1.0f / kC);
+  }
+  __syncthreads();
+  float mu[kTT];
+#pragma unroll
+  for (int t = 0; t < kTT; ++t) {
+    mu[t] = s_stat[t];
+    float d0 = a0[t] - mu[t], d1 = a1[t] - mu[t];
+    part[t] = warp_sum(d0 * d0 + d1 * d1);
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < kTT; ++t) s_red[warp][t] = part[t];
+  }
+  __syncthreads();
+  if (tid < kTT) {
+    float s = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 16; ++wi) s += s_red[wi][tid];
+    s_stat[tid] = rsqrtf(s * (1.0f / kC) + 1e-5f);
+  }
+  __syncthreads();
+  const float g0 = __ldg(ln_w + c), g1 = __ldg(ln_w + c + 1);
+  const float b0 = __ldg(ln_b + c), b1 = __ldg(ln_b + c + 1);
+#pragma unroll
+  for (int t = 0; t < kTT; ++t) {
+    if (t0 + t < rows) {
+      const float rs = s_stat[t];
+      float y0 = (a0[t] - mu[t]) * rs * g0 + b0;
+      float y1 = (a1[t] - mu[t]) * rs * g1 + b1;
+      y0 = y0 * sigmoidf_(y0);
+      y1 = y1 * sigmoidf_(y1);
+      st2<T>(out + (size_t)(r0 + t0 + t) * kC + c, y0, y1);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float* ln_weight,
+                                   const float* ln_bias, const b2t_batch* b, void* out,
+                                   int precision, void* stream) {
+  B2T_REQUIRE(x && w_dw && ln_weight && ln_bias && b && out, B2T_ERR_ARG, "b2t_dwconv_ln_swish: null argument");
+  int rc = b2t_arch_ok();
+  if (rc != B2T_OK) return rc;
+  if (b->n_ctiles <= 0) return B2T_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == B2T_PREC_BF16)
+    dwconv_ln_swish_kernel<__nv_bfloat16, true><<<b->n_ctiles, kThreads, 0, st>>>(
+        (const __nv_bfloat16*)x, w_dw, ln_weight, ln_bias, b->row_off, b->ctile_clip, b->ctile_t0, (__nv_bfloat16*)out);
+  else
+    dwconv_ln_swish_kernel<float, false><<<b->n_ctiles, kThreads, 0, st>>>(
+        (const float*)x, w_dw, ln_weight, ln_bias, b->row_off, b->ctile_clip, b->ctile_t0, (float*)out);
+  B2T_LAUNCH_CHECK();
+  return B2T_OK;
+}

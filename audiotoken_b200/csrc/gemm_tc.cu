@@ -1,0 +1,309 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  out = A[M,K] (bf16, K-major) . W[N,K]^T (bf16, K-major)
+// with fp32 accumulation in tensor memory and the fused epilogues of gemm_epilogue.cuh.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0     TMA producer  : cp.async.bulk.tensor 2D loads of a 128x64 A tile and a BNx64 W tile
+//                              (SWIZZLE_128B) into a kStages-deep shared-memory ring, mbarrier
+//                              complete_tx signalling.
+//   warp 1     MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                              (M=128, N=BN, K=16) x4 per 64-wide k-block; tcgen05.commit frees the
+//                              smem slot / publishes the accumulator.  Also owns the TMEM allocation.
+//   warps 2-5  epilogue      : tcgen05.ld 32x32b.x32 (each warp its own 32-lane quadrant), bias /
+//                              activation / residual / GLU, direct 16-byte global stores.
+// The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  Tiles are visited n-fastest so concurrently running CTAs share the A tile in L2.
+#include <cuda.h>
+#include "gemm_epilogue.cuh"
+
+namespace {
+
+constexpr int kBM = 128, kBK = 64;
+constexpr int kThreads = 192;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+B2T_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+B2T_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+B2T_DEVICE void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+B2T_DEVICE void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+B2T_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch failure reported by the host) instead of hanging
+// the GPU box.  2^26 probes of a hardware-sleeping try_wait is seconds, far beyond any real wait.
+B2T_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+B2T_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+B2T_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+B2T_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+B2T_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+B2T_DEVICE void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+B2T_DEVICE void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+B2T_DEVICE void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+B2T_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, single CTA, bf16 inputs, fp32 accumulate
+B2T_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+B2T_DEVICE void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+B2T_DEVICE void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64).
+B2T_DEVICE uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a_format BF16 [7,10)=1, b_format BF16 [10,13)=1,
+// a/b K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
+constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStageA = kBM * kBK * 2;         // 16 KB
+  static constexpr int kStageB = BN * kBK * 2;          // 32 KB (BN=256)
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTileBytes = kStages * (kStageA + kStageB);
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kTileBytes + kBarBytes + 1024;  // +1024 for manual alignment
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               int K, EpiParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + kStages * L::kStageA;
+  const uint32_t bars = base + L::kTileBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = p.N / BN;
+  const int tiles_m = (p.M + kBM - 1) / kBM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + kBK - 1) / kBK;
+  constexpr uint32_t kTmemCols = 2 * BN;   // 512 (BN=256) or 256 (BN=128): powers of two
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), L::kStageA + L::kStageB);
+          tma_load_2d(sA + stage * L::kStageA, &map_a, full_bar(stage), kb * kBK, m0);
+          tma_load_2d(sB + stage * L::kStageB, &map_w, full_bar(stage), kb * kBK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(sA + stage * L::kStageA);
+          const uint64_t db = make_smem_desc(sB + stage * L::kStageB);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 field
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));   // implies tcgen05.fence::before_thread_sync
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        epilogue_store<EPI, true, 32>(p, row, n0 + c * 32, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// [rows, K] bf16 row-major with leading dimension ld (elements); box = 64 (K) x box_rows, 128B swizzle
+int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2T_REQUIRE(fn != nullptr, B2T_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2T_REQUIRE(r == CUDA_SUCCESS, B2T_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+  return B2T_OK;
+}
+
+template <int BN, int EPI>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  static bool configured = false;
+  if (!configured) {
+    B2T_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = ((a->M + kBM - 1) / kBM) * (a->N / BN);
+  int grid = b2t_num_sms();
+  if (tiles < grid) grid = tiles;
+  gemm_tc_kernel<BN, EPI><<<grid, kThreads, L::kTotal, st>>>(ma, mw, a->K, p);
+  B2T_LAUNCH_CHECK();
+  return B2T_OK;
+}
+
+template <int BN>
+int dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mw, const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st) {
+  switch (a->epilogue) {
+    case B2T_EPI_BIAS: return launch_tc<BN, B2T_EPI_BIAS>(ma, mw, a, p, st);
+    case B2T_EPI_BIAS_SWISH: return launch_tc<BN, B2T_EPI_BIAS_SWISH>(ma, mw, a, p, st);
+    case B2T_EPI_RESID: return launch_tc<BN, B2T_EPI_RESID>(ma, mw, a, p, st);
+    case B2T_EPI_GLU: return launch_tc<BN, B2T_EPI_GLU>(ma, mw, a, p, st);
+    case B2T_EPI_BIAS_MASK: return launch_tc<BN, B2T_EPI_BIAS_MASK>(ma, mw, a, p, st);
+  }
+  b2t_set_error("b2t_gemm: unknown epilogue %d", a->epilogue);
+  return B2T_ERR_ARG;
+}
+
+}  // namespace
+
+int b2t_gemm_tensor(const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st) {
+  B2T_REQUIRE(a->N % 128 == 0, B2T_ERR_ARG, "b2t_gemm(tensor): N must be a multiple of 128 (N=%d)", a->N);
+  B2T_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->W % 16) == 0, B2T_ERR_ARG,
+              "b2t_gemm(tensor): A and W must be 16-byte aligned");
+  CUtensorMap ma, mw;
+  const int bn = (a->N % 256 == 0) ? 256 : 128;
+  int rc = make_map(&ma, a->A, a->M, a->K, a->lda, kBM);
+  if (rc != B2T_OK) return rc;
+  rc = make_map(&mw, a->W, a->N, a->K, a->K, bn);
+  if (rc != B2T_OK) return rc;
+  if (bn == 256) return dispatch_epi<256>(ma, mw, a, p, st);
+  return dispatch_epi<128>(ma, mw, a, p, st);
+}

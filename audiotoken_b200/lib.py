@@ -1,0 +1,121 @@
+"""ctypes binding of libb200tok.so (include/b200tok.h).
+
+There is deliberately no fallback: if the library is missing or the device is not sm_100,
+every entry point raises.  PyTorch is used only to own device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libb200tok.so')
+
+PREC_BF16, PREC_FP32 = 0, 1
+EPI_BIAS, EPI_BIAS_SWISH, EPI_RESID, EPI_GLU, EPI_BIAS_MASK = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR = 0, 1, 2
+
+EXPORTS = [
+    'b2t_version', 'b2t_last_error', 'b2t_device_check', 'b2t_fbank_logmel', 'b2t_fbank_stats',
+    'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_dwconv_ln_swish',
+    'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_semantic_create', 'b2t_semantic_destroy',
+    'b2t_semantic_set_tensor', 'b2t_semantic_workspace_bytes', 'b2t_semantic_encode',
+    'b2t_last_launch_count',
+]
+
+
+class B2TError(RuntimeError):
+    pass
+
+
+class Batch(C.Structure):
+    """b2t_batch"""
+    _fields_ = [('n_clips', C.c_int32), ('total_frames', C.c_int32), ('total_rows', C.c_int32),
+                ('n_qtiles', C.c_int32), ('n_ctiles', C.c_int32), ('max_rows', C.c_int32),
+                ('wave_off', C.c_void_p), ('frame_off', C.c_void_p), ('stack_frames', C.c_void_p),
+                ('row_off', C.c_void_p), ('valid_rows', C.c_void_p), ('qtile_clip', C.c_void_p),
+                ('qtile_q0', C.c_void_p), ('ctile_clip', C.c_void_p), ('ctile_t0', C.c_void_p)]
+
+
+class FbankTables(C.Structure):
+    """b2t_fbank_tables"""
+    _fields_ = [('window', C.c_void_p), ('mel_start', C.c_void_p), ('mel_count', C.c_void_p),
+                ('mel_weight', C.c_void_p)]
+
+
+class GemmArgs(C.Structure):
+    """b2t_gemm_args"""
+    _fields_ = [('A', C.c_void_p), ('lda', C.c_int32), ('W', C.c_void_p), ('bias', C.c_void_p),
+                ('out', C.c_void_p), ('ldo', C.c_int32), ('resid', C.c_void_p), ('row_valid', C.c_void_p),
+                ('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32), ('epilogue', C.c_int32),
+                ('alpha', C.c_float), ('round_resid_bf16', C.c_int32), ('precision', C.c_int32),
+                ('impl', C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed for loading / symbol checks)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B2TError(f'{LIB_PATH} not found: build it with `python -m audiotoken_b200.build` '
+                       '(there is no CPU fallback)')
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.b2t_version.restype = i32
+    lib.b2t_last_error.restype = C.c_char_p
+    lib.b2t_device_check.argtypes = [i32]
+    lib.b2t_fbank_logmel.argtypes = [vp, C.POINTER(Batch), C.POINTER(FbankTables), vp, i32, vp]
+    lib.b2t_fbank_stats.argtypes = [vp, C.POINTER(Batch), vp, vp, vp]
+    lib.b2t_fbank_stack_ln.argtypes = [vp, vp, vp, C.POINTER(Batch), vp, vp, vp, vp, vp, i32, vp]
+    lib.b2t_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.b2t_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+    lib.b2t_relkey_attention.argtypes = [vp, vp, C.POINTER(Batch), vp, i32, i32, vp]
+    lib.b2t_dwconv_ln_swish.argtypes = [vp, vp, vp, vp, C.POINTER(Batch), vp, i32, vp]
+    lib.b2t_vq_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.b2t_vq_workspace_bytes.restype = sz
+    lib.b2t_vq_argmin.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, sz, vp]
+    lib.b2t_semantic_create.argtypes = [i32, i32, i32]
+    lib.b2t_semantic_create.restype = vp
+    lib.b2t_semantic_destroy.argtypes = [vp]
+    lib.b2t_semantic_destroy.restype = None
+    lib.b2t_semantic_set_tensor.argtypes = [vp, C.c_char_p, vp]
+    lib.b2t_semantic_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.b2t_semantic_workspace_bytes.restype = sz
+    lib.b2t_semantic_encode.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(FbankTables), vp, sz, vp, i32, vp, vp]
+    lib.b2t_last_launch_count.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = '') -> None:
+    if rc != 0:
+        msg = load().b2t_last_error().decode('utf-8', 'replace')
+        raise B2TError(f'{what} failed (status {rc}): {msg}')
+
+
+def require_device(device: torch.device) -> None:
+    """Fail loudly unless `device` is a CUDA sm_100 device."""
+    if device.type != 'cuda' or not torch.cuda.is_available():
+        raise B2TError(f"device '{device}' is not a CUDA device: b200tok has no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    check(load().b2t_device_check(idx), 'b2t_device_check')
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def np_to_dev(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)

@@ -1,0 +1,185 @@
+/*
+ * b200tok.h — C ABI of the B200-native waveform->token encode path.
+ *
+ * Drop-in boundary.  The reference (cmeraki/audiotoken) is pure Python; the operator it calls
+ * on the hot path is `self.encoder(input_batch, attention_mask) -> int16 [B, K, T]`
+ * (audiotoken/core.py:194 and :276).  Everything below that call is replaced by this library;
+ * the Python classes in audiotoken_b200/encoder.py mirror the reference's encoder modules
+ * (audiotoken/encoder.py:29-57 AcousticEncoder, :111-186 Wav2VecBertEncoder) and bind these
+ * entry points with ctypes (INTEGRATION.md shows the stub a maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - no allocation inside: the caller owns inputs, outputs and the workspace
+ *     (query with the *_workspace_bytes functions);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *   - return value: 0 = ok, negative = b2t_status; b2t_last_error() gives a thread-local text;
+ *   - sm_100a only.  On any other device the entry points return B2T_ERR_ARCH — there is no
+ *     CPU fallback by design.
+ *
+ * Packed ("ragged") batch layout.  The reference pads every clip of a batch to chunk_size
+ * seconds (audiotoken/datasets.py:99-103).  Here a batch is a list of clips, each with its own
+ * number of samples, log-mel frames and token rows; rows of all clips are concatenated into
+ * [total_rows, C] matrices.  SURVEY.md A.6 argues (and tests/ check) that this is exact.
+ */
+#ifndef B200TOK_H
+#define B200TOK_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B2T_OK = 0,
+  B2T_ERR_ARG = -1,        /* bad argument (null pointer, bad shape, misalignment) */
+  B2T_ERR_ARCH = -2,       /* device is not sm_100 */
+  B2T_ERR_CUDA = -3,       /* a CUDA runtime/driver call failed */
+  B2T_ERR_WORKSPACE = -4,  /* workspace too small */
+  B2T_ERR_STATE = -5       /* model not fully populated */
+} b2t_status;
+
+typedef enum { B2T_PREC_BF16 = 0, B2T_PREC_FP32 = 1 } b2t_precision;
+
+/* GEMM epilogues (all compute out = A[M,K] . W[N,K]^T with fp32 accumulation).
+ * "r16(x)" = x rounded to bf16 in B2T_PREC_BF16, identity in B2T_PREC_FP32 — the rounding that
+ * torch.amp.autocast applies to a Linear/conv output (reference encoder.py:164). */
+typedef enum {
+  B2T_EPI_BIAS = 0,        /* out = r16(acc + bias)                                  */
+  B2T_EPI_BIAS_SWISH = 1,  /* h = r16(acc + bias); out = r16(h * sigmoid(h))         */
+  B2T_EPI_RESID = 2,       /* resid = [r16](resid + alpha * r16(acc + bias)) (fp32 stream) */
+  B2T_EPI_GLU = 3,         /* W rows interleaved (a0,g0,a1,g1,..): out[:, j] = r16(r16(a_j) * sigmoid(r16(g_j))) */
+  B2T_EPI_BIAS_MASK = 4    /* out = row_valid ? r16(acc + bias) : 0, written to the fp32 stream */
+} b2t_epilogue;
+
+typedef enum { B2T_IMPL_AUTO = 0, B2T_IMPL_SIMT = 1, B2T_IMPL_TENSOR = 2 } b2t_impl;
+
+/* ---- library --------------------------------------------------------------------------- */
+int b2t_version(void);
+const char* b2t_last_error(void);
+/* B2T_OK iff `device` is compute capability 10.x. */
+int b2t_device_check(int device);
+
+/* ---- batch descriptor (all arrays on the device, built by the host packer) --------------- */
+typedef struct {
+  int32_t n_clips;
+  int32_t total_frames;        /* sum of valid log-mel frames                                */
+  int32_t total_rows;          /* M: sum over clips of token rows computed                   */
+  int32_t n_qtiles;            /* attention work items (64 query rows each)                  */
+  int32_t n_ctiles;            /* depthwise-conv work items (16 rows each)                   */
+  int32_t max_rows;            /* longest clip, in rows                                      */
+  const int64_t* wave_off;     /* [n_clips]   first sample of clip i in `wave`               */
+  const int32_t* frame_off;    /* [n_clips+1] prefix sum of valid frames (1+floor((len-400)/160)) */
+  const int32_t* stack_frames; /* [n_clips]   frames that enter stride-2 stacking (<= valid) */
+  const int32_t* row_off;      /* [n_clips+1] prefix sum of token rows                       */
+  const int32_t* valid_rows;   /* [n_clips]   rows whose attention_mask is 1 (= ceil(stack_frames/2)) */
+  const int32_t* qtile_clip;   /* [n_qtiles]                                                 */
+  const int32_t* qtile_q0;     /* [n_qtiles]  first query row (within the clip)              */
+  const int32_t* ctile_clip;   /* [n_ctiles]                                                 */
+  const int32_t* ctile_t0;     /* [n_ctiles]                                                 */
+} b2t_batch;
+
+/* ---- front end: reference audiotoken/processors.py ------------------------------------------ */
+typedef struct {
+  const float* window;         /* [400]  hann(400, sym)^0.85          (processors.py:75)      */
+  const int32_t* mel_start;    /* [80]   first FFT bin of filter f                            */
+  const int32_t* mel_count;    /* [80]   number of bins (<= 32)                               */
+  const float* mel_weight;     /* [80*32] triangle weights            (processors.py:8-26)    */
+} b2t_fbank_tables;
+
+/* processors.py:137-190 (_create_spectrogram): x*2^15, per frame DC removal, pre-emphasis 0.97,
+ * window, 512-point real FFT, power, mel projection, floor, ln.  One log-mel row per VALID frame.
+ * mel_bf16 != 0 reproduces the bf16 autocast of the mel matmul (processors.py:184).           */
+int b2t_fbank_logmel(const float* wave, const b2t_batch* batch, const b2t_fbank_tables* tables,
+                     float* logmel /* [total_frames, 80] */, int mel_bf16, void* stream);
+
+/* processors.py:117-135: per clip and mel bin, mean and biased variance over valid frames.
+ * Writes mean[n_clips*80] and std[n_clips*80] = sqrt(var + 1e-7)  (processors.py:242).        */
+int b2t_fbank_stats(const float* logmel, const b2t_batch* batch, float* mean, float* std_,
+                    void* stream);
+
+/* processors.py:242-259, 192-207 + HF Wav2Vec2BertFeatureProjection.layer_norm:
+ * normalise, stack frame pairs to 160-d rows, 1.0 at invalid elements / pad rows, then
+ * LayerNorm(160).  `features` (optional) receives the pre-LayerNorm input_features, `out` the
+ * LayerNormed rows (bf16 or fp32 per `precision`), `row_valid` the attention_mask.            */
+int b2t_fbank_stack_ln(const float* logmel, const float* mean, const float* std_,
+                       const b2t_batch* batch, const float* ln_weight, const float* ln_bias,
+                       void* out, float* features, uint8_t* row_valid, int precision,
+                       void* stream);
+
+/* ---- conformer building blocks (HF modeling_wav2vec2_bert.py:118-225, 397-460) ------------- */
+
+/* out[r,:] = LayerNorm(x[r,:]) over `cols` (1024 or 160), eps 1e-5; weight/bias may be NULL
+ * (affine-free, reference encoder.py:138-144).  If row_valid != NULL rows with 0 are written as
+ * zeros (conv module, modeling_wav2vec2_bert.py:200-201).  out is bf16 or fp32.               */
+int b2t_layernorm(const float* x, const float* weight, const float* bias,
+                  const uint8_t* row_valid, void* out, int rows, int cols, int out_precision,
+                  void* stream);
+
+typedef struct {
+  const void* A; int32_t lda;        /* [M, K] row-major, bf16 (BF16) or fp32 (FP32)           */
+  const void* W;                     /* [N, K] row-major (torch Linear layout), same type      */
+  const float* bias;                 /* [N] or NULL                                            */
+  void* out; int32_t ldo;            /* see b2t_epilogue                                        */
+  float* resid;                      /* B2T_EPI_RESID / BIAS_MASK: fp32 [M, N] stream           */
+  const uint8_t* row_valid;          /* B2T_EPI_BIAS_MASK                                       */
+  int32_t M, N, K;
+  int32_t epilogue;                  /* b2t_epilogue                                            */
+  float alpha;                       /* B2T_EPI_RESID scale (0.5 for the half-step FFNs)        */
+  int32_t round_resid_bf16;          /* layer 0 of the autocast path keeps a bf16 stream        */
+  int32_t precision;                 /* b2t_precision                                           */
+  int32_t impl;                      /* b2t_impl; AUTO = tcgen05 for BF16, SIMT for FP32        */
+} b2t_gemm_args;
+
+/* Dense contraction with fused epilogue.  BF16 + TENSOR runs the tcgen05/TMEM/TMA kernel.      */
+int b2t_gemm(const b2t_gemm_args* args, void* stream);
+
+/* reference audiotoken/modeling_wav2vec2_bert.py:37-77: softmax(q k^T / 8 + q E[clamp(j-i,-64,8)+64] / 8
+ * + key padding) v.  qkv is [M, 3072] = q | k | v (16 heads x 64 each), dist_emb [73, 64],
+ * out [M, 1024].  Keys >= valid_rows[clip] are masked; every row (incl. pad rows) is a query. */
+int b2t_relkey_attention(const void* qkv, const void* dist_emb, const b2t_batch* batch,
+                         void* out, int precision, int impl, void* stream);
+
+/* HF Wav2Vec2BertConvolutionModule (:213-221): causal depthwise conv k=31 (left pad 30, per
+ * clip) -> LayerNorm(1024) -> swish.  x, out: [M, 1024] bf16/fp32; w_dw [1024, 31] fp32.       */
+int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float* ln_weight,
+                        const float* ln_bias, const b2t_batch* batch, void* out, int precision,
+                        void* stream);
+
+/* ---- quantisers ----------------------------------------------------------------------------- */
+
+/* Nearest centroid (reference encoder.py:100-101 k-means, :180 VectorQuantize):
+ * idx[r] = argmin_k |x_r - c_k|^2, first index on ties, written as int16.  If apply_ln != 0 the
+ * affine-free LayerNorm of encoder.py:175-176 is applied to each row first.  Candidates from
+ * the fast pass are re-checked in fp64, so the result equals the exact fp64 argmin.           */
+size_t b2t_vq_workspace_bytes(int rows, int dim, int codebook_size);
+int b2t_vq_argmin(const float* x, int ldx, int rows, int dim, const float* codebook,
+                  const float* half_norm /* [K] 0.5*|c_k|^2 fp32, or NULL */, int codebook_size,
+                  int apply_ln, int16_t* out, int32_t* out_i32 /* optional */, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---- whole semantic encoder (reference Wav2VecBertEncoder.forward, encoder.py:163-186) ------- */
+typedef struct b2t_semantic_model b2t_semantic_model;
+
+b2t_semantic_model* b2t_semantic_create(int n_layers, int codebook_size, int precision);
+void b2t_semantic_destroy(b2t_semantic_model* m);
+/* Names: HF state-dict names ("encoder.layers.3.ffn1.intermediate_dense.weight", ...) plus
+ * "codebook" [K, 1024] fp32, and fused/preprocessed tensors documented in pipeline.cu.  The
+ * library keeps the pointer, not a copy: the caller keeps the device buffer alive.            */
+int b2t_semantic_set_tensor(b2t_semantic_model* m, const char* name, const void* ptr);
+size_t b2t_semantic_workspace_bytes(const b2t_semantic_model* m, int total_rows, int total_frames,
+                                    int n_clips);
+/* wave -> tokens int16 [total_rows] (one codebook).  `tap_layer` >= 0 copies hidden_states[tap_layer]
+ * (fp32 [M,1024]) to `tap_out` for parity tests; pass -1 / NULL otherwise.                      */
+int b2t_semantic_encode(const b2t_semantic_model* m, const float* wave, const b2t_batch* batch,
+                        const b2t_fbank_tables* tables, void* workspace, size_t workspace_bytes,
+                        int16_t* tokens, int tap_layer, float* tap_out, void* stream);
+/* number of kernels the last b2t_semantic_encode on this thread launched */
+int b2t_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TOK_H */

@@ -1,0 +1,296 @@
+"""GPU (-m gpu): every kernel class through the C ABI against the CPU oracle / a plain fp32 torch
+reference of the same op.  Tolerances: fp32 mode 1e-4 relative (north star), bf16 mode 1e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audiotoken_b200 import lib as L
+from audiotoken_b200 import ops, packing
+from audiotoken_b200.weights import synthetic_codebook, synthetic_w2vbert_state_dict, synthetic_waveform
+from oracle import conformer, fbank, quantize
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+# ------------------------------------------------------------------------------------------- fbank
+def _golden_clips(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'fbank.npz'))
+    lengths = [int(v) for v in g['lengths']]
+    total = int(g['total'])
+    return g, lengths, total
+
+
+def test_fbank_matches_reference_golden(cuda_device, golden_dir):
+    g, lengths, total = _golden_clips(golden_dir)
+    B = len(lengths)
+    wave = torch.zeros(B, total)
+    for i, n in enumerate(lengths):
+        wave[i, :n] = synthetic_waveform(i, n, 16000)
+    plan = packing.plan_semantic(lengths, np.arange(B) * total, total)
+    sd = synthetic_w2vbert_state_dict(0, seed=0)
+    lw, lb = sd['feature_projection.layer_norm.weight'].to(cuda_device), sd['feature_projection.layer_norm.bias'].to(cuda_device)
+    logmel, feats, ln_out, valid = ops.fbank_features(wave.to(cuda_device).view(-1), plan, lw, lb, 'fp32')
+    T = plan.total_rows // B
+    ref = torch.from_numpy(g['input_features'])
+    got = feats.view(B, T, 160).cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) < 2e-4, float((got - ref).abs().max())
+    assert np.array_equal(valid.view(B, T).cpu().numpy().astype(np.float32), g['attention_mask'])
+    ln_ref = torch.nn.functional.layer_norm(ref, (160,), lw.cpu(), lb.cpu(), 1e-5)
+    assert float((ln_out.view(B, T, 160).cpu() - ln_ref).abs().max()) < 5e-4
+
+
+def test_fbank_packed_equals_padded_and_bf16_mel(cuda_device):
+    # ragged clips packed back to back == the same clips in a padded batch (batch-composition invariance)
+    lengths = [16000, 9999, 3200, 12345]
+    clips = [synthetic_waveform(10 + i, n, 16000) for i, n in enumerate(lengths)]
+    total = 16000
+    padded = torch.zeros(len(lengths), total)
+    for i, c in enumerate(clips):
+        padded[i, :c.numel()] = c
+    sd = synthetic_w2vbert_state_dict(0, seed=0)
+    lw, lb = sd['feature_projection.layer_norm.weight'].to(cuda_device), sd['feature_projection.layer_norm.bias'].to(cuda_device)
+    plan_a = packing.plan_semantic(lengths, np.arange(len(lengths)) * total, total)
+    offs = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+    plan_b = packing.plan_semantic(lengths, offs, total)
+    fa = ops.fbank_features(padded.to(cuda_device).view(-1), plan_a, lw, lb, 'fp32')
+    fb = ops.fbank_features(torch.cat(clips).to(cuda_device), plan_b, lw, lb, 'fp32')
+    for a, b in zip(fa, fb):
+        assert torch.equal(a, b)
+    # oracle with the autocast cast point of the mel matmul (processors.py:184)
+    mask = torch.zeros(len(lengths), total)
+    for i, n in enumerate(lengths):
+        mask[i, :n] = 1
+    ref, _ = fbank.features(padded, mask, mel_in_bf16=True)
+    got = ops.fbank_features(padded.to(cuda_device).view(-1), plan_a, lw, lb, 'fp32', mel_bf16=True)[1]
+    d = (got.view(ref.shape).cpu() - ref).abs()
+    # bf16 rounding of the mel energies can flip one ulp (2^-8 relative => ~4e-3 in ln) on a few bins
+    assert float(d.mean()) < 2e-3 and float((d > 0.05).float().mean()) < 1e-3
+
+
+# --------------------------------------------------------------------------------------- layernorm
+@pytest.mark.parametrize('rows', [1, 37, 1000])
+def test_layernorm(cuda_device, rows):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, 1024, generator=g) * 3 + 0.5
+    w, b = torch.randn(1024, generator=g), torch.randn(1024, generator=g)
+    ref = torch.nn.functional.layer_norm(x, (1024,), w, b, 1e-5)
+    xd, wd, bd = x.to(cuda_device), w.to(cuda_device), b.to(cuda_device)
+    out = ops.layernorm(xd, wd, bd)
+    assert float((out.cpu() - ref).abs().max()) < 2e-5
+    out16 = ops.layernorm(xd, wd, bd, out_precision='bf16')
+    assert torch.equal(out16.cpu(), out.cpu().to(torch.bfloat16)) or rel_err(out16.float(), ref) < 4e-3
+    valid = (torch.arange(rows) % 3 != 0).to(torch.uint8).to(cuda_device)
+    outz = ops.layernorm(xd, wd, bd, row_valid=valid)
+    assert float(outz.cpu()[0::3].abs().max()) == 0.0
+    noaff = ops.layernorm(xd, None, None)
+    assert float((noaff.cpu() - torch.nn.functional.layer_norm(x, (1024,))).abs().max()) < 2e-5
+
+
+# -------------------------------------------------------------------------------------------- GEMM
+def _gemm_ref(A, W, bias, epi, alpha=1.0, resid=None, valid=None, bf16=False, round_resid=False):
+    r = bf if bf16 else (lambda t: t)
+    acc = A.double() @ W.double().t()
+    v = r((acc + (bias.double() if bias is not None else 0)).float())
+    if epi == L.EPI_BIAS:
+        return v
+    if epi == L.EPI_BIAS_SWISH:
+        return r(v * torch.sigmoid(v))
+    if epi == L.EPI_RESID:
+        out = resid + alpha * v
+        return r(out) if round_resid else out
+    if epi == L.EPI_GLU:
+        return r(v[:, 0::2] * torch.sigmoid(v[:, 1::2]))
+    if epi == L.EPI_BIAS_MASK:
+        return v * valid.float().unsqueeze(1)
+    raise ValueError
+
+
+GEMM_CASES = [(130, 1024, 160, L.EPI_BIAS_MASK), (257, 4096, 1024, L.EPI_BIAS_SWISH), (64, 1024, 4096, L.EPI_RESID),
+              (300, 3072, 1024, L.EPI_BIAS), (129, 2048, 1024, L.EPI_GLU), (1, 1024, 1024, L.EPI_RESID)]
+
+
+@pytest.mark.parametrize('M,N,K,epi', GEMM_CASES)
+def test_gemm_simt_fp32(cuda_device, M, N, K, epi):
+    g = torch.Generator().manual_seed(M * 7 + epi)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias = None if epi == L.EPI_GLU else torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g)
+    valid = (torch.arange(M) % 4 != 1).to(torch.uint8)
+    ref = _gemm_ref(A, W, bias, epi, 0.5, resid, valid)
+    out = ops.gemm(A.to(cuda_device), W.to(cuda_device), None if bias is None else bias.to(cuda_device), epi, 'fp32',
+                   L.IMPL_SIMT, resid=resid.clone().to(cuda_device), row_valid=valid.to(cuda_device), alpha=0.5)
+    assert rel_err(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize('impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
+@pytest.mark.parametrize('M,N,K,epi', GEMM_CASES + [(5000, 4096, 1024, L.EPI_BIAS_SWISH), (4099, 1024, 4096, L.EPI_RESID)])
+def test_gemm_bf16(cuda_device, impl, M, N, K, epi):
+    g = torch.Generator().manual_seed(M * 11 + epi)
+    A, W = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.05)
+    bias = None if epi == L.EPI_GLU else bf(torch.randn(N, generator=g))
+    resid = torch.randn(M, N, generator=g)
+    valid = (torch.arange(M) % 4 != 1).to(torch.uint8)
+    ref = _gemm_ref(A, W, bias, epi, 0.5, resid, valid, bf16=True, round_resid=True)
+    out = ops.gemm(A.to(cuda_device, torch.bfloat16), W.to(cuda_device, torch.bfloat16),
+                   None if bias is None else bias.to(cuda_device), epi, 'bf16', impl,
+                   resid=resid.clone().to(cuda_device), row_valid=valid.to(cuda_device), alpha=0.5, round_resid=True)
+    torch.cuda.synchronize()
+    out = out.float().cpu()
+    # identical bf16 inputs, fp32 accumulation: only summation order differs -> at most 1 bf16 ulp on a few elements
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+    assert float(((out - ref).abs() > 0.02 * ref.abs() + 1e-2).float().mean()) < 1e-4
+
+
+def test_gemm_tensor_equals_simt_bitwise_mostly(cuda_device):
+    g = torch.Generator().manual_seed(99)
+    M, N, K = 1000, 1024, 1024
+    A = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.03).to(cuda_device, torch.bfloat16)
+    bias = bf(torch.randn(N, generator=g)).to(cuda_device)
+    o1 = ops.gemm(A, W, bias, L.EPI_BIAS, 'bf16', L.IMPL_SIMT).float()
+    o2 = ops.gemm(A, W, bias, L.EPI_BIAS, 'bf16', L.IMPL_TENSOR).float()
+    torch.cuda.synchronize()
+    assert float((o1 != o2).float().mean()) < 0.02          # rare 1-ulp flips from summation order
+    assert rel_err(o2, o1) < 1e-3
+
+
+# --------------------------------------------------------------------------------------- attention
+def _attn_case(seed, lengths_rows, valid_rows):
+    """Build a packed qkv and the per-clip oracle output."""
+    g = torch.Generator().manual_seed(seed)
+    M = sum(lengths_rows)
+    qkv = torch.randn(M, 3072, generator=g) * 0.7
+    E = torch.randn(73, 64, generator=g)
+    return qkv, E
+
+
+def _attn_oracle(qkv, E, rows, valid, emu):
+    """oracle.conformer.rel_key_attention without the projections (identity weights trick is too
+    large), restated on the q/k/v tensors directly with the same formula."""
+    outs = []
+    off = 0
+    for T, tv in zip(rows, valid):
+        blk = qkv[off:off + T]
+        q, k, v = (blk[:, i * 1024:(i + 1) * 1024].view(T, 16, 64).transpose(0, 1) for i in range(3))
+        pos = torch.arange(T)
+        dist = (pos.view(1, -1) - pos.view(-1, 1)).clamp(-64, 8) + 64
+        r = torch.einsum('hld,rd->hlr', q, E)
+        if emu:
+            r = bf(r)
+        bias = torch.gather(r, 2, dist.view(1, T, T).expand(16, T, T)) / 8.0
+        s = torch.einsum('hld,hrd->hlr', q, k) / 8.0 + bias
+        s[:, :, tv:] = float('-inf')
+        p = torch.softmax(s, dim=-1)
+        if emu:
+            p = bf(p)
+        o = torch.einsum('hlr,hrd->hld', p, v)
+        outs.append(o.transpose(0, 1).reshape(T, 1024))
+        off += T
+    return torch.cat(outs, 0)
+
+
+def _attn_plan(rows, valid):
+    # lengths chosen so that plan_semantic reproduces (rows, valid_rows): len = 400 + 160*(2*valid-1)
+    lengths = [400 + 160 * (2 * v - 1) for v in valid]
+    pad = [400 + 160 * (2 * r - 1) for r in rows]
+    offs = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+    plan = packing.plan_semantic(lengths, offs, pad, rows=rows)
+    assert plan.valid_rows.tolist() == list(valid) and plan.rows.tolist() == list(rows)
+    return plan
+
+
+ATTN_CASES = [([50], [50]), ([200, 64, 130], [199, 20, 130]), ([500, 75], [499, 74]), ([1, 2, 3], [1, 1, 2])]
+
+
+@pytest.mark.parametrize('rows,valid', ATTN_CASES)
+def test_attention_simt_fp32(cuda_device, rows, valid):
+    qkv, E = _attn_case(len(rows), rows, valid)
+    plan = _attn_plan(rows, valid)
+    ref = _attn_oracle(qkv, E, rows, valid, False)
+    out = ops.relkey_attention(qkv.to(cuda_device), E.to(cuda_device), plan, 'fp32', L.IMPL_SIMT)
+    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
+
+
+@pytest.mark.parametrize('impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
+@pytest.mark.parametrize('rows,valid', ATTN_CASES)
+def test_attention_bf16(cuda_device, impl, rows, valid):
+    qkv, E = _attn_case(10 + len(rows), rows, valid)
+    qkv, E = bf(qkv), bf(E)
+    plan = _attn_plan(rows, valid)
+    ref = bf(_attn_oracle(qkv, E, rows, valid, True))
+    out = ops.relkey_attention(qkv.to(cuda_device, torch.bfloat16), E.to(cuda_device, torch.bfloat16), plan, 'bf16', impl)
+    assert rel_err(out.float(), ref) < 1e-2, rel_err(out.float(), ref)
+
+
+# ---------------------------------------------------------------------------------- depthwise conv
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_dwconv_ln_swish(cuda_device, precision):
+    rows, valid = [70, 16, 33, 1], [70, 10, 33, 1]
+    plan = _attn_plan(rows, valid)
+    g = torch.Generator().manual_seed(7)
+    M = sum(rows)
+    x = torch.randn(M, 1024, generator=g)
+    wd = torch.randn(1024, 31, generator=g) * 0.25
+    lw, lb = torch.randn(1024, generator=g) * 0.1 + 1, torch.randn(1024, generator=g) * 0.1
+    emu = precision == 'bf16'
+    if emu:
+        x = bf(x)
+    outs, off = [], 0
+    for T in rows:
+        h = x[off:off + T].t().unsqueeze(0)
+        hp = torch.nn.functional.pad(h, (30, 0))
+        c = torch.nn.functional.conv1d(hp, (bf(wd) if emu else wd).unsqueeze(1), groups=1024)[0].t()
+        if emu:
+            c = bf(c)
+        y = torch.nn.functional.layer_norm(c, (1024,), lw, lb, 1e-5)
+        outs.append(y * torch.sigmoid(y))
+        off += T
+    ref = torch.cat(outs, 0)
+    act = torch.bfloat16 if emu else torch.float32
+    out = ops.dwconv_ln_swish(x.to(cuda_device, act), wd.to(cuda_device), lw.to(cuda_device), lb.to(cuda_device), plan, precision)
+    assert rel_err(out.float(), bf(ref) if emu else ref) < (1e-2 if emu else 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------- VQ
+@pytest.mark.parametrize('M,D,K', [(1000, 1024, 2048), (777, 1024, 1000), (300, 128, 1024), (64, 256, 1), (50, 64, 3)])
+def test_vq_argmin_bit_exact(cuda_device, M, D, K):
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, D, generator=g)
+    cb = torch.randn(K, D, generator=g)
+    if K >= 1000:
+        cb[K - 5:] = cb[:5]                                  # duplicated centroids: first index must win
+        x[:5] = cb[:5] + 1e-3 * torch.randn(5, D, generator=g)
+    idx, tie = quantize.nearest_centroid(x, cb)
+    o16, o32 = ops.vq_argmin(x.to(cuda_device), cb.to(cuda_device))
+    torch.cuda.synchronize()
+    assert torch.equal(o32.cpu().long()[~tie], idx[~tie])
+    assert torch.equal(o16.cpu().long(), o32.cpu().long())
+
+
+def test_vq_argmin_near_ties_and_layernorm(cuda_device):
+    # rows placed (almost) on the bisector of two centroids: the fp64 re-check has to decide
+    g = torch.Generator().manual_seed(5)
+    cb = torch.randn(2048, 1024, generator=g)
+    a, b = cb[torch.randint(0, 2048, (400,), generator=g)], cb[torch.randint(0, 2048, (400,), generator=g)]
+    x = 0.5 * (a + b) + 1e-6 * torch.randn(400, 1024, generator=g)
+    idx, tie = quantize.nearest_centroid(x, cb, tie_rel_margin=1e-12)
+    _, o32 = ops.vq_argmin(x.to(cuda_device), cb.to(cuda_device))
+    assert torch.equal(o32.cpu().long()[~tie], idx[~tie])
+    # fused affine-free LayerNorm (reference encoder.py:175-176)
+    h = torch.randn(500, 1024, generator=g) * 2 + 1
+    emb = conformer.final_embedding(h)
+    idx2, tie2 = quantize.nearest_centroid(emb, cb)
+    _, o = ops.vq_argmin(h.to(cuda_device), cb.to(cuda_device), apply_ln=True)
+    assert (o.cpu().long()[~tie2] == idx2[~tie2]).float().mean() > 0.995

@@ -1,0 +1,139 @@
+"""GPU (-m gpu): the whole semantic encoder through the C ABI against the reference goldens and the
+oracle.  Stated tolerances (BASELINE.json north star): embeddings within 1e-4 relative in fp32 and
+1e-2 in bf16; token agreement >= 99.5 %; the argmin itself bit-exact (test_gpu_kernels.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audiotoken_b200 import lib as L
+from audiotoken_b200 import packing
+from audiotoken_b200.encoder import Wav2VecBertEncoder
+from audiotoken_b200.weights import synthetic_codebook, synthetic_w2vbert_state_dict, synthetic_waveform
+from oracle import conformer, fbank, quantize
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def golden_batch(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'fbank.npz'))
+    lengths = [int(v) for v in g['lengths']]
+    total = int(g['total'])
+    wave = torch.zeros(len(lengths), total)
+    mask = torch.zeros(len(lengths), total)
+    for i, n in enumerate(lengths):
+        wave[i, :n] = synthetic_waveform(i, n, 16000)
+        mask[i, :n] = 1
+    return g, wave, mask, lengths
+
+
+@pytest.mark.parametrize('n_layers,tag,tol', [(2, 'l2', 1e-4), (19, 'l19', 1e-4)])
+def test_fp32_pipeline_matches_reference_golden(cuda_device, golden_dir, n_layers, tag, tol):
+    g, wave, mask, lengths = golden_batch(golden_dir)
+    c = np.load(os.path.join(golden_dir, f'conformer_{tag}.npz'))
+    enc = Wav2VecBertEncoder(device='cuda:0', precision='fp32', n_layers=n_layers,
+                             state_dict=synthetic_w2vbert_state_dict(n_layers, 0),
+                             codebook=synthetic_codebook(2048, 1024, 4))
+    toks, hid = enc(wave.to(cuda_device), mask.to(cuda_device), tap_layer=n_layers)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(c['hidden_last'])
+    assert toks.shape == (4, 1, 50) and toks.dtype == torch.int16
+    err = rel_err(hid, ref)
+    assert err < tol, err
+    agree = float((toks[:, 0].cpu().numpy() == c['tokens']).mean())
+    assert agree >= 0.995, agree
+    if n_layers == 2:
+        _, h0 = enc(wave.to(cuda_device), mask.to(cuda_device), tap_layer=0)
+        assert rel_err(h0, torch.from_numpy(c['hidden_0'])) < 1e-5
+        _, h1 = enc(wave.to(cuda_device), mask.to(cuda_device), tap_layer=1)
+        assert rel_err(h1, torch.from_numpy(c['hidden_1'])) < 1e-5
+
+
+@pytest.mark.parametrize('gemm_impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
+@pytest.mark.parametrize('attn_impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
+def test_bf16_pipeline_matches_autocast_oracle(cuda_device, golden_dir, gemm_impl, attn_impl):
+    g, wave, mask, lengths = golden_batch(golden_dir)
+    n_layers = 2
+    sd = synthetic_w2vbert_state_dict(n_layers, 0)
+    cb = synthetic_codebook(2048, 1024, 4)
+    enc = Wav2VecBertEncoder(device='cuda:0', precision='bf16', n_layers=n_layers, state_dict=sd, codebook=cb)
+    enc.set_option('gemm_impl', gemm_impl)
+    enc.set_option('attn_impl', attn_impl)
+    toks, hid = enc(wave.to(cuda_device), mask.to(cuda_device), tap_layer=n_layers)
+    torch.cuda.synchronize()
+    feats, am = fbank.features(wave, mask, mel_in_bf16=True)
+    hs = conformer.hidden_states(feats, am, sd, n_layers, emulate_bf16=True)
+    err = rel_err(hid.view(hs[n_layers].shape), hs[n_layers])
+    assert err < 1e-2, err
+    idx, _ = quantize.nearest_centroid(conformer.final_embedding(hs[n_layers]).reshape(-1, 1024), cb)
+    agree = float((toks[:, 0].cpu().reshape(-1).long() == idx).float().mean())
+    assert agree >= 0.97, agree       # 200 tokens, bf16 noise floor of two correct implementations
+    # and against the fp32 reference golden: the bf16 path stays within the autocast noise
+    c = np.load(os.path.join(golden_dir, 'conformer_l2.npz'))
+    assert rel_err(hid.view(4, 50, 1024), torch.from_numpy(c['hidden_last'])) < 3e-2
+
+
+def test_bf16_pipeline_19_layers_report(cuda_device, golden_dir):
+    g, wave, mask, lengths = golden_batch(golden_dir)
+    sd = synthetic_w2vbert_state_dict(19, 0)
+    cb = synthetic_codebook(2048, 1024, 4)
+    enc = Wav2VecBertEncoder(device='cuda:0', precision='bf16', n_layers=19, state_dict=sd, codebook=cb)
+    toks, hid = enc(wave.to(cuda_device), mask.to(cuda_device), tap_layer=19)
+    torch.cuda.synchronize()
+    feats, am = fbank.features(wave, mask, mel_in_bf16=True)
+    hs = conformer.hidden_states(feats, am, sd, 19, emulate_bf16=True)
+    c = np.load(os.path.join(golden_dir, 'conformer_l19.npz'))
+    e_emu = rel_err(hid.view(hs[19].shape), hs[19])
+    e_ref = rel_err(hid.view(4, 50, 1024), torch.from_numpy(c['hidden_last']))
+    e_floor = rel_err(hs[19], torch.from_numpy(c['hidden_last']))
+    print(f'bf16 19 layers: vs autocast oracle {e_emu:.4f}, vs fp32 reference {e_ref:.4f}, '
+          f'autocast oracle vs fp32 reference (noise floor) {e_floor:.4f}')
+    # random-init weights amplify bf16 rounding (3.3 % between autocast and fp32);
+    # the CUDA path must sit at that floor, not above it
+    assert e_ref < 2.0 * e_floor + 1e-2
+    assert torch.isfinite(hid).all()
+
+
+def test_packed_equals_padded_tokens(cuda_device):
+    """A clip's tokens do not depend on its batch mates or on how much padding follows."""
+    lengths = [48000, 20000, 7777, 3200, 31111]
+    clips = [synthetic_waveform(50 + i, n, 16000) for i, n in enumerate(lengths)]
+    enc = Wav2VecBertEncoder(device='cuda:0', precision='bf16', n_layers=2)
+    total = 48000
+    wave = torch.zeros(len(lengths), total)
+    mask = torch.zeros(len(lengths), total)
+    for i, c in enumerate(clips):
+        wave[i, :c.numel()] = c
+        mask[i, :c.numel()] = 1
+    padded = enc(wave.to(cuda_device), mask.to(cuda_device)).cpu()
+    rows = [packing.length_tokens(n, 16000, 50) for n in lengths]
+    packed = [t.cpu() for t in enc.encode_packed(clips, total, rows)]
+    alone = [enc.encode_packed([c], total, [r])[0].cpu() for c, r in zip(clips, rows)]
+    for i, r in enumerate(rows):
+        assert torch.equal(packed[i][0], padded[i, 0, :r])
+        assert torch.equal(alone[i][0], packed[i][0])
+    # a longer virtual padding (30 s chunk) gives the same saved tokens
+    longer = [t.cpu() for t in enc.encode_packed(clips, 480000, rows)]
+    for a, b in zip(longer, packed):
+        assert torch.equal(a, b)
+
+
+def test_missing_tensor_fails_loudly(cuda_device):
+    enc = Wav2VecBertEncoder(device='cuda:0', precision='bf16', n_layers=1)
+    lib = L.load()
+    h = lib.b2t_semantic_create(1, 2048, L.PREC_BF16)
+    w = torch.zeros(16000, device=cuda_device)
+    plan = packing.plan_semantic([16000], [0], 16000)
+    db = packing.DeviceBatch(plan, cuda_device)
+    ws = torch.empty(lib.b2t_semantic_workspace_bytes(h, plan.total_rows, plan.total_frames, 1), dtype=torch.uint8, device=cuda_device)
+    out = torch.empty(plan.total_rows, dtype=torch.int16, device=cuda_device)
+    rc = lib.b2t_semantic_encode(h, w.data_ptr(), db.byref(), enc.tables.byref(), ws.data_ptr(), ws.numel(),
+                                 out.data_ptr(), -1, None, L.stream_ptr())
+    assert rc == -5 and b'not set' in lib.b2t_last_error()
+    lib.b2t_semantic_destroy(h)

@@ -1,0 +1,107 @@
+"""CPU: the oracle (oracle/) against fixtures generated from the reference itself
+(tests/golden/make_golden.py ran /root/reference's processors.py + attention patch on HF models)."""
+import os
+
+import numpy as np
+import torch
+
+from audiotoken_b200.weights import synthetic_codebook, synthetic_w2vbert_state_dict, synthetic_waveform
+from oracle import conformer, fbank, quantize
+
+
+def _clips(lengths, total):
+    wave = torch.zeros(len(lengths), total)
+    mask = torch.zeros(len(lengths), total)
+    for i, n in enumerate(lengths):
+        wave[i, :n] = synthetic_waveform(i, int(n), 16000)
+        mask[i, :n] = 1
+    return wave, mask
+
+
+def test_mel_filters_and_window_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'fbank.npz'))
+    assert np.array_equal(fbank.mel_filters().numpy(), g['mel_filters'])
+    assert np.array_equal(fbank.povey_window().numpy(), g['window'])
+    m = g['mel_filters']
+    assert m.shape == (257, 80) and not m[256].any() and not m[0].any()
+    assert ((m[:256] != 0).sum(axis=1) <= 2).all()          # each FFT bin feeds at most two filters
+
+
+def test_features_match_reference_ragged_batch(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'fbank.npz'))
+    wave, mask = _clips(g['lengths'], int(g['total']))
+    x, am = fbank.features(wave, mask)
+    np.testing.assert_allclose(x.numpy(), g['input_features'], rtol=0, atol=1e-5)
+    assert np.array_equal(am.numpy(), g['attention_mask'])
+    assert am.sum(1).tolist() == [49.0, 34.0, 24.0, 9.0]
+
+
+def test_features_match_reference_single_clips(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'fbank_single.npz'))
+    for n in (4800, 16037):
+        wave, mask = _clips([n], n)
+        x, am = fbank.features(wave, mask)
+        np.testing.assert_allclose(x.numpy(), g[f'feat_{n}'], rtol=0, atol=1e-5)
+        assert np.array_equal(am.numpy(), g[f'mask_{n}'])
+
+
+def _run_conformer(golden_dir, tag, n_layers):
+    g = np.load(os.path.join(golden_dir, 'fbank.npz'))
+    c = np.load(os.path.join(golden_dir, f'conformer_{tag}.npz'))
+    sd = synthetic_w2vbert_state_dict(n_layers, seed=0)
+    hs = conformer.hidden_states(torch.from_numpy(g['input_features']), torch.from_numpy(g['attention_mask']),
+                                 sd, n_layers)
+    return hs, c
+
+
+def test_conformer_2_layers_match_reference(golden_dir):
+    hs, c = _run_conformer(golden_dir, 'l2', 2)
+    for i, key in enumerate(('hidden_0', 'hidden_1', 'hidden_last')):
+        ref = c[key]
+        err = np.linalg.norm(hs[i].numpy() - ref) / np.linalg.norm(ref)
+        assert err < 1e-5, (key, err)
+    emb = conformer.final_embedding(hs[2]).reshape(-1, 1024)
+    idx, tie = quantize.nearest_centroid(emb, synthetic_codebook(2048, 1024, 4))
+    assert not tie.any()
+    assert np.array_equal(idx.numpy().reshape(c['tokens'].shape), c['tokens'])
+
+
+def test_conformer_19_layers_match_reference(golden_dir):
+    hs, c = _run_conformer(golden_dir, 'l19', 19)
+    ref = c['hidden_last']
+    err = np.linalg.norm(hs[19].numpy() - ref) / np.linalg.norm(ref)
+    assert err < 1e-4, err
+    emb = conformer.final_embedding(hs[19]).reshape(-1, 1024)
+    idx, _ = quantize.nearest_centroid(emb, synthetic_codebook(2048, 1024, 4))
+    agree = (idx.numpy().reshape(c['tokens'].shape) == c['tokens']).mean()
+    assert agree >= 0.995, agree
+
+
+def test_nearest_centroid_matches_reference_expression():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(512, 256, generator=g)
+    cb = torch.randn(1000, 256, generator=g)
+    idx, tie = quantize.nearest_centroid(x, cb)
+    ref = quantize.kmeans_assign_fp32(x, cb)                 # encoder.py:100-101 verbatim
+    assert (idx[~tie] == ref[~tie]).float().mean() > 0.999
+    cb2 = torch.cat([cb, cb[:5]], 0)                         # duplicates: first index wins
+    idx2, _ = quantize.nearest_centroid(x, cb2)
+    assert (idx2 < 1000).all()
+
+
+def test_rvq_residual_property():
+    g = torch.Generator().manual_seed(5)
+    emb = torch.randn(300, 128, generator=g)
+    cbs = torch.randn(16, 1024, 128, generator=g)
+    codes = quantize.rvq_encode(emb, cbs, 16)
+    assert codes.shape == (16, 300)
+    r = emb.double().clone()
+    prev = (r * r).sum(1)
+    for q in range(16):
+        r = r - cbs[q].double()[codes[q]]
+        cur = (r * r).sum(1)
+        # the chosen code is the nearest one, so no other single code gives a smaller residual
+        alt = ((r + cbs[q].double()[codes[q]]).unsqueeze(1) - cbs[q].double().unsqueeze(0)).pow(2).sum(-1).min(1).values
+        assert torch.allclose(cur, alt)
+        prev = cur
+    assert quantize.num_quantizers(12.0) == 16 and quantize.num_quantizers(1.5) == 2
