@@ -19,6 +19,51 @@
 
 void b2t_reset_launch_count();
 
+// ---- optional per-kernel-class CUDA-event profiling (bench.py roofline numbers) ------------------
+namespace {
+enum { PC_FBANK = 0, PC_LN, PC_GEMM, PC_ATTN, PC_DWCONV, PC_VQ, PC_COUNT };
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Span { int cls; size_t e0, e1; };
+  std::vector<Span> spans;
+  double flops_gemm = 0.0;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+};
+thread_local Prof g_prof;
+struct Scope {
+  int cls; cudaStream_t st; size_t e0 = 0; bool on;
+  Scope(int c, cudaStream_t s) : cls(c), st(s), on(g_prof.on) {
+    if (on) { e0 = g_prof.used; cudaEventRecord(g_prof.get(), st); }
+  }
+  ~Scope() {
+    if (on) { size_t e1 = g_prof.used; cudaEventRecord(g_prof.get(), st); g_prof.spans.push_back({cls, e0, e1}); }
+  }
+};
+}  // namespace
+
+extern "C" int b2t_profile_enable(int on) { g_prof.on = on != 0; return B2T_OK; }
+
+// Synchronises, adds up the event spans recorded since the last read into ms_per_class[6]
+// (fbank, layernorm, gemm, attention, dwconv, vq) and returns the GEMM FLOPs issued in *gemm_flops.
+extern "C" int b2t_profile_read(float* ms_per_class, double* gemm_flops) {
+  B2T_REQUIRE(ms_per_class, B2T_ERR_ARG, "b2t_profile_read: null argument");
+  for (int i = 0; i < PC_COUNT; ++i) ms_per_class[i] = 0.f;
+  for (auto& sp : g_prof.spans) {
+    B2T_CUDA(cudaEventSynchronize(g_prof.pool[sp.e1]));
+    float ms = 0.f;
+    B2T_CUDA(cudaEventElapsedTime(&ms, g_prof.pool[sp.e0], g_prof.pool[sp.e1]));
+    ms_per_class[sp.cls] += ms;
+  }
+  if (gemm_flops) *gemm_flops = g_prof.flops_gemm;
+  g_prof.spans.clear(); g_prof.used = 0; g_prof.flops_gemm = 0.0;
+  return B2T_OK;
+}
+
 struct b2t_semantic_model {
   int n_layers;
   int codebook_size;
@@ -123,18 +168,30 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
     g.A = A; g.lda = lda; g.W = W; g.bias = (const float*)bias; g.out = out; g.ldo = ldo; g.resid = resid;
     g.row_valid = w.row_valid; g.M = M; g.N = N; g.K = K; g.epilogue = epi; g.alpha = alpha;
     g.round_resid_bf16 = round_resid; g.precision = prec; g.impl = bf ? m->gemm_impl : B2T_IMPL_SIMT;
+    Scope sc(PC_GEMM, st);
+    if (g_prof.on) g_prof.flops_gemm += 2.0 * M * (double)N * K;
     return b2t_gemm(&g, stream);
   };
 
+  auto ln = [&](const float* x, const void* lw, const void* lb, const uint8_t* rv, void* out, int oprec) -> int {
+    Scope sc(PC_LN, st);
+    return b2t_layernorm(x, (const float*)lw, (const float*)lb, rv, out, M, 1024, oprec, stream);
+  };
   // ---- front end
   const int mel_bf16 = m->mel_bf16 >= 0 ? m->mel_bf16 : (bf ? 1 : 0);
-  RUN(b2t_fbank_logmel(wave, b, tables, w.logmel, mel_bf16, stream));
-  RUN(b2t_fbank_stats(w.logmel, b, w.mean, w.std_, stream));
+  {
+    Scope sc(PC_FBANK, st);
+    RUN(b2t_fbank_logmel(wave, b, tables, w.logmel, mel_bf16, stream));
+    RUN(b2t_fbank_stats(w.logmel, b, w.mean, w.std_, stream));
+  }
   const void* fplw = T("fp.ln.w"); const void* fplb = T("fp.ln.b");
   const void* fpw = T("fp.proj.w"); const void* fpb = T("fp.proj.b");
   NEED();
-  RUN(b2t_fbank_stack_ln(w.logmel, w.mean, w.std_, b, (const float*)fplw, (const float*)fplb, w.a160, nullptr,
-                         w.row_valid, prec, stream));
+  {
+    Scope sc(PC_FBANK, st);
+    RUN(b2t_fbank_stack_ln(w.logmel, w.mean, w.std_, b, (const float*)fplw, (const float*)fplb, w.a160, nullptr,
+                           w.row_valid, prec, stream));
+  }
   // feature projection; padded rows zeroed (HF :493); residual stream x starts here
   RUN(gemm(w.a160, 160, fpw, fpb, nullptr, 0, w.x, 1024, 160, B2T_EPI_BIAS_MASK, 1.f, 0));
   if (tap_layer == 0 && tap_out) B2T_CUDA(cudaMemcpyAsync(tap_out, w.x, (size_t)M * 4096, cudaMemcpyDeviceToDevice, st));
@@ -149,18 +206,18 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
         const void* wqkv = T(L + "attn.wqkv"); const void* bqkv = T(L + "attn.bqkv");
         const void* wo = T(L + "attn.wo"); const void* bo = T(L + "attn.bo"); const void* dist = T(L + "attn.dist");
         NEED();
-        RUN(b2t_layernorm(w.x, (const float*)lw, (const float*)lb, nullptr, w.ln_out, M, 1024, prec, stream));
+        RUN(ln(w.x, lw, lb, nullptr, w.ln_out, prec));
         RUN(gemm(w.ln_out, 1024, wqkv, bqkv, w.big, 3072, nullptr, 3072, 1024, B2T_EPI_BIAS, 1.f, 0));
-        RUN(b2t_relkey_attention(w.big, dist, b, w.att, prec, bf ? m->attn_impl : B2T_IMPL_SIMT, stream));
+        { Scope sc(PC_ATTN, st); RUN(b2t_relkey_attention(w.big, dist, b, w.att, prec, bf ? m->attn_impl : B2T_IMPL_SIMT, stream)); }
         RUN(gemm(w.att, 1024, wo, bo, nullptr, 0, w.x, 1024, 1024, B2T_EPI_RESID, 1.f, rr));
         // ---- convolution module
         const void* clw = T(L + "conv.ln.w"); const void* clb = T(L + "conv.ln.b");
         const void* pw1 = T(L + "conv.pw1"); const void* dw = T(L + "conv.dw");
         const void* dlw = T(L + "conv.dwln.w"); const void* dlb = T(L + "conv.dwln.b"); const void* pw2 = T(L + "conv.pw2");
         NEED();
-        RUN(b2t_layernorm(w.x, (const float*)clw, (const float*)clb, w.row_valid, w.ln_out, M, 1024, prec, stream));
+        RUN(ln(w.x, clw, clb, w.row_valid, w.ln_out, prec));
         RUN(gemm(w.ln_out, 1024, pw1, nullptr, w.big, 1024, nullptr, 2048, 1024, B2T_EPI_GLU, 1.f, 0));
-        RUN(b2t_dwconv_ln_swish(w.big, (const float*)dw, (const float*)dlw, (const float*)dlb, b, w.att, prec, stream));
+        { Scope sc(PC_DWCONV, st); RUN(b2t_dwconv_ln_swish(w.big, (const float*)dw, (const float*)dlw, (const float*)dlb, b, w.att, prec, stream)); }
         RUN(gemm(w.att, 1024, pw2, nullptr, nullptr, 0, w.x, 1024, 1024, B2T_EPI_RESID, 1.f, rr));
       }
       // ---- half-step feed forward (ffn1 before attention, ffn2 after the conv module)
@@ -168,13 +225,13 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
       const void* lw = T(F + "ln.w"); const void* lb = T(F + "ln.b");
       const void* w1 = T(F + "w1"); const void* b1 = T(F + "b1"); const void* w2 = T(F + "w2"); const void* b2 = T(F + "b2");
       NEED();
-      RUN(b2t_layernorm(w.x, (const float*)lw, (const float*)lb, nullptr, w.ln_out, M, 1024, prec, stream));
+      RUN(ln(w.x, lw, lb, nullptr, w.ln_out, prec));
       RUN(gemm(w.ln_out, 1024, w1, b1, w.big, 4096, nullptr, 4096, 1024, B2T_EPI_BIAS_SWISH, 1.f, 0));
       RUN(gemm(w.big, 4096, w2, b2, nullptr, 0, w.x, 1024, 4096, B2T_EPI_RESID, 0.5f, rr));
     }
     const void* flw = T(L + "final.ln.w"); const void* flb = T(L + "final.ln.b");
     NEED();
-    RUN(b2t_layernorm(w.x, (const float*)flw, (const float*)flb, nullptr, w.x, M, 1024, B2T_PREC_FP32, stream));
+    RUN(ln(w.x, flw, flb, nullptr, w.x, B2T_PREC_FP32));
     if (tap_layer == i + 1 && tap_out)
       B2T_CUDA(cudaMemcpyAsync(tap_out, w.x, (size_t)M * 4096, cudaMemcpyDeviceToDevice, st));
   }
@@ -183,7 +240,7 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
   NEED();
   auto it = m->t.find("codebook.half_norm");
   const float* hn = it == m->t.end() ? nullptr : (const float*)it->second;
-  RUN(b2t_vq_argmin(w.x, 1024, M, 1024, (const float*)cb, hn, m->codebook_size, 1, tokens, nullptr, w.vq, w.vq_bytes, stream));
+  { Scope sc(PC_VQ, st); RUN(b2t_vq_argmin(w.x, 1024, M, 1024, (const float*)cb, hn, m->codebook_size, 1, tokens, nullptr, w.vq, w.vq_bytes, stream)); }
   (void)act;
   return B2T_OK;
 #undef RUN

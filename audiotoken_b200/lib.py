@@ -24,7 +24,7 @@ EXPORTS = [
     'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_dwconv_ln_swish',
     'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_semantic_create', 'b2t_semantic_destroy',
     'b2t_semantic_set_tensor', 'b2t_semantic_workspace_bytes', 'b2t_semantic_encode',
-    'b2t_last_launch_count',
+    'b2t_last_launch_count', 'b2t_profile_enable', 'b2t_profile_read',
 ]
 
 
@@ -91,6 +91,8 @@ def load() -> C.CDLL:
     lib.b2t_semantic_workspace_bytes.restype = sz
     lib.b2t_semantic_encode.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(FbankTables), vp, sz, vp, i32, vp, vp]
     lib.b2t_last_launch_count.restype = i32
+    lib.b2t_profile_enable.argtypes = [i32]
+    lib.b2t_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double)]
     _lib = lib
     return lib
 

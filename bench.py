@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds tokenised per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the semantic_m encode path (log-mel front end -> 19 conformer layers ->
+LayerNorm -> VQ 2048) over this rank's shard of BASELINE config[2]: 10 000 synthetic clips of
+U(2, 30) s @16 kHz (seed 0), 1250 clips per GPU (weak scaling: per-GPU work is fixed), packed into
+length-bucketed ragged batches.  Random-init weights of the named architecture (`data: synthetic`).
+
+  value : whole-job audio-s/s with the waveforms already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the public call with HOST (pinned) waveforms: per batch H2D copy, batch
+          planning, encode, D2H copy of the int16 tokens — copies overlapped on a second stream
+  roofline      : dominant kernel class = the tcgen05 GEMM; CUDA-event time of every GEMM launch of
+                  instrumented steps vs MEASURED_PEAKS.json bf16 (sustained: timed inside a long step)
+  cpu_baseline  : the oracle pipeline (oracle/, fp32 torch-CPU restatement of the reference) on the
+                  host cores, on a bounded sample of the same workload, run the way the reference
+                  runs it (clips padded to chunk_size = 30 s, all 21 layers of its checkpoint)
+
+`--impl reference` prints the CPU arm alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+TOKEN_RATE = 50
+TOTAL_CLIPS = 10000
+CLIPS_PER_GPU = 1250
+CHUNK_S = 30
+N_LAYERS = 19
+REF_LAYERS = 21
+CODEBOOK = 2048
+ROW_BUDGET = 65536          # token rows per ragged batch
+
+
+def shard_lengths(rank: int, workload: str):
+    """Clip lengths (samples) of this rank's shard."""
+    if workload == 'c2':                      # BASELINE config[1] shape: 64 x 10 s
+        return np.full(64, 10 * SR, dtype=np.int64)
+    g = torch.Generator().manual_seed(0)
+    dur = torch.rand(TOTAL_CLIPS, generator=g, dtype=torch.float64) * 28.0 + 2.0
+    lens = (dur * SR).round().to(torch.int64).numpy()
+    r = rank % (TOTAL_CLIPS // CLIPS_PER_GPU)
+    return lens[r * CLIPS_PER_GPU:(r + 1) * CLIPS_PER_GPU]
+
+
+def synth_on_device(lengths: np.ndarray, seed: int, device) -> torch.Tensor:
+    """Flat fp32 buffer of the clips back to back: 0.1*noise + 3 sinusoids per clip, in [-1, 1]."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    n = len(lengths)
+    lens = torch.from_numpy(lengths).to(device)
+    total = int(lengths.sum())
+    x = 0.1 * torch.randn(total, generator=g, device=device)
+    start = torch.cumsum(lens, 0) - lens
+    t = (torch.arange(total, device=device) - torch.repeat_interleave(start, lens)).to(torch.float32) / SR
+    for _ in range(3):
+        f = torch.rand(n, generator=g, device=device) * (4000 - 80) + 80
+        a = torch.rand(n, generator=g, device=device) * 0.15 + 0.05
+        ph = torch.rand(n, generator=g, device=device) * 2 * math.pi
+        x += torch.repeat_interleave(a, lens) * torch.sin(
+            2 * math.pi * torch.repeat_interleave(f, lens) * t + torch.repeat_interleave(ph, lens))
+    return x.clamp_(-1, 1)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (NVML, 100 ms period)."""
+    REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown',
+               0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown', 0x2: 'applications_clocks_setting'}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        med = float(np.median(self.samples)) if self.samples else None
+        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1360.2), d.get('hbm_gbs', 6549.4), 'measured (MEASURED_PEAKS.json, sustained bf16)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(lengths: np.ndarray, steps: int, warmup: int, n_sample: int = 4):
+    """Oracle pipeline on the host cores, run as the reference runs it (padded 30 s chunks, 21 layers)."""
+    from audiotoken_b200.weights import synthetic_codebook, synthetic_w2vbert_state_dict, synthetic_waveform
+    from oracle import conformer, fbank, quantize
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_w2vbert_state_dict(REF_LAYERS, seed=0)
+    cb = synthetic_codebook(CODEBOOK, 1024, seed=4)
+    lens = [int(v) for v in lengths[:n_sample]]
+    pad = CHUNK_S * SR
+    wave = torch.zeros(len(lens), pad)
+    mask = torch.zeros(len(lens), pad)
+    for i, n in enumerate(lens):
+        wave[i, :n] = synthetic_waveform(i, n, SR)
+        mask[i, :n] = 1
+    audio_s = sum(lens) / SR
+
+    def step():
+        with torch.no_grad():
+            feats, am = fbank.features(wave, mask)
+            hs = conformer.hidden_states(feats, am, sd, REF_LAYERS)
+            emb = conformer.final_embedding(hs[N_LAYERS])
+            return quantize.kmeans_assign_fp32(emb.reshape(-1, 1024), cb)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    return dict(value=audio_s / (ms / 1e3), unit='audio-s/s', cores=cores, kind='port',
+                sample=f'{len(lens)} clips of the workload ({audio_s:.1f} audio-s) padded to {CHUNK_S} s, '
+                       f'{REF_LAYERS} layers, fp32 torch-CPU oracle, {steps} timed steps'), ms
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    lengths = shard_lengths(0, args.workload)
+    base, ms = cpu_reference_run(lengths, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {'impl': 'reference', 'metric': 'audio_seconds_per_second', 'value': base['value'], 'unit': 'audio-s/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.workload, lengths), 'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, lengths):
+    name = ('semantic_m encode_batch_files-equivalent: per-GPU shard of BASELINE configs[2] '
+            f'({len(lengths)} of {TOTAL_CLIPS} synthetic clips, U(2,30) s @16 kHz, seed 0); '
+            f'w2v-BERT 2.0 conformer x{N_LAYERS} + LayerNorm + VQ {CODEBOOK}x1024')
+    if workload == 'c2':
+        name = f'semantic_m encode of 64 x 10 s @16 kHz clips (BASELINE configs[1] shape); conformer x{N_LAYERS} + VQ {CODEBOOK}'
+    return {'workload': name, 'clips_per_gpu': int(len(lengths)), 'audio_seconds_per_gpu': float(lengths.sum() / SR),
+            'row_budget_per_batch': ROW_BUDGET,
+            'l2': 'inputs larger than L2: every batch streams >1 GB of activations through HBM'}
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=['c3', 'c2'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+
+    from audiotoken_b200 import lib as L
+    from audiotoken_b200 import packing
+    from audiotoken_b200.encoder import Wav2VecBertEncoder
+
+    lengths = shard_lengths(rank, args.workload)
+    audio_s = float(lengths.sum() / SR)
+    rows = np.array([packing.length_tokens(int(n), SR, TOKEN_RATE) for n in lengths])
+    batches = packing.bucket_by_rows(rows.tolist(), ROW_BUDGET)
+    enc = Wav2VecBertEncoder(device=str(device), precision='bf16', n_layers=N_LAYERS)
+
+    # synthetic waveforms: generated on the device, kept there (value) and mirrored in pinned host memory (e2e)
+    dev_waves, host_waves, plans, host_tokens = [], [], [], []
+    for bi, idx in enumerate(batches):
+        ln = lengths[idx]
+        w = synth_on_device(ln, 1000 + rank * 1000 + bi, device)
+        offs = np.zeros(len(idx), dtype=np.int64)
+        offs[1:] = np.cumsum(ln)[:-1]
+        plan = packing.plan_semantic(ln, offs, CHUNK_S * SR, rows[idx])
+        dev_waves.append(w)
+        hw = torch.empty(w.numel(), dtype=torch.float32, pin_memory=True)
+        hw.copy_(w)
+        host_waves.append(hw)
+        plans.append(plan)
+        host_tokens.append(torch.empty(plan.total_rows, dtype=torch.int16, pin_memory=True))
+    torch.cuda.synchronize()
+    h2d_bytes = sum(h.numel() * 4 for h in host_waves)
+    d2h_bytes = sum(h.numel() * 2 for h in host_tokens)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    launches = [0]
+
+    def step_resident():
+        for w, plan in zip(dev_waves, plans):
+            enc.encode_plan(w, plan)
+            launches[0] += enc.last_launches
+
+    copy_stream = torch.cuda.Stream(device=device)
+    max_samples = max(w.numel() for w in dev_waves)
+    stage = [torch.empty(max_samples, dtype=torch.float32, device=device) for _ in range(2)]
+
+    def step_e2e():
+        comp = torch.cuda.current_stream()
+        free_ev = [None, None]
+        for i, (idx, hw, ht) in enumerate(zip(batches, host_waves, host_tokens)):
+            buf = stage[i % 2][:hw.numel()]
+            with torch.cuda.stream(copy_stream):
+                if free_ev[i % 2] is not None:
+                    copy_stream.wait_event(free_ev[i % 2])
+                buf.copy_(hw, non_blocking=True)
+                ready = copy_stream.record_event()
+            ln = lengths[idx]
+            offs = np.zeros(len(idx), dtype=np.int64)
+            offs[1:] = np.cumsum(ln)[:-1]
+            plan = packing.plan_semantic(ln, offs, CHUNK_S * SR, rows[idx])     # host planning is inside e2e
+            comp.wait_event(ready)
+            tokens, _ = enc.encode_plan(buf, plan)
+            done = comp.record_event()
+            free_ev[i % 2] = done
+            tokens.record_stream(copy_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                ht.copy_(tokens, non_blocking=True)
+        comp.wait_stream(copy_stream)
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        return max_over_ranks(s.elapsed_time(e) / steps)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches[0] = 0
+    ms_res = timed(step_resident, args.steps)
+    gpu_launches = launches[0]
+    clocks = sampler.result()
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # instrumented steps: CUDA-event time per kernel class
+    import ctypes as C
+    lib = L.load()
+    lib.b2t_profile_enable(1)
+    cls_ms = np.zeros(6)
+    gemm_flops = 0.0
+    for w, plan in zip(dev_waves, plans):
+        enc.encode_plan(w, plan)
+        arr = (C.c_float * 6)()
+        fl = C.c_double(0)
+        L.check(lib.b2t_profile_read(arr, C.byref(fl)), 'profile_read')
+        cls_ms += np.array(list(arr))
+        gemm_flops += fl.value
+    lib.b2t_profile_enable(0)
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    ach = gemm_flops / (cls_ms[2] / 1e3) / 1e12 if cls_ms[2] > 0 else 0.0
+
+    if rank == 0:
+        value = world * audio_s / (ms_res / 1e3)
+        e2e = world * audio_s / (ms_e2e / 1e3)
+        line = {
+            'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_res, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': workload_config(args.workload, lengths), 'clocks': clocks,
+            'e2e': {'value': e2e, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d_bytes),
+                    'd2h_bytes_per_step': int(d2h_bytes)},
+            'gpu_launches': int(gpu_launches),
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all 153 launches per batch)',
+                         'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
+                         'traffic': None, 'peak_source': peak_src,
+                         'gemm_share_of_step': float(cls_ms[2] / cls_ms.sum()) if cls_ms.sum() > 0 else None},
+            'breakdown_ms_per_step': dict(zip(['fbank', 'layernorm', 'gemm', 'attention', 'dwconv', 'vq'],
+                                              [float(v) for v in cls_ms])),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base, _ = cpu_reference_run(lengths, steps=2, warmup=1)
+            line['cpu_baseline'] = base
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

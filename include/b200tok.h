@@ -179,6 +179,12 @@ int b2t_semantic_encode(const b2t_semantic_model* m, const float* wave, const b2
 /* number of kernels the last b2t_semantic_encode on this thread launched */
 int b2t_last_launch_count(void);
 
+/* Optional CUDA-event profiling of b2t_semantic_encode (used by bench.py for the roofline line).
+ * b2t_profile_read synchronises and returns the milliseconds spent per kernel class since the last
+ * read — ms_per_class[6] = {fbank, layernorm, gemm, attention, dwconv, vq} — and the GEMM FLOPs. */
+int b2t_profile_enable(int on);
+int b2t_profile_read(float* ms_per_class_host, double* gemm_flops_host);
+
 #ifdef __cplusplus
 }
 #endif
