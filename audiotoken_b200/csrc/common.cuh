@@ -50,7 +50,10 @@ B2T_DEVICE float r16(float x) {
   if constexpr (kRound) return bf16_round(x); else return x;
 }
 
-B2T_DEVICE float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// fast-intrinsic forms (MUFU.EX2 + MUFU.RCP, ~2 ulp): the IEEE division path costs ~10x more in the
+// GEMM epilogues, and every consumer rounds to bf16 or tolerates 1e-6
+B2T_DEVICE float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+B2T_DEVICE float swishf_(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 B2T_DEVICE float warp_sum(float v) {
 #pragma unroll

@@ -108,8 +108,8 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
       const float rs = s_stat[t];
       float y0 = (a0[t] - mu[t]) * rs * g0 + b0;
       float y1 = (a1[t] - mu[t]) * rs * g1 + b1;
-      y0 = y0 * sigmoidf_(y0);
-      y1 = y1 * sigmoidf_(y1);
+      y0 = swishf_(y0);
+      y1 = swishf_(y1);
       st2<T>(out + (size_t)(r0 + t0 + t) * kC + c, y0, y1);
     }
   }

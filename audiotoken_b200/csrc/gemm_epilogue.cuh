@@ -3,6 +3,11 @@
 #include <type_traits>
 #include "common.cuh"
 
+B2T_DEVICE uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 struct EpiParams {
   const float* bias;
   void* out;
@@ -22,24 +27,36 @@ B2T_DEVICE void epilogue_store(const EpiParams& p, int row, int col0, const floa
   using OutT = typename std::conditional<kBF16, __nv_bfloat16, float>::type;
   if (row >= p.M) return;
   float v[NV];
+  if (p.bias != nullptr) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float b = (p.bias != nullptr) ? __ldg(p.bias + col0 + i) : 0.f;
-    v[i] = r16<kBF16>(acc[i] + b);
+    for (int i = 0; i < NV; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      v[i] = r16<kBF16>(acc[i] + b.x); v[i + 1] = r16<kBF16>(acc[i + 1] + b.y);
+      v[i + 2] = r16<kBF16>(acc[i + 2] + b.z); v[i + 3] = r16<kBF16>(acc[i + 3] + b.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = r16<kBF16>(acc[i]);
   }
   if constexpr (EPI == B2T_EPI_BIAS || EPI == B2T_EPI_BIAS_SWISH) {
     OutT* o = reinterpret_cast<OutT*>(p.out) + (size_t)row * p.ldo + col0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if constexpr (EPI == B2T_EPI_BIAS_SWISH) v[i] = v[i] * sigmoidf_(v[i]);
+      if constexpr (EPI == B2T_EPI_BIAS_SWISH) v[i] = swishf_(v[i]);
     }
-    if constexpr (kBF16) {
+    if constexpr (kBF16 && NV % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 8) {
+        uint4 pk;
+        pk.x = pack2_bf16(v[i], v[i + 1]); pk.y = pack2_bf16(v[i + 2], v[i + 3]);
+        pk.z = pack2_bf16(v[i + 4], v[i + 5]); pk.w = pack2_bf16(v[i + 6], v[i + 7]);
+        *reinterpret_cast<uint4*>(o + i) = pk;
+      }
+    } else if constexpr (kBF16) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v[i], v[i + 1]), hi = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
         uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        pk.x = pack2_bf16(v[i], v[i + 1]); pk.y = pack2_bf16(v[i + 2], v[i + 3]);
         *reinterpret_cast<uint2*>(o + i) = pk;
       }
     } else {
@@ -64,12 +81,17 @@ B2T_DEVICE void epilogue_store(const EpiParams& p, int row, int col0, const floa
     float g[NV / 2];
 #pragma unroll
     for (int i = 0; i < NV / 2; ++i) g[i] = v[2 * i] * sigmoidf_(v[2 * i + 1]);
-    if constexpr (kBF16) {
+    if constexpr (kBF16 && NV % 16 == 0) {
 #pragma unroll
-      for (int i = 0; i < NV / 2; i += 2) {
-        __nv_bfloat162 pr = __floats2bfloat162_rn(g[i], g[i + 1]);
-        *reinterpret_cast<uint32_t*>(o + i) = *reinterpret_cast<uint32_t*>(&pr);
+      for (int i = 0; i < NV / 2; i += 8) {
+        uint4 pk;
+        pk.x = pack2_bf16(g[i], g[i + 1]); pk.y = pack2_bf16(g[i + 2], g[i + 3]);
+        pk.z = pack2_bf16(g[i + 4], g[i + 5]); pk.w = pack2_bf16(g[i + 6], g[i + 7]);
+        *reinterpret_cast<uint4*>(o + i) = pk;
       }
+    } else if constexpr (kBF16) {
+#pragma unroll
+      for (int i = 0; i < NV / 2; i += 2) *reinterpret_cast<uint32_t*>(o + i) = pack2_bf16(g[i], g[i + 1]);
     } else {
 #pragma unroll
       for (int i = 0; i < NV / 2; i += 2) *reinterpret_cast<float2*>(o + i) = make_float2(g[i], g[i + 1]);

@@ -1,24 +1,29 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  out = A[M,K] (bf16, K-major) . W[N,K]^T (bf16, K-major)
 // with fp32 accumulation in tensor memory and the fused epilogues of gemm_epilogue.cuh.
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0     TMA producer  : cp.async.bulk.tensor 2D loads of a 128x64 A tile and a BNx64 W tile
 //                              (SWIZZLE_128B) into a kStages-deep shared-memory ring, mbarrier
 //                              complete_tx signalling.
 //   warp 1     MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //                              (M=128, N=BN, K=16) x4 per 64-wide k-block; tcgen05.commit frees the
 //                              smem slot / publishes the accumulator.  Also owns the TMEM allocation.
-//   warps 2-5  epilogue      : tcgen05.ld 32x32b.x32 (each warp its own 32-lane quadrant), bias /
-//                              activation / residual / GLU, direct 16-byte global stores.
+//   warps 2-9  epilogue      : tcgen05.ld 32x32b.x32 (TMEM lane quadrant = warp % 4; the two warps of a
+//                              quadrant split the columns), bias / activation / residual / GLU, direct
+//                              16-byte global stores.  Two warps per scheduler hide the TMEM/ALU latency.
 // The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Tiles are visited n-fastest so concurrently running CTAs share the A tile in L2.
 #include <cuda.h>
 #include "gemm_epilogue.cuh"
+#include "vq_cand.cuh"
+
+constexpr int kEpiArgmax = 100;   // internal epilogue: per-row top-3 of (acc - half_norm[col]) (vq.cu)
 
 namespace {
 
 constexpr int kBM = 128, kBK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quadrant, each owns half of the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 B2T_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,8 +86,8 @@ B2T_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uin
 B2T_DEVICE void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-B2T_DEVICE void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+B2T_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+B2T_DEVICE void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -92,9 +97,6 @@ B2T_DEVICE void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -110,6 +112,72 @@ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Residual epilogue with coalesced global traffic.  After tcgen05.ld each lane owns one accumulator
+// row (32 consecutive columns); writing that straight to the fp32 stream touches 32 different cache
+// lines per instruction.  Instead the delta alpha*r16(acc+bias) is transposed through a per-warp
+// 16x32 fp32 shared-memory tile (16-byte chunks XOR-swizzled by row) so that 8 lanes cover one
+// 128-byte row segment and a warp instruction moves 4 full lines:  x = resid; x += delta; resid = x.
+B2T_DEVICE void resid_chunk_coalesced(const EpiParams& p, float4* stg, int row_base, int col0, int lane,
+                                      const float (&acc)[32]) {
+  float d[32];
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      d[i] = p.alpha * bf16_round(acc[i] + b.x); d[i + 1] = p.alpha * bf16_round(acc[i + 1] + b.y);
+      d[i + 2] = p.alpha * bf16_round(acc[i + 2] + b.z); d[i + 3] = p.alpha * bf16_round(acc[i + 3] + b.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = p.alpha * bf16_round(acc[i]);
+  }
+  const int q = lane & 7;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if ((lane >> 4) == half) {
+      const int rl = lane & 15;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        stg[rl * 8 + (i ^ (rl & 7))] = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+    }
+    __syncwarp();
+    float4 x[4];
+    float* g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rl = j * 4 + (lane >> 3);
+      const int grow = row_base + half * 16 + rl;
+      g[j] = grow < p.M ? p.resid + (size_t)grow * p.N + col0 + q * 4 : nullptr;
+      if (g[j]) x[j] = *reinterpret_cast<const float4*>(g[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rl = j * 4 + (lane >> 3);
+      const float4 dd = stg[rl * 8 + (q ^ (rl & 7))];
+      if (g[j]) {
+        x[j].x += dd.x; x[j].y += dd.y; x[j].z += dd.z; x[j].w += dd.w;
+        if (p.round_resid) {
+          x[j].x = bf16_round(x[j].x); x[j].y = bf16_round(x[j].y); x[j].z = bf16_round(x[j].z); x[j].w = bf16_round(x[j].w);
+        }
+        *reinterpret_cast<float4*>(g[j]) = x[j];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// nearest-centroid epilogue: score = acc - 0.5|c|^2 (p.bias = half norms, +inf beyond the codebook)
+B2T_DEVICE void argmax_chunk(const EpiParams& p, Cand& cand, int col0, const float (&acc)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 h = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+    cand_insert_ordered(cand, acc[i] - h.x, col0 + i);
+    cand_insert_ordered(cand, acc[i + 1] - h.y, col0 + i + 1);
+    cand_insert_ordered(cand, acc[i + 2] - h.z, col0 + i + 2);
+    cand_insert_ordered(cand, acc[i + 3] - h.w, col0 + i + 3);
+  }
+}
+
 template <int BN>
 struct SmemLayout {
   static constexpr int kStageA = kBM * kBK * 2;         // 16 KB
@@ -117,10 +185,14 @@ struct SmemLayout {
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTileBytes = kStages * (kStageA + kStageB);
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kTileBytes + kBarBytes + 1024;  // +1024 for manual alignment
+  static constexpr int kEpiStage = 2048;                 // per epilogue warp: 16 rows x 32 fp32 (transposes)
+  static constexpr int kEpiOff = kTileBytes + 256;       // barriers live in [kTileBytes, kTileBytes+256)
+  static constexpr int kTotal = kEpiOff + kEpiWarps * kEpiStage + 1024;  // +1024 for manual alignment
 };
 
-template <int BN, int EPI>
+// kSplit3: A and W hold [hi | lo] bf16 halves (each Kd = K/3 wide); the K loop runs the three products
+// hi*hi, lo*hi, hi*lo back to back into one accumulator (error-compensated bf16x3 dot product).
+template <int BN, int EPI, bool kSplit3 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                int K, EpiParams p) {
@@ -146,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -164,10 +236,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          int ka = kb * kBK, kw = kb * kBK;
+          if constexpr (kSplit3) {
+            const int nkd = num_kb / 3, seg = kb / nkd, j = kb - seg * nkd;
+            ka = (seg == 1 ? nkd : 0) * kBK + j * kBK;     // A: hi, lo, hi
+            kw = (seg == 2 ? nkd : 0) * kBK + j * kBK;     // W: hi, hi, lo
+          }
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), L::kStageA + L::kStageB);
-          tma_load_2d(sA + stage * L::kStageA, &map_a, full_bar(stage), kb * kBK, m0);
-          tma_load_2d(sB + stage * L::kStageB, &map_w, full_bar(stage), kb * kBK, n0);
+          tma_load_2d(sA + stage * L::kStageA, &map_a, full_bar(stage), ka, m0);
+          tma_load_2d(sB + stage * L::kStageB, &map_w, full_bar(stage), kw, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -200,24 +278,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+    // ===== epilogue warps: TMEM lane quadrant = warp % 4; warps sharing a quadrant split the columns =====
     const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;                       // 0 .. kEpiWarps/4 - 1
+    constexpr int kChunks = BN / 32 / (kEpiWarps / 4);      // 32-column chunks per warp
+    float4* stg = reinterpret_cast<float4*>(smem_raw + (base - smem_u32(smem_raw)) + L::kEpiOff + (warp - 2) * L::kEpiStage);
+    static_assert(kChunks % 2 == 0, "chunks are processed in pairs");
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      if constexpr (EPI == B2T_EPI_RESID) {
+        // pull the residual region of the NEXT tile of this CTA into L2 while this tile is processed:
+        // the read-modify-write below is otherwise a chain of exposed DRAM round trips
+        const int tn = (t == (int)blockIdx.x) ? t : t + (int)gridDim.x;   // first tile: prefetch itself
+        for (int tp = tn; tp <= t + (int)gridDim.x && tp < num_tiles; tp += gridDim.x) {
+          const int pr = (tp / tiles_n) * kBM + quad * 32 + lane;
+          if (pr < p.M) {
+            const float* base_p = p.resid + (size_t)pr * p.N + (tp % tiles_n) * BN + part * kChunks * 32;
+#pragma unroll
+            for (int i = 0; i < kChunks; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base_p + i * 32));
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kChunks * 32);
+      Cand cand = cand_empty();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < kChunks; c += 2) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32_nowait(taddr + (uint32_t)(c * 32), r0);
+        tmem_ld_32x32_nowait(taddr + (uint32_t)(c * 32 + 32), r1);
+        tmem_ld_wait();
+        if (c + 2 >= kChunks) {
+          // the accumulator is now in registers: hand the TMEM buffer back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
         float v[32];
-        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        epilogue_store<EPI, true, 32>(p, row, n0 + c * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
+        if constexpr (EPI == kEpiArgmax) {
+          argmax_chunk(p, cand, n0 + (part * kChunks + c) * 32, v);
+        } else if constexpr (EPI == B2T_EPI_RESID) {
+          resid_chunk_coalesced(p, stg, m0 + quad * 32, n0 + (part * kChunks + c) * 32, lane, v);
+        } else {
+          epilogue_store<EPI, true, 32>(p, row, n0 + (part * kChunks + c) * 32, v);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r1[i]);
+        if constexpr (EPI == kEpiArgmax) {
+          argmax_chunk(p, cand, n0 + (part * kChunks + c + 1) * 32, v);
+        } else if constexpr (EPI == B2T_EPI_RESID) {
+          resid_chunk_coalesced(p, stg, m0 + quad * 32, n0 + (part * kChunks + c + 1) * 32, lane, v);
+        } else {
+          epilogue_store<EPI, true, 32>(p, row, n0 + (part * kChunks + c + 1) * 32, v);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if constexpr (EPI == kEpiArgmax) {
+        // one partial record per (row, column slice): slice = n-tile * (warps per quadrant) + part
+        if (row < p.M)
+          reinterpret_cast<Cand*>(p.out)[(size_t)row * p.ldo + (t % tiles_n) * (kEpiWarps / 4) + part] = cand;
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -293,6 +417,31 @@ int dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mw, const b2t_gemm_ar
 }
 
 }  // namespace
+
+// Fast pass of the nearest-centroid search on tensor cores (vq.cu).
+//   A2 [M, 2*D] bf16 = x_hi | x_lo,  C2 [K, 2*D] bf16 = c_hi | c_lo,  half_norm [Kpad] (+inf padding),
+//   parts [M, slices] Cand with slices = (Kpad / 256) * 2.
+int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, int D, const float* half_norm,
+                       void* parts, int slices, cudaStream_t st) {
+  using L = SmemLayout<256>;
+  CUtensorMap ma, mw;
+  int rc = make_map(&ma, A2, M, 2 * D, 2 * D, kBM);
+  if (rc != B2T_OK) return rc;
+  rc = make_map(&mw, C2, K, 2 * D, 2 * D, 256);
+  if (rc != B2T_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    B2T_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, kEpiArgmax, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  EpiParams p{half_norm, parts, slices, nullptr, nullptr, M, Kpad, 1.f, 0};
+  const int tiles = ((M + kBM - 1) / kBM) * (Kpad / 256);
+  int grid = b2t_num_sms();
+  if (tiles < grid) grid = tiles;
+  gemm_tc_kernel<256, kEpiArgmax, true><<<grid, kThreads, L::kTotal, st>>>(ma, mw, 3 * D, p);
+  B2T_LAUNCH_CHECK();
+  return B2T_OK;
+}
 
 int b2t_gemm_tensor(const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st) {
   B2T_REQUIRE(a->N % 128 == 0, B2T_ERR_ARG, "b2t_gemm(tensor): N must be a multiple of 128 (N=%d)", a->N);

@@ -240,7 +240,7 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
   NEED();
   auto it = m->t.find("codebook.half_norm");
   const float* hn = it == m->t.end() ? nullptr : (const float*)it->second;
-  { Scope sc(PC_VQ, st); RUN(b2t_vq_argmin(w.x, 1024, M, 1024, (const float*)cb, hn, m->codebook_size, 1, tokens, nullptr, w.vq, w.vq_bytes, stream)); }
+  { Scope sc(PC_VQ, st); RUN(b2t_vq_argmin(w.x, 1024, M, 1024, (const float*)cb, hn, m->codebook_size, 1, bf ? B2T_IMPL_AUTO : B2T_IMPL_SIMT, tokens, nullptr, w.vq, w.vq_bytes, stream)); }
   (void)act;
   return B2T_OK;
 #undef RUN

@@ -8,20 +8,10 @@
 //                    maximum is re-scored in fp64.  delta bounds |A_k - exact|.
 // Result == exact fp64 argmin, first index on ties.  Optional fused affine-free LayerNorm(1024)
 // (reference encoder.py:175-176).
-#include "common.cuh"
+#include <string.h>
+#include "vq_cand.cuh"
 
 namespace {
-
-struct Cand {
-  float v1, v2, v3;   // best, second, third fast score
-  int i1, i2;         // their indices
-};
-
-B2T_DEVICE void top3_insert(float v, int idx, float& v1, float& v2, float& v3, int& i1, int& i2) {
-  if (v > v1) { v3 = v2; v2 = v1; i2 = i1; v1 = v; i1 = idx; }
-  else if (v > v2) { v3 = v2; v2 = v; i2 = idx; }
-  else if (v > v3) { v3 = v; }
-}
 
 __global__ void half_norm_kernel(const float* __restrict__ cb, int K, int D, float* __restrict__ hn) {
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -71,10 +61,9 @@ vq_scan_simt_kernel(const float* __restrict__ x, int ldx, int M, int D, const fl
   const int m0 = blockIdx.x * 64;
   const int lr = tid >> 2, lk = (tid & 3) * 4;
   const int ty = tid >> 4, tx = tid & 15;
-  float v1[4], v2[4], v3[4];
-  int i1[4], i2[4];
+  Cand loc[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { v1[i] = v2[i] = v3[i] = -INFINITY; i1[i] = i2[i] = 0; }
+  for (int i = 0; i < 4; ++i) loc[i] = cand_empty();
 
   for (int n0 = 0; n0 < K; n0 += 64) {
     float acc[4][4] = {};
@@ -103,32 +92,37 @@ vq_scan_simt_kernel(const float* __restrict__ x, int ldx, int M, int D, const fl
       if (k < K) {
         const float h = __ldg(hn + k);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) top3_insert(acc[i][j] - h, k, v1[i], v2[i], v3[i], i1[i], i2[i]);
+        for (int i = 0; i < 4; ++i) cand_insert_ordered(loc[i], acc[i][j] - h, k);
       }
     }
   }
-  // merge the 16 per-thread lists of each row (ascending tx keeps the lowest index on ties)
+  // merge the 16 per-thread lists of each row
 #pragma unroll
-  for (int i = 0; i < 4; ++i) s_c[ty * 4 + i][tx] = Cand{v1[i], v2[i], v3[i], i1[i], i2[i]};
+  for (int i = 0; i < 4; ++i) s_c[ty * 4 + i][tx] = loc[i];
   __syncthreads();
   if (tid < 64 && m0 + tid < M) {
-    float b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
-    int j1 = 0, j2 = 0;
-    for (int t = 0; t < 16; ++t) {
-      const Cand c = s_c[tid][t];
-      // candidates arrive with strictly larger indices only within a thread; across threads compare
-      // (value, -index) so that equal values keep the smaller index first
-      auto ins = [&](float v, int idx) {
-        if (v > b1 || (v == b1 && idx < j1)) { b3 = b2; b2 = b1; j2 = j1; b1 = v; j1 = idx; }
-        else if (v > b2 || (v == b2 && idx < j2)) { b3 = b2; b2 = v; j2 = idx; }
-        else if (v > b3) { b3 = v; }
-      };
-      if (c.v1 > -INFINITY) ins(c.v1, c.i1);
-      if (c.v2 > -INFINITY) ins(c.v2, c.i2);
-      if (c.v3 > b3) b3 = c.v3;
-    }
-    cand[m0 + tid] = Cand{b1, b2, b3, j1, j2};
+    Cand best = cand_empty();
+    for (int t = 0; t < 16; ++t) cand_merge(best, s_c[tid][t]);
+    cand[m0 + tid] = best;
   }
+}
+
+// x (optionally LayerNormed) -> error-compensated bf16 pair: hi = bf16(x), lo = bf16(x - hi); [rows, 2*D]
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ x, int ldx, int rows, int D, __nv_bfloat16* __restrict__ out) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = x[(size_t)r * ldx + d];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[(size_t)r * 2 * D + d] = hi;
+    out[(size_t)r * 2 * D + D + d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+__global__ void fill_inf_kernel(float* __restrict__ p, int from, int to) {
+  const int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < to) p[i] = INFINITY;
 }
 
 B2T_DEVICE double exact_dist(const float* __restrict__ xr, const float* __restrict__ c, int D, int lane) {
@@ -140,15 +134,25 @@ B2T_DEVICE double exact_dist(const float* __restrict__ xr, const float* __restri
 // one warp per row
 __global__ void __launch_bounds__(256)
 vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const float* __restrict__ cb,
-                   const float* __restrict__ hn, int K, const Cand* __restrict__ cand, float rel_eps,
+                   const float* __restrict__ hn, int K, const Cand* __restrict__ cand, int slices, float rel_eps,
                    const float* __restrict__ cmax_half_ptr /* max_k 0.5|c_k|^2 */,
                    int16_t* __restrict__ out, int32_t* __restrict__ out32,
-                   unsigned int* __restrict__ n_fallback) {
+                   unsigned int* __restrict__ n_fallback, unsigned int* __restrict__ max_err) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= M) return;
   const float* xr = x + (size_t)r * ldx;
-  const Cand c = cand[r];
+  // merge the per-slice records of this row (lane-strided, then a shuffle tree)
+  Cand c = cand_empty();
+  for (int sidx = lane; sidx < slices; sidx += 32) cand_merge(c, cand[(size_t)r * slices + sidx]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Cand other;
+    other.v1 = __shfl_xor_sync(0xffffffffu, c.v1, o); other.v2 = __shfl_xor_sync(0xffffffffu, c.v2, o);
+    other.v3 = __shfl_xor_sync(0xffffffffu, c.v3, o); other.i1 = __shfl_xor_sync(0xffffffffu, c.i1, o);
+    other.i2 = __shfl_xor_sync(0xffffffffu, c.i2, o);
+    cand_merge(c, other);
+  }
   // |x|: bound on the fast-pass error  delta = rel_eps * (|x| |c|max + 0.5 |c|max^2)
   double xx = 0.0;
   for (int d = lane; d < D; d += 32) xx += (double)xr[d] * (double)xr[d];
@@ -159,10 +163,15 @@ vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const flo
   int best;
   if (K == 1) {
     best = 0;
-  } else if (!(c.v3 >= c.v1 - 2.0f * delta)) {
+  } else if (!(c.v3 >= c.v1 - 2.0f * delta) && c.i1 < K) {
     const double d1 = exact_dist(xr, cb + (size_t)c.i1 * D, D, lane);
-    const double d2 = exact_dist(xr, cb + (size_t)c.i2 * D, D, lane);
+    const double d2 = c.i2 < K ? exact_dist(xr, cb + (size_t)c.i2 * D, D, lane) : INFINITY;
     best = (d2 < d1 || (d2 == d1 && c.i2 < c.i1)) ? c.i2 : c.i1;
+    if (lane == 0 && max_err) {
+      // observed fast-pass error on the best candidate, in units of the bound's scale
+      const float obs = fabsf(c.v1 - (float)(0.5 * (xx - d1))) / ((float)sqrt(xx) * cmax + cmax_half);
+      atomicMax(max_err, __float_as_uint(obs));
+    }
   } else {
     if (lane == 0 && n_fallback) atomicAdd(n_fallback, 1u);
     // re-scan: lane-strided centroids, fp32 filter, fp64 re-score of everything near the running max
@@ -216,17 +225,41 @@ __global__ void max_reduce_kernel(const float* __restrict__ v, int n, float* __r
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, int D, const float* half_norm,
+                       void* parts, int slices, cudaStream_t st);   // gemm_tc.cu
+
+namespace {
+struct VqWs {
+  float* xn; __nv_bfloat16* a2; __nv_bfloat16* c2; float* hn; Cand* parts; float* cmax; unsigned int* nfb;
+  unsigned int* maxerr; size_t total; int kpad; int slices;
+};
+VqWs vq_carve(void* base, int rows, int dim, int K) {
+  VqWs w;
+  uint8_t* p = (uint8_t*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p ? (void*)(p + off) : nullptr; off += align_up(bytes, 256); return r; };
+  w.kpad = (K + 255) / 256 * 256;
+  w.slices = w.kpad / 256 * 2;
+  w.xn = (float*)take((size_t)rows * dim * 4);
+  w.a2 = (__nv_bfloat16*)take((size_t)rows * dim * 4);
+  w.c2 = (__nv_bfloat16*)take((size_t)K * dim * 4);
+  w.hn = (float*)take((size_t)w.kpad * 4);
+  w.parts = (Cand*)take((size_t)rows * w.slices * sizeof(Cand));
+  float* misc = (float*)take(256);
+  w.cmax = misc;
+  w.nfb = (unsigned int*)misc + 4;
+  w.maxerr = (unsigned int*)misc + 8;
+  w.total = off;
+  return w;
+}
+}  // namespace
+
 extern "C" size_t b2t_vq_workspace_bytes(int rows, int dim, int codebook_size) {
-  size_t b = 0;
-  b += align_up((size_t)rows * dim * 4, 256);          // LayerNormed rows
-  b += align_up((size_t)rows * sizeof(Cand), 256);     // candidates
-  b += align_up((size_t)codebook_size * 4, 256);       // half norms
-  b += 256;                                            // cmax_half, fallback counter
-  return b;
+  return vq_carve(nullptr, rows, dim, codebook_size).total;
 }
 
 extern "C" int b2t_vq_argmin(const float* x, int ldx, int rows, int dim, const float* codebook,
-                             const float* half_norm, int codebook_size, int apply_ln, int16_t* out,
+                             const float* half_norm, int codebook_size, int apply_ln, int impl, int16_t* out,
                              int32_t* out_i32, void* workspace, size_t workspace_bytes, void* stream) {
   B2T_REQUIRE(x && codebook && (out || out_i32) && workspace, B2T_ERR_ARG, "b2t_vq_argmin: null argument");
   B2T_REQUIRE(dim % 32 == 0 && dim >= 32 && ldx % 4 == 0 && ldx >= dim, B2T_ERR_ARG,
@@ -234,41 +267,73 @@ extern "C" int b2t_vq_argmin(const float* x, int ldx, int rows, int dim, const f
   B2T_REQUIRE(codebook_size >= 1 && codebook_size <= 32768, B2T_ERR_ARG,
               "b2t_vq_argmin: codebook_size must be in [1, 32768] for int16 tokens (got %d)", codebook_size);
   B2T_REQUIRE(!apply_ln || dim == 1024, B2T_ERR_ARG, "b2t_vq_argmin: fused LayerNorm needs dim == 1024");
-  B2T_REQUIRE(workspace_bytes >= b2t_vq_workspace_bytes(rows, dim, codebook_size), B2T_ERR_WORKSPACE,
-              "b2t_vq_argmin: workspace too small");
+  const bool tensor_ok = dim % 64 == 0;
+  B2T_REQUIRE(impl != B2T_IMPL_TENSOR || tensor_ok, B2T_ERR_ARG, "b2t_vq_argmin: tensor path needs dim %% 64 == 0");
   int rc = b2t_arch_ok();
   if (rc != B2T_OK) return rc;
   if (rows <= 0) return B2T_OK;
+  VqWs w = vq_carve(workspace, rows, dim, codebook_size);
+  B2T_REQUIRE(workspace_bytes >= w.total, B2T_ERR_WORKSPACE, "b2t_vq_argmin: workspace %zu < %zu", workspace_bytes, w.total);
   cudaStream_t st = (cudaStream_t)stream;
-  uint8_t* ws = (uint8_t*)workspace;
-  float* xn = (float*)ws;                 ws += align_up((size_t)rows * dim * 4, 256);
-  Cand* cand = (Cand*)ws;                 ws += align_up((size_t)rows * sizeof(Cand), 256);
-  float* hn = (float*)ws;                 ws += align_up((size_t)codebook_size * 4, 256);
-  float* cmax = (float*)ws;
-  unsigned int* nfb = (unsigned int*)(ws + 16);
+  const bool tensor = impl == B2T_IMPL_TENSOR || (impl == B2T_IMPL_AUTO && tensor_ok && codebook_size >= 64);
 
   const float* xs = x;
   int lds = ldx;
   if (apply_ln) {
-    vq_ln_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, ldx, xn, rows);
+    vq_ln_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, ldx, w.xn, rows);
     B2T_LAUNCH_CHECK();
-    xs = xn; lds = 1024;
+    xs = w.xn; lds = 1024;
   }
   if (half_norm == nullptr) {
-    half_norm_kernel<<<(codebook_size + 7) / 8, 256, 0, st>>>(codebook, codebook_size, dim, hn);
+    half_norm_kernel<<<(codebook_size + 7) / 8, 256, 0, st>>>(codebook, codebook_size, dim, w.hn);
     B2T_LAUNCH_CHECK();
   } else {
-    B2T_CUDA(cudaMemcpyAsync(hn, half_norm, (size_t)codebook_size * 4, cudaMemcpyDeviceToDevice, st));
+    B2T_CUDA(cudaMemcpyAsync(w.hn, half_norm, (size_t)codebook_size * 4, cudaMemcpyDeviceToDevice, st));
   }
-  max_reduce_kernel<<<1, 1024, 0, st>>>(hn, codebook_size, cmax);
+  max_reduce_kernel<<<1, 1024, 0, st>>>(w.hn, codebook_size, w.cmax);
   B2T_LAUNCH_CHECK();
-  B2T_CUDA(cudaMemsetAsync(nfb, 0, 4, st));
-  vq_scan_simt_kernel<<<(rows + 63) / 64, 256, 0, st>>>(xs, lds, rows, dim, codebook, hn, codebook_size, cand);
+  B2T_CUDA(cudaMemsetAsync(w.nfb, 0, 32, st));   // fallback counter + max observed error
+  int slices = 1;
+  float rel_eps;
+  if (tensor) {
+    if (w.kpad > codebook_size) {
+      fill_inf_kernel<<<(w.kpad - codebook_size + 255) / 256, 256, 0, st>>>(w.hn, codebook_size, w.kpad);
+      B2T_LAUNCH_CHECK();
+    }
+    split_rows_kernel<<<rows, 256, 0, st>>>(xs, lds, rows, dim, w.a2);
+    B2T_LAUNCH_CHECK();
+    split_rows_kernel<<<codebook_size, 256, 0, st>>>(codebook, dim, codebook_size, dim, w.c2);
+    B2T_LAUNCH_CHECK();
+    slices = w.slices;
+    rc = b2t_vq_scan_tensor(w.a2, w.c2, rows, codebook_size, w.kpad, dim, w.hn, w.parts, slices, st);
+    if (rc != B2T_OK) return rc;
+    // bf16x3 product: dropped terms lo*lo and the third mantissa piece, each <= 2^-16 |x_d c_d|, plus
+    // fp32 accumulation of 3D/16 MMA steps; 2^-14 leaves >= 8x head-room (checked by b2t_vq_debug_stats)
+    rel_eps = 6.103515625e-5f;
+  } else {
+    vq_scan_simt_kernel<<<(rows + 63) / 64, 256, 0, st>>>(xs, lds, rows, dim, codebook, w.hn, codebook_size, w.parts);
+    B2T_LAUNCH_CHECK();
+    // sequential fp32 FMA dot of length D: |err| <= D * 2^-24 * sum|x_d c_d|; 2x margin
+    rel_eps = 2.0f * (float)dim * 5.9604645e-8f;
+  }
+  vq_finalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(xs, lds, rows, dim, codebook, w.hn, codebook_size, w.parts,
+                                                     slices, rel_eps, w.cmax, out, out_i32, w.nfb, w.maxerr);
   B2T_LAUNCH_CHECK();
-  // fp32 FMA dot of length D: |err| <= ~D * 2^-24 * sum|x_d c_d| <= D*2^-24 * |x||c|; 8x margin
-  const float rel_eps = 8.0f * (float)dim * 5.9604645e-8f;
-  vq_finalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(xs, lds, rows, dim, codebook, hn, codebook_size, cand,
-                                                        rel_eps, cmax, out, out_i32, nfb);
-  B2T_LAUNCH_CHECK();
+  return B2T_OK;
+}
+
+// Test/diagnostic hook: after a b2t_vq_argmin on `workspace` has completed, returns the number of rows
+// that took the re-scan path and the largest observed |fast score - exact score| relative to the bound's
+// scale (|x| |c|max + 0.5 |c|max^2) together with the rel_eps the call certified with.
+extern "C" int b2t_vq_debug_stats(const void* workspace, int rows, int dim, int codebook_size,
+                                  unsigned int* n_fallback_host, float* max_rel_err_host) {
+  B2T_REQUIRE(workspace, B2T_ERR_ARG, "b2t_vq_debug_stats: null argument");
+  VqWs w = vq_carve(const_cast<void*>(workspace), rows, dim, codebook_size);
+  B2T_CUDA(cudaDeviceSynchronize());
+  unsigned int tmp[2] = {0, 0};
+  B2T_CUDA(cudaMemcpy(&tmp[0], w.nfb, 4, cudaMemcpyDeviceToHost));
+  B2T_CUDA(cudaMemcpy(&tmp[1], w.maxerr, 4, cudaMemcpyDeviceToHost));
+  if (n_fallback_host) *n_fallback_host = tmp[0];
+  if (max_rel_err_host) { float f; memcpy(&f, &tmp[1], 4); *max_rel_err_host = f; }
   return B2T_OK;
 }

@@ -22,7 +22,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR = 0, 1, 2
 EXPORTS = [
     'b2t_version', 'b2t_last_error', 'b2t_device_check', 'b2t_fbank_logmel', 'b2t_fbank_stats',
     'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_dwconv_ln_swish',
-    'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_semantic_create', 'b2t_semantic_destroy',
+    'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_vq_debug_stats', 'b2t_semantic_create', 'b2t_semantic_destroy',
     'b2t_semantic_set_tensor', 'b2t_semantic_workspace_bytes', 'b2t_semantic_encode',
     'b2t_last_launch_count', 'b2t_profile_enable', 'b2t_profile_read',
 ]
@@ -81,7 +81,8 @@ def load() -> C.CDLL:
     lib.b2t_dwconv_ln_swish.argtypes = [vp, vp, vp, vp, C.POINTER(Batch), vp, i32, vp]
     lib.b2t_vq_workspace_bytes.argtypes = [i32, i32, i32]
     lib.b2t_vq_workspace_bytes.restype = sz
-    lib.b2t_vq_argmin.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, sz, vp]
+    lib.b2t_vq_argmin.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.b2t_vq_debug_stats.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_uint), C.POINTER(C.c_float)]
     lib.b2t_semantic_create.argtypes = [i32, i32, i32]
     lib.b2t_semantic_create.restype = vp
     lib.b2t_semantic_destroy.argtypes = [vp]

@@ -107,8 +107,10 @@ def dwconv_ln_swish(x: torch.Tensor, w_dw: torch.Tensor, ln_w: torch.Tensor, ln_
 
 
 def vq_argmin(x: torch.Tensor, codebook: torch.Tensor, apply_ln: bool = False,
-              workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """x [M, D] fp32, codebook [K, D] fp32 -> (int16 [M], int32 [M])."""
+              workspace: Optional[torch.Tensor] = None, impl: int = L.IMPL_AUTO, stats: Optional[dict] = None
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x [M, D] fp32, codebook [K, D] fp32 -> (int16 [M], int32 [M]).  `stats` (dict) receives the number
+    of re-scanned rows and the largest observed fast-pass error (relative to the bound's scale)."""
     lib = L.load()
     L.require_device(x.device)
     M, D = x.shape
@@ -118,7 +120,11 @@ def vq_argmin(x: torch.Tensor, codebook: torch.Tensor, apply_ln: bool = False,
         workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
     o16 = torch.empty(M, dtype=torch.int16, device=x.device)
     o32 = torch.empty(M, dtype=torch.int32, device=x.device)
-    L.check(lib.b2t_vq_argmin(x.data_ptr(), x.stride(0), M, D, codebook.data_ptr(), None, K, int(apply_ln),
+    L.check(lib.b2t_vq_argmin(x.data_ptr(), x.stride(0), M, D, codebook.data_ptr(), None, K, int(apply_ln), impl,
                               o16.data_ptr(), o32.data_ptr(), workspace.data_ptr(), workspace.numel(),
                               L.stream_ptr()), 'vq_argmin')
+    if stats is not None:
+        nfb, err = C.c_uint(0), C.c_float(0)
+        L.check(lib.b2t_vq_debug_stats(workspace.data_ptr(), M, D, K, C.byref(nfb), C.byref(err)), 'vq_debug_stats')
+        stats['n_fallback'], stats['max_rel_err'] = nfb.value, err.value
     return o16, o32

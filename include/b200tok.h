@@ -152,13 +152,19 @@ int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float* ln_weight
 
 /* Nearest centroid (reference encoder.py:100-101 k-means, :180 VectorQuantize):
  * idx[r] = argmin_k |x_r - c_k|^2, first index on ties, written as int16.  If apply_ln != 0 the
- * affine-free LayerNorm of encoder.py:175-176 is applied to each row first.  Candidates from
- * the fast pass are re-checked in fp64, so the result equals the exact fp64 argmin.           */
+ * affine-free LayerNorm of encoder.py:175-176 is applied to each row first.  The fast pass (tensor
+ * cores: error-compensated bf16x3 distance GEMM with a fused top-3 epilogue — the distance matrix is
+ * never written) yields two candidates per row; they are re-scored in fp64 and rows the error bound
+ * cannot certify are re-scanned, so the result equals the exact fp64 argmin.                    */
 size_t b2t_vq_workspace_bytes(int rows, int dim, int codebook_size);
 int b2t_vq_argmin(const float* x, int ldx, int rows, int dim, const float* codebook,
                   const float* half_norm /* [K] 0.5*|c_k|^2 fp32, or NULL */, int codebook_size,
-                  int apply_ln, int16_t* out, int32_t* out_i32 /* optional */, void* workspace,
-                  size_t workspace_bytes, void* stream);
+                  int apply_ln, int impl /* b2t_impl: TENSOR = bf16x3 tcgen05 fast pass */, int16_t* out,
+                  int32_t* out_i32 /* optional */, void* workspace, size_t workspace_bytes, void* stream);
+/* Diagnostics of the last b2t_vq_argmin that used `workspace` (synchronises): rows that needed the
+ * re-scan path, and the largest observed fast-pass error relative to the certified bound's scale. */
+int b2t_vq_debug_stats(const void* workspace, int rows, int dim, int codebook_size,
+                       unsigned int* n_fallback_host, float* max_rel_err_host);
 
 /* ---- whole semantic encoder (reference Wav2VecBertEncoder.forward, encoder.py:163-186) ------- */
 typedef struct b2t_semantic_model b2t_semantic_model;

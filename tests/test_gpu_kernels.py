@@ -264,8 +264,10 @@ def test_dwconv_ln_swish(cuda_device, precision):
 
 
 # ---------------------------------------------------------------------------------------------- VQ
-@pytest.mark.parametrize('M,D,K', [(1000, 1024, 2048), (777, 1024, 1000), (300, 128, 1024), (64, 256, 1), (50, 64, 3)])
-def test_vq_argmin_bit_exact(cuda_device, M, D, K):
+@pytest.mark.parametrize('impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
+@pytest.mark.parametrize('M,D,K', [(1000, 1024, 2048), (777, 1024, 1000), (300, 128, 1024), (64, 256, 1), (50, 64, 3),
+                                   (4000, 1024, 16384)])
+def test_vq_argmin_bit_exact(cuda_device, M, D, K, impl):
     g = torch.Generator().manual_seed(M + K)
     x = torch.randn(M, D, generator=g)
     cb = torch.randn(K, D, generator=g)
@@ -273,24 +275,41 @@ def test_vq_argmin_bit_exact(cuda_device, M, D, K):
         cb[K - 5:] = cb[:5]                                  # duplicated centroids: first index must win
         x[:5] = cb[:5] + 1e-3 * torch.randn(5, D, generator=g)
     idx, tie = quantize.nearest_centroid(x, cb)
-    o16, o32 = ops.vq_argmin(x.to(cuda_device), cb.to(cuda_device))
+    stats = {}
+    o16, o32 = ops.vq_argmin(x.to(cuda_device), cb.to(cuda_device), impl=impl, stats=stats)
     torch.cuda.synchronize()
     assert torch.equal(o32.cpu().long()[~tie], idx[~tie])
     assert torch.equal(o16.cpu().long(), o32.cpu().long())
+    # the certified error bound must hold with head-room: observed fast-pass error / bound scale
+    bound = 6.103515625e-5 if impl == L.IMPL_TENSOR else 2.0 * D * 5.9604645e-8
+    assert stats['max_rel_err'] < bound / 4, stats
+    print(f'vq impl={impl} M={M} D={D} K={K}: re-scanned rows {stats["n_fallback"]}, '
+          f'max observed err {stats["max_rel_err"]:.2e} (bound {bound:.2e})')
 
 
-def test_vq_argmin_near_ties_and_layernorm(cuda_device):
+@pytest.mark.parametrize('impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
+def test_vq_argmin_near_ties_and_layernorm(cuda_device, impl):
     # rows placed (almost) on the bisector of two centroids: the fp64 re-check has to decide
     g = torch.Generator().manual_seed(5)
     cb = torch.randn(2048, 1024, generator=g)
     a, b = cb[torch.randint(0, 2048, (400,), generator=g)], cb[torch.randint(0, 2048, (400,), generator=g)]
     x = 0.5 * (a + b) + 1e-6 * torch.randn(400, 1024, generator=g)
     idx, tie = quantize.nearest_centroid(x, cb, tie_rel_margin=1e-12)
-    _, o32 = ops.vq_argmin(x.to(cuda_device), cb.to(cuda_device))
+    _, o32 = ops.vq_argmin(x.to(cuda_device), cb.to(cuda_device), impl=impl)
     assert torch.equal(o32.cpu().long()[~tie], idx[~tie])
+    # clusters of 4 nearly identical centroids: top-2 is not enough, the re-scan path must take over
+    cb2 = cb.clone()
+    for j in range(50):
+        cb2[4 * j + 1:4 * j + 4] = cb2[4 * j] + 1e-5 * torch.randn(3, 1024, generator=g)
+    x2 = cb2[0:200:4] + 0.05 * torch.randn(50, 1024, generator=g)
+    idx2, tie2 = quantize.nearest_centroid(x2, cb2, tie_rel_margin=1e-13)
+    stats = {}
+    _, o2 = ops.vq_argmin(x2.to(cuda_device), cb2.to(cuda_device), impl=impl, stats=stats)
+    assert torch.equal(o2.cpu().long()[~tie2], idx2[~tie2])
+    assert stats['n_fallback'] >= 40, stats
     # fused affine-free LayerNorm (reference encoder.py:175-176)
     h = torch.randn(500, 1024, generator=g) * 2 + 1
     emb = conformer.final_embedding(h)
-    idx2, tie2 = quantize.nearest_centroid(emb, cb)
-    _, o = ops.vq_argmin(h.to(cuda_device), cb.to(cuda_device), apply_ln=True)
-    assert (o.cpu().long()[~tie2] == idx2[~tie2]).float().mean() > 0.995
+    idx3, tie3 = quantize.nearest_centroid(emb, cb)
+    _, o = ops.vq_argmin(h.to(cuda_device), cb.to(cuda_device), apply_ln=True, impl=impl)
+    assert (o.cpu().long()[~tie3] == idx3[~tie3]).float().mean() > 0.995
