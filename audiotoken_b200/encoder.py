@@ -140,6 +140,18 @@ class Wav2VecBertEncoder(torch.nn.Module):
         """'gemm_impl' / 'attn_impl' (lib.IMPL_*), 'mel_bf16' (0/1)."""
         L.check(self.lib.b2t_semantic_set_tensor(self.handle, f'opt.{name}'.encode(), C.c_void_p(value)), name)
 
+    # ---- row bookkeeping used by the batched file loop -------------------------------------------
+    num_codebooks = 1
+
+    def rows_for(self, padded_samples: int) -> int:
+        """Rows the reference returns for a segment padded to `padded_samples` (T)."""
+        from .packing import padded_rows
+        return padded_rows(padded_samples)
+
+    def rows_for_tokens(self, n_tokens: int, padded_samples: int) -> int:
+        """Rows that have to be computed to save `n_tokens` tokens of a segment."""
+        return max(1, min(n_tokens, self.rows_for(padded_samples)))
+
     # ---- packed (ragged) entry point ------------------------------------------------------------
     def _workspace(self, plan: SemanticPlan) -> torch.Tensor:
         need = self.lib.b2t_semantic_workspace_bytes(self.handle, plan.total_rows, plan.total_frames, plan.n_clips)

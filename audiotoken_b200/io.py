@@ -1,0 +1,167 @@
+"""Host-side file plumbing around the encode path: WAV reading, segmentation rules, token writers.
+
+Mirrors the behaviour (not the code) of the reference's
+  * ``read_audio`` / ``convert_audio`` ............ audiotoken/utils.py:26-68  (mono mix-down, resample)
+  * ``AudioBatchDataset._iter_chunk`` ............. audiotoken/datasets.py:75-105 (chunking, 3200-sample rule)
+  * ``save_audio_tokens`` / ``save_rel_audio_tokens`` audiotoken/utils.py:199-225, 367-396 (on-disk layout)
+  * ``sanitize_path`` / ``find_audio_files`` ...... audiotoken/utils.py:342-353, 172-184
+
+On-disk contract: ``<outdir>/<name>.npy``, dtype int16, C order, shape ``(K, T_total)``; the tokens of
+successive chunks of one file are concatenated along axis 1, each chunk trimmed to
+``ceil(chunk_seconds * token_rate)`` tokens.  Unlike the reference (np.load + hstack + np.save per
+chunk) a file is written exactly once, through a temporary name and an atomic rename, so re-running is
+idempotent.  Only RIFF/WAV input is decoded here (no ffmpeg / torchcodec offline).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .configs import AUDIO_EXTS, MIN_SEGMENT_SAMPLES, AudioConfig
+
+
+def sanitize_path(path) -> str:
+    """expanduser, make absolute, resolve, mkdir -p (reference utils.py:342-353)."""
+    p = Path(path).expanduser()
+    if not p.is_absolute():
+        p = p.absolute()
+    p = p.resolve()
+    if not p.exists():
+        p.mkdir(parents=True, exist_ok=True)
+    return str(p)
+
+
+def find_audio_files(folder) -> List[str]:
+    out = []
+    for root, _dirs, files in os.walk(folder):
+        for f in files:
+            if f.lower().endswith(AUDIO_EXTS):
+                out.append(os.path.join(root, f))
+    return sorted(out)
+
+
+def wav_info(path) -> Tuple[int, int, int]:
+    """(sample_rate, num_frames, num_channels) from the RIFF header only."""
+    import wave
+    with wave.open(str(path), 'rb') as w:
+        return w.getframerate(), w.getnframes(), w.getnchannels()
+
+
+def convert_audio(audio: torch.Tensor, sample_rate: int, target_sample_rate: int) -> torch.Tensor:
+    """[C, L] -> mono [1, L'] at the target rate (reference utils.py:26-44)."""
+    c = audio.shape[0]
+    if c == 2:
+        audio = audio.mean(-2, keepdim=True)
+    elif c != 1:
+        raise RuntimeError("Only mono or stereo audio is supported")
+    if sample_rate != target_sample_rate:
+        import torchaudio
+        audio = torchaudio.transforms.Resample(sample_rate, target_sample_rate)(audio)
+    return audio
+
+
+def read_audio(path, model_sample_rate: int) -> torch.Tensor:
+    """WAV file -> fp32 [1, L] in [-1, 1] at `model_sample_rate` (reference utils.py:47-68)."""
+    if not str(path).lower().endswith('.wav'):
+        raise NotImplementedError(f'{path}: only .wav can be decoded offline (no ffmpeg/torchcodec in this image)')
+    from scipy.io import wavfile
+    sr, data = wavfile.read(str(path))
+    if data.dtype == np.int16:
+        x = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        x = data.astype(np.float32) / 2147483648.0
+    elif data.dtype == np.uint8:
+        x = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = data.astype(np.float32)
+    if x.ndim == 1:
+        x = x[None, :]
+    else:
+        x = x.T
+    audio = torch.from_numpy(np.ascontiguousarray(x))
+    assert audio.dim() == 2, f"Audio needs to be 2D array, provided {audio.dim()}D for {path}"
+    return convert_audio(audio, int(sr), model_sample_rate)
+
+
+def write_wav(path, wave: torch.Tensor, sample_rate: int) -> None:
+    """fp32 [L] or [1, L] in [-1, 1] -> PCM16 WAV (synthetic corpora for tests / benchmarks)."""
+    from scipy.io import wavfile
+    x = wave.reshape(-1).clamp(-1, 1).numpy()
+    wavfile.write(str(path), sample_rate, np.round(x * 32767.0).astype(np.int16))
+
+
+@dataclass
+class Segment:
+    """One independently encoded unit: a <= chunk_size slice of a file."""
+    file_name: str
+    chunk_index: int
+    wave: torch.Tensor            # fp32 [n], n >= MIN_SEGMENT_SAMPLES
+    config: AudioConfig
+
+
+def iter_segments(wave: torch.Tensor, file_name: str, sample_rate: int, token_rate: int,
+                  chunk_size: int) -> Iterator[Segment]:
+    """Chunking rules of the reference's dataset for one decoded file `wave` [1, L].
+
+    The reference first streams `chunk_size`-second chunks (utils.py:82-101), then cuts each chunk into
+    segments of chunk_size*sr samples (datasets.py:88-105) — i.e. one segment per chunk — skips a
+    segment shorter than 3200 samples and right-pads the rest; length_seconds is per chunk.
+    """
+    seg_len = int(chunk_size * sample_rate)
+    total = wave.shape[-1]
+    for ci, start in enumerate(range(0, total, seg_len)):
+        seg = wave[0, start:start + seg_len]
+        n = int(seg.shape[0])
+        if n < MIN_SEGMENT_SAMPLES:
+            continue
+        cfg = AudioConfig(file_name=file_name, start_idx=0, end_idx=min(seg_len, n),
+                          length_seconds=n / sample_rate, length_samples=n, model_token_rate=token_rate)
+        yield Segment(file_name, ci, seg, cfg)
+
+
+def token_path_flat(file_name: str, root_dir: str) -> str:
+    """reference save_audio_tokens: <root>/<basename up to the FIRST '.'>.npy (utils.py:202-203)."""
+    stem = file_name.split('/')[-1].split('.')[0]
+    return os.path.join(root_dir, f'{stem}.npy')
+
+
+def token_path_rel(file_name: str, root_dir: str, rel_dir: str) -> str:
+    """reference save_rel_audio_tokens: <root>/<relative dir>/<stem>.npy (utils.py:374-382)."""
+    rel = os.path.dirname(os.path.relpath(file_name, start=rel_dir))
+    stem = os.path.splitext(os.path.basename(file_name))[0]
+    return os.path.join(root_dir, rel, f'{stem}.npy')
+
+
+def save_tokens_atomic(path: str, chunks: Sequence[np.ndarray]) -> None:
+    """Concatenate per-chunk (K, T_i) int16 arrays along axis 1 and write <path> exactly once."""
+    arr = np.ascontiguousarray(np.hstack([np.asarray(c, dtype=np.int16) for c in chunks]))
+    os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+    tmp = f'{path}.tmp.{os.getpid()}'
+    with open(tmp, 'wb') as f:
+        np.save(f, arr)
+    os.replace(tmp, path)
+
+
+def save_audio_tokens(tokens, audio_pointer: AudioConfig, root_dir: str) -> None:
+    """Drop-in for the reference helper of the same name (utils.py:199-225): trim to length_tokens and
+    APPEND to an existing file along axis 1."""
+    t = tokens.cpu().numpy() if isinstance(tokens, torch.Tensor) else np.asarray(tokens)
+    t = t[:, :audio_pointer.length_tokens]
+    path = token_path_flat(audio_pointer.file_name, root_dir)
+    prev = [np.load(path)] if os.path.exists(path) else []
+    save_tokens_atomic(path, prev + [t])
+
+
+def save_rel_audio_tokens(tokens, audio_pointer: AudioConfig, root_dir: str, rel_dir: str) -> None:
+    """Drop-in for reference utils.py:367-396."""
+    t = tokens.cpu().numpy() if isinstance(tokens, torch.Tensor) else np.asarray(tokens)
+    t = t[:, :audio_pointer.length_tokens]
+    path = token_path_rel(audio_pointer.file_name, root_dir, rel_dir)
+    prev = [np.load(path)] if os.path.exists(path) else []
+    save_tokens_atomic(path, prev + [t])

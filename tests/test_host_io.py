@@ -1,0 +1,120 @@
+"""CPU: on-disk token layout, segmentation rules, sharding (incl. a 2-rank gloo run)."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from audiotoken_b200 import io as aio
+from audiotoken_b200.configs import AudioConfig, Tokenizers, num_codebooks_to_bandwidth, AcousticEncoderConfig
+from audiotoken_b200.sharding import lpt_shards, shard_files
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tokenizer_enum_and_configs():
+    assert Tokenizers('semantic_m') is Tokenizers.semantic_m and str(Tokenizers.acoustic) == 'acoustic'
+    assert [num_codebooks_to_bandwidth(k) for k in (2, 4, 8, 16)] == [1.5, 3, 6, 12]
+    assert AcousticEncoderConfig(bandwidth=12).num_codebooks == 16
+    assert AcousticEncoderConfig(bandwidth=1.5).num_codebooks == 2
+    cfg = AudioConfig(file_name='a.wav', length_seconds=7.3, model_token_rate=50)
+    assert cfg.length_tokens == math.ceil(7.3 * 50) == 365
+    with pytest.raises(ValueError):
+        AudioConfig(file_name='a.wav').length_tokens
+
+
+def test_sanitize_path(tmp_path, monkeypatch):
+    # reference test/utils.py: relative -> absolute, ~ expansion, mkdir
+    monkeypatch.chdir(tmp_path)
+    p = aio.sanitize_path('rel/dir')
+    assert os.path.isabs(p) and os.path.isdir(p)
+    monkeypatch.setenv('HOME', str(tmp_path))
+    q = aio.sanitize_path('~/x/y')
+    assert q == str((tmp_path / 'x' / 'y').resolve()) and os.path.isdir(q)
+
+
+def test_token_file_layout_and_append(tmp_path):
+    root = str(tmp_path)
+    cfg = AudioConfig(file_name='/data/in/spk1/clip.v2.wav', length_seconds=1.0, model_token_rate=50)
+    toks = torch.arange(2 * 60, dtype=torch.int16).reshape(2, 60)
+    aio.save_audio_tokens(toks, cfg, root)
+    path = os.path.join(root, 'clip.npy')                      # basename up to the FIRST '.'
+    a = np.load(path)
+    assert a.dtype == np.int16 and a.shape == (2, 50) and a.flags['C_CONTIGUOUS']
+    aio.save_audio_tokens(toks + 1, cfg, root)                 # second chunk of the same file: appended on axis 1
+    b = np.load(path)
+    assert b.shape == (2, 100) and np.array_equal(b[:, :50], a) and np.array_equal(b[:, 50:], (toks + 1)[:, :50].numpy())
+    aio.save_rel_audio_tokens(toks, cfg, root, '/data/in')
+    assert np.load(os.path.join(root, 'spk1', 'clip.v2.npy')).shape == (2, 50)
+    assert not [f for f in os.listdir(root) if '.tmp.' in f]
+
+
+def test_wav_roundtrip_and_segments(tmp_path):
+    sr = 16000
+    x = torch.sin(torch.arange(sr * 7 + 1234) / 20.0) * 0.5
+    p = str(tmp_path / 'a.wav')
+    aio.write_wav(p, x, sr)
+    assert aio.wav_info(p) == (sr, x.numel(), 1)
+    y = aio.read_audio(p, sr)
+    assert y.shape == (1, x.numel()) and float((y[0] - x).abs().max()) < 1e-4
+    segs = list(aio.iter_segments(y, p, sr, 50, chunk_size=3))
+    assert [s.wave.numel() for s in segs] == [48000, 48000, 16000 + 1234]      # 7 s + 1234 samples in 3 s chunks
+    assert [s.config.length_tokens for s in segs] == [150, 150, math.ceil((16000 + 1234) / 16000 * 50)]
+    # a trailing piece shorter than 3200 samples is skipped (reference datasets.py:95-97)
+    short = list(aio.iter_segments(y[:, :48000 + 3199], p, sr, 50, chunk_size=3))
+    assert len(short) == 1
+    stereo = torch.stack([x, -x * 0.5])
+    assert aio.convert_audio(stereo, sr, sr).shape == (1, x.numel())
+    with pytest.raises(RuntimeError):
+        aio.convert_audio(torch.zeros(3, 10), sr, sr)
+
+
+def test_lpt_shards_balance_and_partition():
+    rng = np.random.default_rng(0)
+    dur = rng.uniform(2, 30, size=1000)
+    for world in (1, 2, 4, 8):
+        shards = lpt_shards(dur, world)
+        assert sorted(i for s in shards for i in s) == list(range(1000))
+        loads = [dur[s].sum() for s in shards]
+        assert max(loads) - min(loads) <= 30.0
+    files = [f'f{i}.wav' for i in range(10)]
+    parts = [shard_files(files, list(range(10)), 3, r) for r in range(3)]
+    assert sorted(f for p in parts for f in p) == files
+    with pytest.raises(ValueError):
+        shard_files(files, list(range(10)), 2, 2)
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """world_size 2 on CPU (gloo): both ranks derive the same disjoint partition and agree on the totals."""
+    script = tmp_path / 'w.py'
+    script.write_text(f'''
+import os, sys, json
+sys.path.insert(0, {ROOT!r})
+import torch, torch.distributed as dist
+from audiotoken_b200.sharding import shard_files
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+files = [f"clip{{i:03d}}.wav" for i in range(101)]
+dur = [2 + (i * 37 % 29) for i in range(101)]
+mine = shard_files(files, dur, world, rank)
+out = [None] * world
+dist.all_gather_object(out, mine)
+load = torch.tensor([float(sum(dur[files.index(f)] for f in mine))])
+tot = load.clone(); dist.all_reduce(tot)
+mx = load.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+if rank == 0:
+    allf = sorted(f for part in out for f in part)
+    print(json.dumps(dict(ok=allf == sorted(files) and not set(out[0]) & set(out[1]), total=float(tot), max=float(mx))))
+dist.destroy_process_group()
+''')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29731', str(script)],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = [l for l in r.stdout.splitlines() if l.startswith('{')][-1]
+    res = json.loads(line)
+    assert res['ok'] and res['max'] <= res['total'] / 2 + 30
