@@ -73,8 +73,12 @@ def test_encode_single_inputs(cuda_device, tmp_path):
     aio.write_wav(str(p), x[0], SR)
     t3 = tok.encode(p)
     assert t3.shape == t.shape
-    t4 = tok.encode(p, chunk_size=1)
-    assert t4.dim() == 2 and t4.shape[0] == 1                 # [K, T_total] when chunked (reference core.py:175-179)
+    with pytest.raises(ValueError):
+        tok.encode(p, chunk_size=1)                           # trailing 37-sample chunk: no frame fits (the reference fails too)
+    p2 = tmp_path / 'y.wav'
+    aio.write_wav(str(p2), synthetic_waveform(4, 40000, SR), SR)
+    t4 = tok.encode(p2, chunk_size=1)
+    assert t4.dim() == 2 and t4.shape == (1, 50 + 50 + 24)    # [K, T_total] when chunked (reference core.py:175-179)
     with pytest.raises(AssertionError):
         tok.encode(torch.zeros(2, 16000))
     with pytest.raises(NotImplementedError):
