@@ -1,0 +1,227 @@
+"""Acoustic tokenizer: host side of the EnCodec 24 kHz encode path.
+
+Mirror of the reference's ``AcousticEncoder`` (audiotoken/encoder.py:29-57): called as
+``encoder(input_batch[B, L], attention_mask) -> int16 [B, n_q, ceil(L/320)]`` (the mask is ignored, as in the
+reference), plus ``encode_packed`` for ragged batches.  Weight preparation (weight-norm folding, tap-major
+reordering), batch planning and buffer ownership live here; all arithmetic is in libb200tok.so
+(csrc/acoustic.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .configs import AcousticEncoderConfig
+from .weights import SEANET_CONVS, synthetic_encodec_state_dict, weight_norm_weight
+
+STRIDES = (2, 4, 5, 8)
+HOP = 320
+TILE = 64
+
+
+@dataclass
+class AcousticPlan:
+    n_clips: int
+    wave_off: np.ndarray          # int64 [n]
+    true_len: np.ndarray          # int32 [n]
+    lens: List[np.ndarray]        # 5 x int32 [n]
+    offs: List[np.ndarray]        # 5 x int32 [n+1]
+    tile_clip: List[np.ndarray]
+    tile_t0: List[np.ndarray]
+    order: np.ndarray             # int32 [n]
+    active: np.ndarray            # int32 [t_max]
+
+    @property
+    def frames(self) -> np.ndarray:
+        return self.lens[4]
+
+    @property
+    def total_frames(self) -> int:
+        return int(self.offs[4][-1])
+
+
+def plan_acoustic(true_lens: Sequence[int], wave_offsets: Sequence[int], virt_lens: Sequence[int]) -> AcousticPlan:
+    """true_lens[i] samples are read from the wave buffer, the clip behaves as a signal of virt_lens[i]
+    samples (zeros after true_len) — the reference's right zero-padding (datasets.py:99-103)."""
+    n = len(true_lens)
+    tl = np.asarray(true_lens, dtype=np.int64)
+    vl = np.asarray(virt_lens, dtype=np.int64)
+    if n == 0 or np.any(tl < 1) or np.any(vl < tl):
+        raise ValueError('clips must be non-empty and virt_len >= true_len')
+    lens = [vl]
+    for s in STRIDES:
+        lens.append(-(-lens[-1] // s))
+    offs, tc, tt = [], [], []
+    for l in range(5):
+        o = np.zeros(n + 1, dtype=np.int64)
+        o[1:] = np.cumsum(lens[l])
+        if o[-1] >= 2 ** 31:
+            raise ValueError('batch too large for int32 offsets')
+        offs.append(o.astype(np.int32))
+        cl, t0 = [], []
+        for i in range(n):
+            t = np.arange(0, lens[l][i], TILE, dtype=np.int32)
+            cl.append(np.full(t.shape, i, dtype=np.int32))
+            t0.append(t)
+        tc.append(np.concatenate(cl))
+        tt.append(np.concatenate(t0))
+    order = np.argsort(-lens[4], kind='stable').astype(np.int32)
+    t_max = int(lens[4].max())
+    sorted_len = lens[4][order]
+    active = (sorted_len[None, :] > np.arange(t_max)[:, None]).sum(axis=1).astype(np.int32)
+    return AcousticPlan(n, np.asarray(wave_offsets, dtype=np.int64), tl.astype(np.int32),
+                        [x.astype(np.int32) for x in lens], offs, tc, tt, order, active)
+
+
+class DeviceAcousticBatch:
+    def __init__(self, plan: AcousticPlan, device):
+        arrays = [plan.true_len] + plan.lens + plan.offs + plan.tile_clip + plan.tile_t0 + [plan.order]
+        n64 = plan.wave_off.size
+        total = 2 * n64 + sum(a.size for a in arrays)
+        host = torch.empty(total, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        hv = host.numpy()
+        hv[:2 * n64] = plan.wave_off.view(np.int32)
+        off, ptrs = 2 * n64, []
+        for a in arrays:
+            hv[off:off + a.size] = a
+            ptrs.append(off)
+            off += a.size
+        self.host = host
+        self.dev = host.to(device, non_blocking=True)
+        base = self.dev.data_ptr()
+        p = [base + 4 * o for o in ptrs]
+        b = L.AcousticBatch()
+        b.n_clips = plan.n_clips
+        b.t_max = int(plan.active.size)
+        for l in range(5):
+            b.total[l] = int(plan.offs[l][-1])
+            b.n_tiles[l] = int(plan.tile_clip[l].size)
+            b.len[l] = p[1 + l]
+            b.off[l] = p[6 + l]
+            b.tile_clip[l] = p[11 + l]
+            b.tile_t0[l] = p[16 + l]
+        b.wave_off = base
+        b.true_len = p[0]
+        b.order = p[21]
+        self.c = b
+        self.active = np.ascontiguousarray(plan.active)
+
+    def byref(self):
+        return C.byref(self.c)
+
+
+class AcousticWeights:
+    """HF EncodecModel-named state dict -> fp32 device tensors for csrc/acoustic.cu."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device, n_q_total: int):
+        t: Dict[str, torch.Tensor] = {}
+        for i, (name, cin, cout, k, _s) in enumerate(SEANET_CONVS):
+            w = weight_norm_weight(sd, name).float()                       # [cout, cin, k]
+            w = w.permute(0, 2, 1).reshape(cout, k * cin)                  # tap-major: index = tap * cin + ci
+            kpad = (k * cin + 15) // 16 * 16
+            wp = torch.zeros(cout, kpad)
+            wp[:, :k * cin] = w
+            t[f'conv{i}.w'] = wp.to(device).contiguous()
+            t[f'conv{i}.b'] = sd[name + '.bias'].float().to(device).contiguous()
+        for layer in range(2):
+            p = 'encoder.layers.13.lstm.'
+            t[f'lstm{layer}.w_ih'] = sd[p + f'weight_ih_l{layer}'].float().to(device).contiguous()
+            t[f'lstm{layer}.w_hh'] = sd[p + f'weight_hh_l{layer}'].float().to(device).contiguous()
+            t[f'lstm{layer}.b'] = (sd[p + f'bias_ih_l{layer}'] + sd[p + f'bias_hh_l{layer}']).float().to(device).contiguous()
+        cb = torch.stack([sd[f'quantizer.layers.{q}.codebook.embed'].float() for q in range(n_q_total)])
+        hn = (0.5 * (cb.double() ** 2).sum(-1))
+        t['rvq.codebooks'] = cb.to(device).contiguous()
+        t['rvq.half_norm'] = hn.float().to(device).contiguous()
+        t['rvq.cmax_half'] = hn.max(dim=1).values.float().to(device).contiguous()
+        self.tensors = t
+
+
+class AcousticEncoder(torch.nn.Module):
+    """Same call shape as reference audiotoken/encoder.py:29-57; fp32 numerics (the reference's CPU path)."""
+
+    max_rows_per_batch = 75 * 1200          # frames per ragged batch (~26 GB of fp32 activations)
+
+    def __init__(self, config: Optional[AcousticEncoderConfig] = None, device: str = 'cuda:0',
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0, **_unused):
+        super().__init__()
+        self.config = config if config is not None else AcousticEncoderConfig()
+        self.device = torch.device(device)
+        L.require_device(self.device)
+        self.lib = L.load()
+        self.num_codebooks = self.config.num_codebooks           # floor(bw*1000 / (10*75))
+        if state_dict is None:
+            state_dict = synthetic_encodec_state_dict(seed)
+        n_total = sum(1 for k in state_dict if k.endswith('codebook.embed'))
+        assert self.num_codebooks <= n_total
+        with torch.cuda.device(self.device):
+            self.weights = AcousticWeights(state_dict, self.device, n_total)
+            self.handle = self.lib.b2t_acoustic_create()
+            for name, t in self.weights.tensors.items():
+                L.check(self.lib.b2t_acoustic_set_tensor(self.handle, name.encode(), t.data_ptr()), name)
+        self._ws: Optional[torch.Tensor] = None
+        self.last_launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.b2t_acoustic_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def rows_for(self, padded_samples: int) -> int:
+        return -(-padded_samples // HOP)
+
+    def rows_for_tokens(self, n_tokens: int, padded_samples: int) -> int:
+        return max(1, min(n_tokens, self.rows_for(padded_samples)))
+
+    def encode_plan(self, wave: torch.Tensor, plan: AcousticPlan, want_emb: bool = False):
+        """-> codes int16 [n_q, total_frames] (and fp32 embeddings [total_frames, 128])."""
+        assert wave.is_cuda and wave.dtype == torch.float32 and wave.is_contiguous()
+        with torch.cuda.device(self.device):
+            db = DeviceAcousticBatch(plan, self.device)
+            need = self.lib.b2t_acoustic_workspace_bytes(db.byref())
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(int(need * 1.05) + 1024, dtype=torch.uint8, device=self.device)
+            codes = torch.empty(self.num_codebooks, plan.total_frames, dtype=torch.int16, device=self.device)
+            emb = torch.empty(plan.total_frames, 128, device=self.device) if want_emb else None
+            L.check(self.lib.b2t_acoustic_encode(self.handle, wave.data_ptr(), db.byref(), self.num_codebooks,
+                                                 self._ws.data_ptr(), self._ws.numel(), codes.data_ptr(), L.ptr(emb),
+                                                 db.active.ctypes.data, L.stream_ptr()), 'b2t_acoustic_encode')
+            self.last_launches = self.lib.b2t_last_launch_count()
+            self._keep = db
+        return codes, emb
+
+    def forward(self, input_batch: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, want_emb: bool = False):
+        """input_batch [B, L] fp32 -> int16 [B, n_q, ceil(L/320)]; attention_mask is ignored (encoder.py:44)."""
+        assert input_batch.dim() == 2
+        B, Lp = input_batch.shape
+        wave = input_batch.to(self.device, torch.float32).contiguous()
+        plan = plan_acoustic([Lp] * B, np.arange(B, dtype=np.int64) * Lp, [Lp] * B)
+        codes, emb = self.encode_plan(wave.view(-1), plan, want_emb)
+        T = plan.total_frames // B
+        out = codes.view(self.num_codebooks, B, T).transpose(0, 1).contiguous()
+        if want_emb:
+            return out, emb.view(B, T, 128).transpose(1, 2)
+        return out
+
+    def encode_packed(self, clips: Sequence[torch.Tensor], padded_samples, rows: Optional[Sequence[int]] = None
+                      ) -> List[torch.Tensor]:
+        """Ragged batch -> list of int16 [n_q, rows_i]; clip i is zero-extended to rows_i * 320 samples."""
+        lengths = [int(c.numel()) for c in clips]
+        if rows is None:
+            rows = [-(-n // HOP) for n in lengths]
+        virt = [max(r * HOP, n) for r, n in zip(rows, lengths)]
+        offs = np.zeros(len(clips), dtype=np.int64)
+        offs[1:] = np.cumsum(lengths)[:-1]
+        wave = torch.cat([c.reshape(-1).to(torch.float32) for c in clips]).to(self.device)
+        plan = plan_acoustic(lengths, offs, virt)
+        codes, _ = self.encode_plan(wave, plan)
+        fo = plan.offs[4]
+        return [codes[:, fo[i]:fo[i] + rows[i]] for i in range(len(clips))]

@@ -120,7 +120,7 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
     """The batched file loop: read -> segment -> ragged batches -> encode -> one .npy per file."""
     t0 = time.time()
     pad = int(chunk_size * sample_rate)
-    row_budget = max(1, batch_size) * encoder.rows_for(pad)
+    row_budget = min(max(1, batch_size) * encoder.rows_for(pad), getattr(encoder, 'max_rows_per_batch', 1 << 30))
 
     def load(path):
         try:

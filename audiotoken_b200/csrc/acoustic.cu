@@ -1,0 +1,434 @@
+// Acoustic path: EnCodec 24 kHz SEANet encoder + 2-layer LSTM + residual VQ
+// (reference audiotoken/encoder.py:44-57 -> third-party `encodec`; architecture as mirrored by
+//  transformers models/encodec/modeling_encodec.py:82-176, 222-313, 364-438).
+//
+// Round-1 implementation: fp32 CUDA-core kernels (the reference's CPU numerics, BASELINE config 1),
+// channels-last activations, ragged clips:
+//   seanet_conv_kernel : causal strided conv as an implicit GEMM (64x64x16 tiles).  The A-operand gather
+//                        applies the reflect left padding, the reflect "extra" right padding and the
+//                        short-input rule of EncodecConv1d._pad1d on the fly (no padded copies), an
+//                        optional ELU on the input, bias and an optional residual add.
+//   lstm_step_kernel   : one time step of one LSTM layer for all still-active clips (clips sorted by
+//                        length, so the active set is a prefix); gate GEMM h.W_hh^T + fused cell update.
+//   rvq_kernel         : all n_q residual-VQ stages for 64 frames per block; the residual stays in shared
+//                        memory, scores are never written out, every stage's winner is re-checked in fp64.
+#include <map>
+#include <string>
+#include <vector>
+#include "vq_cand.cuh"
+
+void b2t_reset_launch_count();
+
+namespace {
+
+constexpr int kLevels = 5;
+
+B2T_DEVICE float eluf(float x) { return x > 0.f ? x : expm1f(x); }
+
+// index into a length-`len` signal for padded position j in [-padL, len + padR)
+// (F.pad(mode='reflect') with the zero-extension of short inputs); -1 = zero
+B2T_DEVICE int reflect_index(int j, int len, int padL, int padR) {
+  const int maxpad = padL > padR ? padL : padR;
+  const int le = len <= maxpad ? maxpad + 1 : len;
+  int i = j < 0 ? -j : (j < le ? j : 2 * (le - 1) - j);
+  return (i >= 0 && i < len) ? i : -1;
+}
+
+struct ConvArgs {
+  const float* in; int cin;
+  const float* w; int kdim_pad;          // [cout][kdim_pad], k index = tap * cin + ci
+  const float* bias; float* out; int cout;
+  const float* resid;                    // [rows_out, cout] or null
+  int k, s, elu_in;
+  const int32_t* in_off; const int32_t* in_len; const int32_t* out_off; const int32_t* out_len;
+  const int32_t* tile_clip; const int32_t* tile_t0;
+  const int64_t* wave_off; const int32_t* true_len;   // layer 0 only (in = waveform)
+};
+
+__global__ void __launch_bounds__(256)
+seanet_conv_kernel(ConvArgs a) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int clip = a.tile_clip[blockIdx.y], t0 = a.tile_t0[blockIdx.y];
+  const int n0 = blockIdx.x * 64;
+  const int in_len = a.in_len[clip], out_len = a.out_len[clip];
+  const int padL = a.k - a.s;
+  const int padR = out_len * a.s - in_len;           // "extra" padding: ceil(len/s)*s - len
+  const long long in_base = a.wave_off ? (long long)a.wave_off[clip] : (long long)a.in_off[clip] * a.cin;
+  const int valid_len = a.true_len ? a.true_len[clip] : in_len;   // samples >= true_len are zeros
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int t = t0 + lr;
+  float acc[4][4] = {};
+  const int kdim = a.k * a.cin;
+  for (int k0 = 0; k0 < a.kdim_pad; k0 += 16) {
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t < out_len) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kidx = k0 + lk + i;
+        if (kidx < kdim) {
+          const int tap = kidx / a.cin, ci = kidx - tap * a.cin;
+          const int src = reflect_index(t * a.s - padL + tap, in_len, padL, padR);
+          if (src >= 0 && src < valid_len) {
+            float v = a.in[in_base + (long long)src * a.cin + ci];
+            av[i] = a.elu_in ? eluf(v) : v;
+          }
+        }
+      }
+    }
+    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + lr < a.cout) wv = *reinterpret_cast<const float4*>(a.w + (size_t)(n0 + lr) * a.kdim_pad + k0 + lk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[lk + i][lr] = av[i];
+    Ws[lk][lr] = wv.x; Ws[lk + 1][lr] = wv.y; Ws[lk + 2][lr] = wv.z; Ws[lk + 3][lr] = wv.w;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 x4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float ar[4] = {x4.x, x4.y, x4.z, x4.w}, wr[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int out_base = a.out_off[clip];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tt = t0 + ty * 4 + i;
+    if (tt >= out_len) continue;
+    const size_t row = (size_t)(out_base + tt) * a.cout;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < a.cout) {
+        float v = acc[i][j] + a.bias[n];
+        if (a.resid) v += a.resid[row + n];
+        a.out[row + n] = v;
+      }
+    }
+  }
+}
+
+// One LSTM time step.  Block = 32 clips x 32 hidden units (x 4 gates); 256 threads.
+// gates[b, g*512 + j] = xg[row_b, g*512 + j] + sum_d h_prev[b, d] * w_hh[g*512 + j, d]     (i, f, g, o)
+__global__ void __launch_bounds__(256)
+lstm_step_kernel(const float* __restrict__ xg, const float* __restrict__ w_hh, const float* __restrict__ h_prev,
+                 float* __restrict__ h_next, float* __restrict__ c_state, float* __restrict__ out_seq,
+                 const float* __restrict__ skip, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ off4, int t, int n_active) {
+  __shared__ float As[16][32 + 4];     // h_prev tile  [k][clip]
+  __shared__ float Ws[16][128 + 4];    // w_hh tile    [k][gate-row]
+  __shared__ float G[32][128 + 1];
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int ty = tid >> 5, tx = tid & 31;          // 8 x 32: thread -> clips ty*4..+3, gate-rows tx*4..+3
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < 512; k0 += 16) {
+    if (tid < 128) {                                 // 32 clips x 16 k = 512 floats = 128 float4
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 + r < n_active && t > 0) v = *reinterpret_cast<const float4*>(h_prev + (size_t)(b0 + r) * 512 + k0 + kq);
+      As[kq][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {                 // 128 gate-rows x 16 k = 512 float4
+      const int idx = tid + it * 256;
+      const int r = idx >> 2, kq = (idx & 3) * 4;
+      const int grow = (r >> 5) * 512 + j0 + (r & 31);     // local row r = gate*32 + jj
+      const float4 v = *reinterpret_cast<const float4*>(w_hh + (size_t)grow * 512 + k0 + kq);
+      Ws[kq][r] = v.x; Ws[kq + 1][r] = v.y; Ws[kq + 2][r] = v.z; Ws[kq + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 x4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float ar[4] = {x4.x, x4.y, x4.z, x4.w}, wr[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) G[ty * 4 + i][tx * 4 + j] = acc[i][j];
+  __syncthreads();
+  // cell update: 32 clips x 32 units = 1024 pairs, 4 per thread
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int p = tid + it * 256;
+    const int bl = p >> 5, jj = p & 31;
+    const int b = b0 + bl;
+    if (b >= n_active) continue;
+    const int clip = order[b];
+    const size_t row = (size_t)(off4[clip] + t);
+    const float* xr = xg + row * 2048 + j0 + jj;
+    const float gi = G[bl][jj] + xr[0], gf = G[bl][32 + jj] + xr[512];
+    const float gg = G[bl][64 + jj] + xr[1024], go = G[bl][96 + jj] + xr[1536];
+    const float si = 1.0f / (1.0f + expf(-gi)), sf = 1.0f / (1.0f + expf(-gf)), so = 1.0f / (1.0f + expf(-go));
+    const size_t sidx = (size_t)b * 512 + j0 + jj;
+    const float cprev = t > 0 ? c_state[sidx] : 0.f;
+    const float c = sf * cprev + si * tanhf(gg);
+    const float h = so * tanhf(c);
+    c_state[sidx] = c;
+    h_next[sidx] = h;
+    const size_t oidx = row * 512 + j0 + jj;
+    out_seq[oidx] = skip ? h + skip[oidx] : h;
+  }
+}
+
+// Residual VQ, all stages, 64 frames per block.
+struct RvqSmem {
+  float rT[128][64 + 4];      // residual, transposed [d][row]
+  float eT[16][64 + 4];       // codebook chunk, transposed [k][code]
+  Cand merge[64][16];
+  int winner[64];
+};
+
+__global__ void __launch_bounds__(256)
+rvq_kernel(const float* __restrict__ emb, int rows, const float* __restrict__ codebooks /*[n_q][1024][128]*/,
+           const float* __restrict__ half_norm /*[n_q][1024]*/, const float* __restrict__ cmax_half /*[n_q]*/,
+           int n_q, int16_t* __restrict__ codes /*[n_q][rows]*/) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  RvqSmem& s = *reinterpret_cast<RvqSmem*>(smem_raw);
+  const int tid = threadIdx.x, m0 = blockIdx.x * 64;
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int i = tid; i < 64 * 128; i += 256) {
+    const int r = i >> 7, d = i & 127;
+    s.rT[d][r] = (m0 + r < rows) ? emb[(size_t)(m0 + r) * 128 + d] : 0.f;
+  }
+  __syncthreads();
+  for (int q = 0; q < n_q; ++q) {
+    const float* E = codebooks + (size_t)q * 1024 * 128;
+    const float* hn = half_norm + (size_t)q * 1024;
+    Cand loc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) loc[i] = cand_empty();
+    for (int n0 = 0; n0 < 1024; n0 += 64) {
+      float acc[4][4] = {};
+      for (int k0 = 0; k0 < 128; k0 += 16) {
+        {
+          const int r = tid >> 2, kq = (tid & 3) * 4;
+          const float4 v = *reinterpret_cast<const float4*>(E + (size_t)(n0 + r) * 128 + k0 + kq);
+          s.eT[kq][r] = v.x; s.eT[kq + 1][r] = v.y; s.eT[kq + 2][r] = v.z; s.eT[kq + 3][r] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          float4 x4 = *reinterpret_cast<const float4*>(&s.rT[k0 + kk][ty * 4]);
+          float4 w4 = *reinterpret_cast<const float4*>(&s.eT[kk][tx * 4]);
+          const float ar[4] = {x4.x, x4.y, x4.z, x4.w}, wr[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int code = n0 + tx * 4 + j;
+        const float h = __ldg(hn + code);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cand_insert_ordered(loc[i], acc[i][j] - h, code);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s.merge[ty * 4 + i][tx] = loc[i];
+    __syncthreads();
+    if (tid < 64) {
+      Cand c = cand_empty();
+      for (int u = 0; u < 16; ++u) cand_merge(c, s.merge[tid][u]);
+      // fp32 dot of length 128: |err| <= 128 * 2^-24 * |r||e| ; 2x margin
+      double rr = 0.0;
+      for (int d = 0; d < 128; ++d) rr += (double)s.rT[d][tid] * (double)s.rT[d][tid];
+      const float ch = cmax_half[q];
+      const float delta = 2.0f * 128.0f * 5.9604645e-8f * ((float)sqrt(rr) * sqrtf(2.0f * ch) + ch);
+      int best;
+      if (!(c.v3 >= c.v1 - 2.0f * delta)) {
+        double d1 = 0.0, d2 = 0.0;
+        const float* e1 = E + (size_t)c.i1 * 128;
+        const float* e2 = E + (size_t)c.i2 * 128;
+        for (int d = 0; d < 128; ++d) {
+          const double r = (double)s.rT[d][tid];
+          const double a1 = r - (double)e1[d], a2 = r - (double)e2[d];
+          d1 += a1 * a1; d2 += a2 * a2;
+        }
+        best = (d2 < d1 || (d2 == d1 && c.i2 < c.i1)) ? c.i2 : c.i1;
+      } else {
+        float run = -INFINITY;
+        double bd = INFINITY;
+        best = 0;
+        for (int code = 0; code < 1024; ++code) {
+          const float* e = E + (size_t)code * 128;
+          float a = 0.f;
+          for (int d = 0; d < 128; ++d) a = fmaf(s.rT[d][tid], e[d], a);
+          a -= hn[code];
+          if (a >= run - 2.0f * delta) {
+            double dd = 0.0;
+            for (int d = 0; d < 128; ++d) { const double t_ = (double)s.rT[d][tid] - (double)e[d]; dd += t_ * t_; }
+            if (dd < bd) { bd = dd; best = code; }
+          }
+          run = fmaxf(run, a);
+        }
+      }
+      s.winner[tid] = best;
+      if (m0 + tid < rows) codes[(size_t)q * rows + m0 + tid] = (int16_t)best;
+    }
+    __syncthreads();
+    // residual update in fp32, as the reference: r = r - E[idx]
+    for (int i = tid; i < 64 * 128; i += 256) {
+      const int r = i >> 7, d = i & 127;
+      s.rT[d][r] -= E[(size_t)s.winner[r] * 128 + d];
+    }
+    __syncthreads();
+  }
+}
+
+struct ConvSpec { int cin, cout, k, s; };
+const ConvSpec kConvs[18] = {
+    {1, 32, 7, 1},   {32, 16, 3, 1},   {16, 32, 1, 1},   {32, 32, 1, 1},   {32, 64, 4, 2},
+    {64, 32, 3, 1},  {32, 64, 1, 1},   {64, 64, 1, 1},   {64, 128, 8, 4},  {128, 64, 3, 1},
+    {64, 128, 1, 1}, {128, 128, 1, 1}, {128, 256, 10, 5}, {256, 128, 3, 1}, {128, 256, 1, 1},
+    {256, 256, 1, 1}, {256, 512, 16, 8}, {512, 128, 7, 1}};
+
+size_t align_up_a(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct b2t_acoustic_model {
+  std::map<std::string, const void*> t;
+};
+
+extern "C" b2t_acoustic_model* b2t_acoustic_create(void) { return new b2t_acoustic_model(); }
+extern "C" void b2t_acoustic_destroy(b2t_acoustic_model* m) { delete m; }
+extern "C" int b2t_acoustic_set_tensor(b2t_acoustic_model* m, const char* name, const void* ptr) {
+  B2T_REQUIRE(m && name && ptr, B2T_ERR_ARG, "b2t_acoustic_set_tensor: null argument");
+  m->t[name] = ptr;
+  return B2T_OK;
+}
+
+namespace {
+struct AcWs {
+  float* a[kLevels];   // level input / block output (C = 32,64,128,256,512)
+  float* h[4];         // residual-block hidden (C/2)
+  float* y[4];         // residual-block output (C)
+  float* xg; float* s1; float* s2; float* emb; float* hA; float* hB; float* c;
+  size_t total;
+};
+AcWs ac_carve(void* base, const b2t_acoustic_batch* b) {
+  AcWs w;
+  uint8_t* p = (uint8_t*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p ? (void*)(p + off) : nullptr; off += align_up_a(bytes, 256); return (float*)r; };
+  const int ch[kLevels] = {32, 64, 128, 256, 512};
+  for (int l = 0; l < kLevels; ++l) w.a[l] = take((size_t)b->total[l] * ch[l] * 4);
+  for (int l = 0; l < 4; ++l) { w.h[l] = take((size_t)b->total[l] * (ch[l] / 2) * 4); w.y[l] = take((size_t)b->total[l] * ch[l] * 4); }
+  const size_t t4 = b->total[4];
+  w.xg = take(t4 * 2048 * 4); w.s1 = take(t4 * 512 * 4); w.s2 = take(t4 * 512 * 4); w.emb = take(t4 * 128 * 4);
+  w.hA = take((size_t)b->n_clips * 512 * 4); w.hB = take((size_t)b->n_clips * 512 * 4); w.c = take((size_t)b->n_clips * 512 * 4);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* b) {
+  if (!b) return 0;
+  return ac_carve(nullptr, b).total;
+}
+
+extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic_batch* b,
+                                   int n_q, void* workspace, size_t workspace_bytes, int16_t* codes,
+                                   float* emb_out, const int32_t* active_host, void* stream) {
+  B2T_REQUIRE(m && wave && b && workspace && codes && active_host, B2T_ERR_ARG, "b2t_acoustic_encode: null argument");
+  B2T_REQUIRE(n_q >= 1 && n_q <= 32, B2T_ERR_ARG, "b2t_acoustic_encode: n_q must be in [1, 32]");
+  int rc = b2t_arch_ok();
+  if (rc != B2T_OK) return rc;
+  b2t_reset_launch_count();
+  if (b->n_clips <= 0 || b->total[4] <= 0) return B2T_OK;
+  AcWs w = ac_carve(workspace, b);
+  B2T_REQUIRE(workspace_bytes >= w.total, B2T_ERR_WORKSPACE, "b2t_acoustic_encode: workspace %zu < %zu", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool missing = false;
+  std::string miss;
+  auto T = [&](const std::string& n) -> const float* {
+    auto it = m->t.find(n);
+    if (it == m->t.end()) { if (!missing) miss = n; missing = true; return nullptr; }
+    return (const float*)it->second;
+  };
+  auto conv = [&](int ci, int lin, int lout, const float* in, float* out, const float* resid, int elu) -> int {
+    const ConvSpec& cs = kConvs[ci];
+    ConvArgs a{};
+    a.in = in; a.cin = cs.cin; a.w = T("conv" + std::to_string(ci) + ".w"); a.bias = T("conv" + std::to_string(ci) + ".b");
+    B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_encode: tensor '%s' not set", miss.c_str());
+    a.kdim_pad = (cs.k * cs.cin + 15) / 16 * 16;
+    a.out = out; a.cout = cs.cout; a.resid = resid; a.k = cs.k; a.s = cs.s; a.elu_in = elu;
+    a.in_off = b->off[lin]; a.in_len = b->len[lin]; a.out_off = b->off[lout]; a.out_len = b->len[lout];
+    a.tile_clip = b->tile_clip[lout]; a.tile_t0 = b->tile_t0[lout];
+    a.wave_off = (ci == 0) ? b->wave_off : nullptr;
+    a.true_len = (ci == 0) ? b->true_len : nullptr;
+    if (b->n_tiles[lout] <= 0) return B2T_OK;
+    dim3 grid((cs.cout + 63) / 64, b->n_tiles[lout]);
+    seanet_conv_kernel<<<grid, 256, 0, st>>>(a);
+    B2T_LAUNCH_CHECK();
+    return B2T_OK;
+  };
+#define RUN(call) do { int rc__ = (call); if (rc__ != B2T_OK) return rc__; } while (0)
+  // conv0, then 4 x (residual block, ELU + strided conv)
+  RUN(conv(0, 0, 0, wave, w.a[0], nullptr, 0));
+  for (int l = 0; l < 4; ++l) {
+    const int c0 = 1 + 4 * l;
+    RUN(conv(c0, l, l, w.a[l], w.h[l], nullptr, 1));            // ELU, k3, C -> C/2
+    RUN(conv(c0 + 2, l, l, w.a[l], w.y[l], nullptr, 0));        // 1x1 shortcut on the block input
+    RUN(conv(c0 + 1, l, l, w.h[l], w.y[l], w.y[l], 1));         // ELU, k1, C/2 -> C, + shortcut
+    RUN(conv(c0 + 3, l, l + 1, w.y[l], w.a[l + 1], nullptr, 1)); // ELU, strided conv k=2s
+  }
+  // LSTM (2 layers) + skip
+  const int t4 = b->total[4];
+  for (int layer = 0; layer < 2; ++layer) {
+    const std::string L = "lstm" + std::to_string(layer) + ".";
+    const float* wih = T(L + "w_ih"); const float* whh = T(L + "w_hh"); const float* bias = T(L + "b");
+    B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_encode: tensor '%s' not set", miss.c_str());
+    {
+      ConvArgs a{};
+      a.in = layer == 0 ? w.a[4] : w.s1; a.cin = 512; a.w = wih; a.kdim_pad = 512; a.bias = bias; a.out = w.xg; a.cout = 2048;
+      a.k = 1; a.s = 1; a.elu_in = 0;
+      a.in_off = b->off[4]; a.in_len = b->len[4]; a.out_off = b->off[4]; a.out_len = b->len[4];
+      a.tile_clip = b->tile_clip[4]; a.tile_t0 = b->tile_t0[4];
+      dim3 grid(2048 / 64, b->n_tiles[4]);
+      seanet_conv_kernel<<<grid, 256, 0, st>>>(a);
+      B2T_LAUNCH_CHECK();
+    }
+    float* hp = w.hA; float* hn = w.hB;
+    for (int t = 0; t < b->t_max; ++t) {
+      const int na = active_host[t];
+      if (na <= 0) break;
+      dim3 grid(512 / 32, (na + 31) / 32);
+      lstm_step_kernel<<<grid, 256, 0, st>>>(w.xg, whh, hp, hn, w.c, layer == 0 ? w.s1 : w.s2,
+                                             layer == 1 ? w.a[4] : nullptr, b->order, b->off[4], t, na);
+      B2T_LAUNCH_CHECK();
+      float* tmp = hp; hp = hn; hn = tmp;
+    }
+  }
+  // ELU + final conv k7 512 -> 128
+  float* emb = emb_out ? emb_out : w.emb;
+  RUN(conv(17, 4, 4, w.s2, emb, nullptr, 1));
+  // residual VQ
+  const float* cbs = T("rvq.codebooks"); const float* hns = T("rvq.half_norm"); const float* cmx = T("rvq.cmax_half");
+  B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_encode: tensor '%s' not set", miss.c_str());
+  static bool cfg = false;
+  if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RvqSmem))); cfg = true; }
+  rvq_kernel<<<(t4 + 63) / 64, 256, sizeof(RvqSmem), st>>>(emb, t4, cbs, hns, cmx, n_q, codes);
+  B2T_LAUNCH_CHECK();
+  (void)t4;
+  return B2T_OK;
+#undef RUN
+}

@@ -142,6 +142,7 @@ class Wav2VecBertEncoder(torch.nn.Module):
 
     # ---- row bookkeeping used by the batched file loop -------------------------------------------
     num_codebooks = 1
+    max_rows_per_batch = 262144
 
     def rows_for(self, padded_samples: int) -> int:
         """Rows the reference returns for a segment padded to `padded_samples` (T)."""

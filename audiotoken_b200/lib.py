@@ -25,6 +25,8 @@ EXPORTS = [
     'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_vq_debug_stats', 'b2t_semantic_create', 'b2t_semantic_destroy',
     'b2t_semantic_set_tensor', 'b2t_semantic_workspace_bytes', 'b2t_semantic_encode',
     'b2t_last_launch_count', 'b2t_profile_enable', 'b2t_profile_read',
+    'b2t_acoustic_create', 'b2t_acoustic_destroy', 'b2t_acoustic_set_tensor', 'b2t_acoustic_workspace_bytes',
+    'b2t_acoustic_encode',
 ]
 
 
@@ -45,6 +47,13 @@ class FbankTables(C.Structure):
     """b2t_fbank_tables"""
     _fields_ = [('window', C.c_void_p), ('mel_start', C.c_void_p), ('mel_count', C.c_void_p),
                 ('mel_weight', C.c_void_p)]
+
+
+class AcousticBatch(C.Structure):
+    """b2t_acoustic_batch"""
+    _fields_ = [('n_clips', C.c_int32), ('t_max', C.c_int32), ('total', C.c_int32 * 5), ('n_tiles', C.c_int32 * 5),
+                ('wave_off', C.c_void_p), ('true_len', C.c_void_p), ('len', C.c_void_p * 5), ('off', C.c_void_p * 5),
+                ('tile_clip', C.c_void_p * 5), ('tile_t0', C.c_void_p * 5), ('order', C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
@@ -93,6 +102,13 @@ def load() -> C.CDLL:
     lib.b2t_semantic_encode.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(FbankTables), vp, sz, vp, i32, vp, vp]
     lib.b2t_last_launch_count.restype = i32
     lib.b2t_profile_enable.argtypes = [i32]
+    lib.b2t_acoustic_create.restype = vp
+    lib.b2t_acoustic_destroy.argtypes = [vp]
+    lib.b2t_acoustic_destroy.restype = None
+    lib.b2t_acoustic_set_tensor.argtypes = [vp, C.c_char_p, vp]
+    lib.b2t_acoustic_workspace_bytes.argtypes = [C.POINTER(AcousticBatch)]
+    lib.b2t_acoustic_workspace_bytes.restype = sz
+    lib.b2t_acoustic_encode.argtypes = [vp, vp, C.POINTER(AcousticBatch), i32, vp, sz, vp, vp, vp, vp]
     lib.b2t_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double)]
     _lib = lib
     return lib

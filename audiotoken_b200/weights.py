@@ -94,3 +94,48 @@ def synthetic_waveform(index: int, num_samples: int, sample_rate: int) -> torch.
     for k in range(3):
         x = x + (a[k].double() * torch.sin(2 * torch.pi * f[k].double() * t + ph[k].double())).float()
     return x.clamp_(-1.0, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# EnCodec 24 kHz SEANet encoder + RVQ codebooks (HF `EncodecModel` state-dict names)
+# ---------------------------------------------------------------------------------------------------
+# (name, C_in, C_out, kernel, stride): the 15 weight-normed causal convs in forward order
+SEANET_CONVS = [
+    ('encoder.layers.0.conv', 1, 32, 7, 1),
+    ('encoder.layers.1.block.1.conv', 32, 16, 3, 1), ('encoder.layers.1.block.3.conv', 16, 32, 1, 1),
+    ('encoder.layers.1.shortcut.conv', 32, 32, 1, 1), ('encoder.layers.3.conv', 32, 64, 4, 2),
+    ('encoder.layers.4.block.1.conv', 64, 32, 3, 1), ('encoder.layers.4.block.3.conv', 32, 64, 1, 1),
+    ('encoder.layers.4.shortcut.conv', 64, 64, 1, 1), ('encoder.layers.6.conv', 64, 128, 8, 4),
+    ('encoder.layers.7.block.1.conv', 128, 64, 3, 1), ('encoder.layers.7.block.3.conv', 64, 128, 1, 1),
+    ('encoder.layers.7.shortcut.conv', 128, 128, 1, 1), ('encoder.layers.9.conv', 128, 256, 10, 5),
+    ('encoder.layers.10.block.1.conv', 256, 128, 3, 1), ('encoder.layers.10.block.3.conv', 128, 256, 1, 1),
+    ('encoder.layers.10.shortcut.conv', 256, 256, 1, 1), ('encoder.layers.12.conv', 256, 512, 16, 8),
+    ('encoder.layers.15.conv', 512, 128, 7, 1),
+]
+
+
+def synthetic_encodec_state_dict(seed: int = 0, n_codebooks: int = 32) -> Dict[str, torch.Tensor]:
+    """HF-named fp32 tensors of the EnCodec 24 kHz encoder, its 2-layer LSTM and the RVQ codebooks."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, cin, cout, k, _s in SEANET_CONVS:
+        v = _randn(g, cout, cin, k, std=1.0 / (cin * k) ** 0.5)
+        norm = v.flatten(1).norm(dim=1).view(cout, 1, 1)
+        sd[name + '.parametrizations.weight.original0'] = norm * (1.0 + 0.1 * _randn(g, cout, 1, 1))
+        sd[name + '.parametrizations.weight.original1'] = v
+        sd[name + '.bias'] = _randn(g, cout, std=0.05)
+    bound = 1.0 / 512 ** 0.5
+    for layer in range(2):
+        for nm, shape in (('weight_ih', (2048, 512)), ('weight_hh', (2048, 512)), ('bias_ih', (2048,)), ('bias_hh', (2048,))):
+            sd[f'encoder.layers.13.lstm.{nm}_l{layer}'] = (torch.rand(*shape, generator=g) * 2 - 1) * bound
+    gq = torch.Generator().manual_seed(seed + 1)
+    for q in range(n_codebooks):
+        # later stages quantise smaller residuals: shrink the codebooks geometrically so every stage stays informative
+        sd[f'quantizer.layers.{q}.codebook.embed'] = torch.randn(1024, 128, generator=gq) * (0.12 * 0.85 ** q)
+    return sd
+
+
+def weight_norm_weight(sd: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
+    """w = g * v / |v| with the norm over (C_in, k) per output channel (torch weight_norm, dim=0)."""
+    g_, v = sd[name + '.parametrizations.weight.original0'], sd[name + '.parametrizations.weight.original1']
+    return g_ * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)

@@ -191,6 +191,41 @@ int b2t_last_launch_count(void);
 int b2t_profile_enable(int on);
 int b2t_profile_read(float* ms_per_class_host, double* gemm_flops_host);
 
+/* ---- acoustic path: EnCodec 24 kHz SEANet encoder + LSTM + residual VQ --------------------------
+ * Replaces reference AcousticEncoder.forward (audiotoken/encoder.py:44-57):
+ *   emb = self.model.encoder(x.unsqueeze(1)); codes = self.model.quantizer.encode(emb, 75, bandwidth)
+ * (third-party `encodec`; architecture: transformers models/encodec/modeling_encodec.py:82-313, 364-438).
+ * Level l = 0..4 is the time resolution after 0..4 strided convs (strides 2,4,5,8): len[l+1] = ceil(len[l]/s).
+ * Activations are channels-last and ragged: clip i occupies rows off[l][i] .. off[l][i]+len[l][i].       */
+typedef struct {
+  int32_t n_clips;
+  int32_t t_max;                 /* longest clip in frames (level 4)                                  */
+  int32_t total[5];              /* sum of len[l]                                                     */
+  int32_t n_tiles[5];            /* 64-row work tiles per level                                       */
+  const int64_t* wave_off;       /* [n_clips] first sample of clip i                                  */
+  const int32_t* true_len;       /* [n_clips] samples actually present (the rest of len[0] reads as 0) */
+  const int32_t* len[5];         /* [n_clips] per level                                               */
+  const int32_t* off[5];         /* [n_clips+1] per level                                             */
+  const int32_t* tile_clip[5];
+  const int32_t* tile_t0[5];
+  const int32_t* order;          /* [n_clips] clip ids sorted by len[4] descending (LSTM active prefix) */
+} b2t_acoustic_batch;
+
+typedef struct b2t_acoustic_model b2t_acoustic_model;
+b2t_acoustic_model* b2t_acoustic_create(void);
+void b2t_acoustic_destroy(b2t_acoustic_model* m);
+/* fp32 tensors: conv<i>.w [C_out, pad16(k*C_in)] (tap-major, weight-norm applied) and conv<i>.b for the 18
+ * convs in forward order, lstm<l>.w_ih / .w_hh [2048,512], lstm<l>.b (= b_ih + b_hh), rvq.codebooks
+ * [n_q_total,1024,128], rvq.half_norm [n_q_total,1024], rvq.cmax_half [n_q_total].                    */
+int b2t_acoustic_set_tensor(b2t_acoustic_model* m, const char* name, const void* ptr);
+size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* batch);
+/* codes: int16 [n_q, total[4]] (stage-major over the packed frames).  emb_out (optional): fp32
+ * [total[4], 128] encoder output.  active_host[t] (HOST array, t_max entries) = number of clips with
+ * more than t frames; it sizes the per-step LSTM launches.                                           */
+int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic_batch* batch,
+                        int n_q, void* workspace, size_t workspace_bytes, int16_t* codes, float* emb_out,
+                        const int32_t* active_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

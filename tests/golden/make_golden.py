@@ -35,7 +35,7 @@ REF = '/root/reference/audiotoken'
 sys.path.insert(0, REPO)
 
 from audiotoken_b200.weights import (synthetic_w2vbert_state_dict, synthetic_waveform,  # noqa: E402
-                                     synthetic_codebook)
+                                     synthetic_codebook, synthetic_encodec_state_dict)
 
 
 def load_reference_modules():
@@ -127,5 +127,31 @@ def main():
         del model
 
 
+def main_acoustic():
+    """EnCodec stand-in (HF EncodecModel) on the synthetic weights: embeddings + RVQ-16 codes."""
+    from transformers import EncodecConfig, EncodecModel
+    sd = synthetic_encodec_state_dict(0)
+    model = EncodecModel(EncodecConfig())
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [k for k in missing if k.startswith('encoder') or k.endswith('codebook.embed')]
+    model.eval()
+    save = {}
+    # BASELINE config 1 shape scaled down (1 s), an odd length (right reflect extra padding), a very short clip
+    for tag, lengths in (('a', [24000, 24000]), ('b', [24137]), ('c', [4800]), ('d', [333])):
+        w = torch.stack([synthetic_waveform(20 + i, n, 24000) for i, n in enumerate(lengths)])
+        with torch.no_grad():
+            emb = model.encoder(w.unsqueeze(1))                            # reference encoder.py:48
+            codes = model.quantizer.encode(emb, 12.0)                      # reference encoder.py:50-52 -> [16, B, T]
+        save[f'lengths_{tag}'] = np.array(lengths)
+        save[f'emb_{tag}'] = emb.numpy()
+        save[f'codes_{tag}'] = codes.transpose(0, 1).numpy().astype(np.int16)   # [B, K, T] as encoder.py:54
+        print('acoustic', tag, tuple(emb.shape), tuple(codes.shape))
+    np.savez_compressed(os.path.join(HERE, 'acoustic.npz'), **save)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'acoustic':
+        main_acoustic()
+    else:
+        main()
+        main_acoustic()

@@ -1,0 +1,77 @@
+"""GPU (-m gpu): acoustic path (SEANet encoder + LSTM + RVQ) through the C ABI vs the EnCodec stand-in goldens
+and the oracle.  fp32 numerics: embeddings within 1e-4 relative, codes >= 99.5 % (RVQ stages compound, so a
+single near-tie flips the later stages of that frame)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audiotoken_b200 import AudioToken, Tokenizers
+from audiotoken_b200 import io as aio
+from audiotoken_b200.acoustic import AcousticEncoder, plan_acoustic
+from audiotoken_b200.weights import synthetic_encodec_state_dict, synthetic_waveform
+from oracle import seanet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def enc(cuda_device):
+    return AcousticEncoder(device='cuda:0', state_dict=synthetic_encodec_state_dict(0))
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
+def test_acoustic_matches_golden(enc, cuda_device, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, 'acoustic.npz'))
+    lengths = g[f'lengths_{tag}']
+    w = torch.stack([synthetic_waveform(20 + i, int(n), 24000) for i, n in enumerate(lengths)])
+    codes, emb = enc(w.to(cuda_device), None, want_emb=True)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g[f'emb_{tag}'])
+    assert emb.shape == ref.shape and codes.dtype == torch.int16
+    err = float((emb.cpu() - ref).norm() / ref.norm())
+    assert err < 1e-4, err
+    agree = float((codes.cpu().numpy() == g[f'codes_{tag}']).mean())
+    assert agree >= 0.995, agree
+    # given the kernel's own embeddings, the RVQ stage is exact (fp64 oracle on the same fp32 residuals)
+    want = seanet.rvq_codes(emb.cpu().float(), synthetic_encodec_state_dict(0), 16).transpose(0, 1)
+    assert torch.equal(codes.cpu().long(), want)
+
+
+def test_acoustic_packed_equals_padded(enc, cuda_device):
+    lengths = [24000, 7777, 3200, 15001]
+    clips = [synthetic_waveform(40 + i, n, 24000) for i, n in enumerate(lengths)]
+    total = 24000
+    wave = torch.zeros(len(lengths), total)
+    for i, c in enumerate(clips):
+        wave[i, :c.numel()] = c
+    padded = enc(wave.to(cuda_device), None).cpu()
+    rows = [math.ceil(n / 24000 * 75) for n in lengths]
+    packed = [t.cpu() for t in enc.encode_packed(clips, total, rows)]
+    for i, r in enumerate(rows):
+        assert packed[i].shape == (16, r)
+        assert torch.equal(packed[i], padded[i, :, :r]), i
+    alone = enc.encode_packed([clips[1]], total, [rows[1]])[0].cpu()
+    assert torch.equal(alone, packed[1])
+
+
+def test_acoustic_audiotoken_api(cuda_device, tmp_path):
+    tok = AudioToken(tokenizer=Tokenizers.acoustic, device='cuda:0', num_codebooks=8)
+    assert tok.model_sample_rate == 24000
+    x = synthetic_waveform(5, 24000, 24000).unsqueeze(0)
+    t = tok.encode(x)
+    assert t.shape == (1, 8, 75) and t.dtype == torch.int16 and t.device.type == 'cpu'
+    full = AudioToken(tokenizer='acoustic', device='cuda:0').encode(x)
+    assert full.shape == (1, 16, 75) and torch.equal(full[:, :8], t)       # RVQ prefix property
+    files = []
+    for i, n in enumerate((24000 * 2 + 100, 9000)):
+        p = tmp_path / f'f{i}.wav'
+        aio.write_wav(str(p), synthetic_waveform(60 + i, n, 24000), 24000)
+        files.append(str(p))
+    tok.encode_batch_files(batch_size=2, outdir=str(tmp_path / 'o'), chunk_size=1, audio_files=files)
+    a = np.load(tmp_path / 'o' / 'f0.npy')
+    assert a.dtype == np.int16 and a.shape == (8, 75 + 75 + 1)
+    b = np.load(tmp_path / 'o' / 'f1.npy')
+    assert b.shape == (8, math.ceil(9000 / 24000 * 75))

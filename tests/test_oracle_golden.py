@@ -105,3 +105,24 @@ def test_rvq_residual_property():
         assert torch.allclose(cur, alt)
         prev = cur
     assert quantize.num_quantizers(12.0) == 16 and quantize.num_quantizers(1.5) == 2
+
+
+def test_seanet_oracle_matches_encodec_standin(golden_dir):
+    """oracle/seanet.py against HF EncodecModel outputs (embeddings + RVQ-16 codes), incl. an odd length
+    (reflect extra padding on the right) and a 333-sample clip (short-input rule of the reflect pad)."""
+    from audiotoken_b200.weights import synthetic_encodec_state_dict
+    from oracle import seanet
+    g = np.load(os.path.join(golden_dir, 'acoustic.npz'))
+    sd = synthetic_encodec_state_dict(0)
+    for tag in 'abcd':
+        lengths = g[f'lengths_{tag}']
+        w = torch.stack([synthetic_waveform(20 + i, int(n), 24000) for i, n in enumerate(lengths)])
+        emb = seanet.encoder(w, sd)
+        ref = torch.from_numpy(g[f'emb_{tag}'])
+        assert emb.shape == ref.shape
+        assert float((emb - ref).abs().max()) < 2e-5
+        codes = seanet.rvq_codes(emb, sd, 16).transpose(0, 1)
+        agree = float((codes.numpy() == g[f'codes_{tag}']).mean())
+        assert agree >= 0.995, (tag, agree)
+        ref32 = seanet.rvq_codes_reference_fp32(emb, sd, 16).transpose(0, 1)
+        assert float((ref32 == codes).float().mean()) >= 0.995
