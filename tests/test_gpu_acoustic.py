@@ -66,12 +66,14 @@ def test_acoustic_audiotoken_api(cuda_device, tmp_path):
     full = AudioToken(tokenizer='acoustic', device='cuda:0').encode(x)
     assert full.shape == (1, 16, 75) and torch.equal(full[:, :8], t)       # RVQ prefix property
     files = []
-    for i, n in enumerate((24000 * 2 + 100, 9000)):
+    for i, n in enumerate((24000 * 2 + 4000, 9000, 24000 + 100)):
         p = tmp_path / f'f{i}.wav'
         aio.write_wav(str(p), synthetic_waveform(60 + i, n, 24000), 24000)
         files.append(str(p))
     tok.encode_batch_files(batch_size=2, outdir=str(tmp_path / 'o'), chunk_size=1, audio_files=files)
     a = np.load(tmp_path / 'o' / 'f0.npy')
-    assert a.dtype == np.int16 and a.shape == (8, 75 + 75 + 1)
+    assert a.dtype == np.int16 and a.shape == (8, 75 + 75 + 13)
     b = np.load(tmp_path / 'o' / 'f1.npy')
     assert b.shape == (8, math.ceil(9000 / 24000 * 75))
+    # a trailing 100-sample chunk is below the 3200-sample minimum and is skipped (reference datasets.py:95-97)
+    assert np.load(tmp_path / 'o' / 'f2.npy').shape == (8, 75)
