@@ -51,6 +51,8 @@ def shard_lengths(rank: int, workload: str):
     """Clip lengths (samples) of this rank's shard."""
     if workload == 'c2':                      # BASELINE config[1] shape: 64 x 10 s
         return np.full(64, 10 * SR, dtype=np.int64)
+    if workload == 'c4':                      # BASELINE config[3]: acoustic, 10k x 20 s @24 kHz, 1250 clips per GPU
+        return np.full(CLIPS_PER_GPU, 20 * 24000, dtype=np.int64)
     g = torch.Generator().manual_seed(0)
     dur = torch.rand(TOTAL_CLIPS, generator=g, dtype=torch.float64) * 28.0 + 2.0
     lens = (dur * SR).round().to(torch.int64).numpy()
@@ -58,7 +60,7 @@ def shard_lengths(rank: int, workload: str):
     return lens[r * CLIPS_PER_GPU:(r + 1) * CLIPS_PER_GPU]
 
 
-def synth_on_device(lengths: np.ndarray, seed: int, device) -> torch.Tensor:
+def synth_on_device(lengths: np.ndarray, seed: int, device, SR: int = SR) -> torch.Tensor:
     """Flat fp32 buffer of the clips back to back: 0.1*noise + 3 sinusoids per clip, in [-1, 1]."""
     g = torch.Generator(device=device).manual_seed(seed)
     n = len(lengths)
@@ -159,12 +161,41 @@ def cpu_reference_run(lengths: np.ndarray, steps: int, warmup: int, n_sample: in
                        f'{REF_LAYERS} layers, fp32 torch-CPU oracle, {steps} timed steps'), ms
 
 
+def cpu_reference_run_acoustic(steps: int, warmup: int):
+    """BASELINE config[0]: EnCodec encode of one 10 s 24 kHz clip on the host CPU (oracle/seanet.py, fp32)."""
+    from audiotoken_b200.weights import synthetic_encodec_state_dict, synthetic_waveform
+    from oracle import seanet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_encodec_state_dict(0)
+    wave = synthetic_waveform(0, 240000, 24000).unsqueeze(0)
+
+    def step():
+        with torch.no_grad():
+            return seanet.rvq_codes_reference_fp32(seanet.encoder(wave, sd), sd, 16)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    return dict(value=10.0 / (ms / 1e3), unit='audio-s/s', cores=cores, kind='port',
+                sample=f'one 10 s 24 kHz clip (BASELINE configs[0]), SEANet + LSTM + RVQ-16, fp32 torch-CPU oracle, '
+                       f'{steps} timed steps'), ms
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     lengths = shard_lengths(0, args.workload)
-    base, ms = cpu_reference_run(lengths, max(1, args.steps), max(0, min(args.warmup, 1)))
+    if args.workload == 'c4':
+        base, ms = cpu_reference_run_acoustic(max(1, args.steps), max(0, min(args.warmup, 1)))
+    else:
+        base, ms = cpu_reference_run(lengths, max(1, args.steps), max(0, min(args.warmup, 1)))
     line = {'impl': 'reference', 'metric': 'audio_seconds_per_second', 'value': base['value'], 'unit': 'audio-s/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -177,9 +208,12 @@ def workload_config(workload, lengths):
     name = ('semantic_m encode_batch_files-equivalent: per-GPU shard of BASELINE configs[2] '
             f'({len(lengths)} of {TOTAL_CLIPS} synthetic clips, U(2,30) s @16 kHz, seed 0); '
             f'w2v-BERT 2.0 conformer x{N_LAYERS} + LayerNorm + VQ {CODEBOOK}x1024')
+    if workload == 'c4':
+        name = ('acoustic encode_batch_files-equivalent: per-GPU shard of BASELINE configs[3] (1250 of 10000 clips x 20 s '
+                '@24 kHz); EnCodec SEANet encoder + LSTM + RVQ 16 codebooks')
     if workload == 'c2':
         name = f'semantic_m encode of 64 x 10 s @16 kHz clips (BASELINE configs[1] shape); conformer x{N_LAYERS} + VQ {CODEBOOK}'
-    return {'workload': name, 'clips_per_gpu': int(len(lengths)), 'audio_seconds_per_gpu': float(lengths.sum() / SR),
+    return {'workload': name, 'clips_per_gpu': int(len(lengths)), 'audio_seconds_per_gpu': float(lengths.sum() / (24000 if workload == 'c4' else SR)),
             'row_budget_per_batch': ROW_BUDGET,
             'l2': 'inputs larger than L2: every batch streams >1 GB of activations through HBM'}
 
@@ -191,7 +225,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c3', choices=['c3', 'c2'])
+    ap.add_argument('--workload', default='c3', choices=['c3', 'c2', 'c4'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -215,25 +249,40 @@ def main():
     from audiotoken_b200.encoder import Wav2VecBertEncoder
 
     lengths = shard_lengths(rank, args.workload)
-    audio_s = float(lengths.sum() / SR)
-    rows = np.array([packing.length_tokens(int(n), SR, TOKEN_RATE) for n in lengths])
-    batches = packing.bucket_by_rows(rows.tolist(), ROW_BUDGET)
-    enc = Wav2VecBertEncoder(device=str(device), precision='bf16', n_layers=N_LAYERS)
+    acoustic = args.workload == 'c4'
+    sr = 24000 if acoustic else SR
+    audio_s = float(lengths.sum() / sr)
+    if acoustic:
+        from audiotoken_b200.acoustic import AcousticEncoder, plan_acoustic
+        rows = np.array([packing.length_tokens(int(n), sr, 75) for n in lengths])
+        enc = AcousticEncoder(device=str(device))
+        batches = packing.bucket_by_rows(rows.tolist(), enc.max_rows_per_batch)
+
+        def make_plan(ln, offs, rws):
+            return plan_acoustic(ln, offs, np.maximum(rws * 320, ln))
+    else:
+        rows = np.array([packing.length_tokens(int(n), sr, TOKEN_RATE) for n in lengths])
+        batches = packing.bucket_by_rows(rows.tolist(), ROW_BUDGET)
+        enc = Wav2VecBertEncoder(device=str(device), precision='bf16', n_layers=N_LAYERS)
+
+        def make_plan(ln, offs, rws):
+            return packing.plan_semantic(ln, offs, CHUNK_S * sr, rws)
 
     # synthetic waveforms: generated on the device, kept there (value) and mirrored in pinned host memory (e2e)
     dev_waves, host_waves, plans, host_tokens = [], [], [], []
     for bi, idx in enumerate(batches):
         ln = lengths[idx]
-        w = synth_on_device(ln, 1000 + rank * 1000 + bi, device)
+        w = synth_on_device(ln, 1000 + rank * 1000 + bi, device, sr)
         offs = np.zeros(len(idx), dtype=np.int64)
         offs[1:] = np.cumsum(ln)[:-1]
-        plan = packing.plan_semantic(ln, offs, CHUNK_S * SR, rows[idx])
+        plan = make_plan(ln, offs, rows[idx])
         dev_waves.append(w)
         hw = torch.empty(w.numel(), dtype=torch.float32, pin_memory=True)
         hw.copy_(w)
         host_waves.append(hw)
         plans.append(plan)
-        host_tokens.append(torch.empty(plan.total_rows, dtype=torch.int16, pin_memory=True))
+        n_tok = plan.total_frames * enc.num_codebooks if acoustic else plan.total_rows
+        host_tokens.append(torch.empty(n_tok, dtype=torch.int16, pin_memory=True))
     torch.cuda.synchronize()
     h2d_bytes = sum(h.numel() * 4 for h in host_waves)
     d2h_bytes = sum(h.numel() * 2 for h in host_tokens)
@@ -274,9 +323,10 @@ def main():
             ln = lengths[idx]
             offs = np.zeros(len(idx), dtype=np.int64)
             offs[1:] = np.cumsum(ln)[:-1]
-            plan = packing.plan_semantic(ln, offs, CHUNK_S * SR, rows[idx])     # host planning is inside e2e
+            plan = make_plan(ln, offs, rows[idx])                                # host planning is inside e2e
             comp.wait_event(ready)
             tokens, _ = enc.encode_plan(buf, plan)
+            tokens = tokens.view(-1)
             done = comp.record_event()
             free_ev[i % 2] = done
             tokens.record_stream(copy_stream)
@@ -309,10 +359,10 @@ def main():
     # instrumented steps: CUDA-event time per kernel class
     import ctypes as C
     lib = L.load()
-    lib.b2t_profile_enable(1)
+    lib.b2t_profile_enable(0 if acoustic else 1)
     cls_ms = np.zeros(6)
     gemm_flops = 0.0
-    for w, plan in zip(dev_waves, plans):
+    for w, plan in ([] if acoustic else zip(dev_waves, plans)):
         enc.encode_plan(w, plan)
         arr = (C.c_float * 6)()
         fl = C.c_double(0)
@@ -322,6 +372,10 @@ def main():
     lib.b2t_profile_enable(0)
     peak_tf, peak_hbm, peak_src = measured_peaks()
     ach = gemm_flops / (cls_ms[2] / 1e3) / 1e12 if cls_ms[2] > 0 else 0.0
+    if acoustic:
+        # 39.73 MFLOP per frame (encoder) + n_q * 2*1024*128 (RVQ); fp32 CUDA-core kernels this round
+        flops = float(rows.sum()) * (39.73e6 + enc.num_codebooks * 2 * 1024 * 128)
+        ach = flops / (ms_res / 1e3) / 1e12
 
     if rank == 0:
         value = world * audio_s / (ms_res / 1e3)
@@ -329,7 +383,7 @@ def main():
         line = {
             'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_res, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if acoustic else 'bf16', 'data': 'synthetic',
             'config': workload_config(args.workload, lengths), 'clocks': clocks,
             'e2e': {'value': e2e, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(d2h_bytes)},
@@ -341,8 +395,11 @@ def main():
             'breakdown_ms_per_step': dict(zip(['fbank', 'layernorm', 'gemm', 'attention', 'dwconv', 'vq'],
                                               [float(v) for v in cls_ms])),
         }
+        if acoustic:
+            line['roofline'].update({'kernel': 'whole acoustic step (fp32 SIMT conv / LSTM / RVQ kernels; tensor-core port pending)',
+                                     'bound': 'tensor', 'gemm_share_of_step': None})
         if world == 1 and not args.no_cpu_baseline:
-            base, _ = cpu_reference_run(lengths, steps=2, warmup=1)
+            base, _ = cpu_reference_run_acoustic(3, 1) if acoustic else cpu_reference_run(lengths, steps=2, warmup=1)
             line['cpu_baseline'] = base
         print(json.dumps(line), flush=True)
     if dist is not None:
