@@ -50,8 +50,8 @@ seanet_conv_kernel(ConvArgs a) {
   __shared__ float As[16][64 + 4];
   __shared__ float Ws[16][64 + 4];
   const int tid = threadIdx.x;
-  const int clip = a.tile_clip[blockIdx.y], t0 = a.tile_t0[blockIdx.y];
-  const int n0 = blockIdx.x * 64;
+  const int clip = a.tile_clip[blockIdx.x], t0 = a.tile_t0[blockIdx.x];   // tiles on x: up to 2^31-1 blocks
+  const int n0 = blockIdx.y * 64;
   const int in_len = a.in_len[clip], out_len = a.out_len[clip];
   const int padL = a.k - a.s;
   const int padR = out_len * a.s - in_len;           // "extra" padding: ceil(len/s)*s - len
@@ -376,7 +376,7 @@ extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wav
     a.wave_off = (ci == 0) ? b->wave_off : nullptr;
     a.true_len = (ci == 0) ? b->true_len : nullptr;
     if (b->n_tiles[lout] <= 0) return B2T_OK;
-    dim3 grid((cs.cout + 63) / 64, b->n_tiles[lout]);
+    dim3 grid(b->n_tiles[lout], (cs.cout + 63) / 64);
     seanet_conv_kernel<<<grid, 256, 0, st>>>(a);
     B2T_LAUNCH_CHECK();
     return B2T_OK;
@@ -403,7 +403,7 @@ extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wav
       a.k = 1; a.s = 1; a.elu_in = 0;
       a.in_off = b->off[4]; a.in_len = b->len[4]; a.out_off = b->off[4]; a.out_len = b->len[4];
       a.tile_clip = b->tile_clip[4]; a.tile_t0 = b->tile_t0[4];
-      dim3 grid(2048 / 64, b->n_tiles[4]);
+      dim3 grid(b->n_tiles[4], 2048 / 64);
       seanet_conv_kernel<<<grid, 256, 0, st>>>(a);
       B2T_LAUNCH_CHECK();
     }

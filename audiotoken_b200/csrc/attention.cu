@@ -143,6 +143,11 @@ B2T_DEVICE void cp_async16(uint32_t dst, const void* src, bool pred) {
   int sz = pred ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+B2T_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 B2T_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> B2T_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -150,14 +155,14 @@ template <int N> B2T_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_g
 B2T_DEVICE uint32_t swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 struct MmaSmem {
-  __nv_bfloat16 q[kQT * kHD];        // 8 KB (also used to stage E in two halves at start)
-  __nv_bfloat16 k[2][kKT * kHD];     // 16 KB
-  __nv_bfloat16 v[2][kKT * kHD];     // 16 KB
-  __nv_bfloat16 e[80 * kHD];         // 10 KB  (73 rows + zero pad)
-  float r[kQT][kRel + 4];            // 19.7 KB  R/8 (bf16-rounded), row stride 77 floats
+  __nv_bfloat16 q[kQT * kHD];          // 8 KB
+  __nv_bfloat16 kv[2][2][kKT * kHD];   // 32 KB: [buffer][K|V]; buffer 1 first stages the distance embedding E
+                                       //        (80 x 64 bf16 = 10 KB, 73 rows + zero pad) until R is computed
+  __nv_bfloat16 r[kQT][kRel + 3];      // 9.5 KB  bf16(q.E^T) — the einsum output the reference rounds to bf16
 };
+static_assert(sizeof(MmaSmem) <= 57 * 1024, "4 CTAs per SM need <= 56.75 KB each");
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dist_emb,
                      const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
                      const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
@@ -168,9 +173,9 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   const int r0 = row_off[clip], rows = row_off[clip + 1] - r0, nkeys = valid_rows[clip];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sq = (uint32_t)__cvta_generic_to_shared(s.q);
-  const uint32_t se = (uint32_t)__cvta_generic_to_shared(s.e);
-  const uint32_t sk[2] = {(uint32_t)__cvta_generic_to_shared(s.k[0]), (uint32_t)__cvta_generic_to_shared(s.k[1])};
-  const uint32_t sv[2] = {(uint32_t)__cvta_generic_to_shared(s.v[0]), (uint32_t)__cvta_generic_to_shared(s.v[1])};
+  const uint32_t se = (uint32_t)__cvta_generic_to_shared(s.kv[1][0]);
+  const uint32_t sk[2] = {(uint32_t)__cvta_generic_to_shared(s.kv[0][0]), (uint32_t)__cvta_generic_to_shared(s.kv[1][0])};
+  const uint32_t sv[2] = {(uint32_t)__cvta_generic_to_shared(s.kv[0][1]), (uint32_t)__cvta_generic_to_shared(s.kv[1][1])};
 
   const __nv_bfloat16* qbase = qkv + (size_t)r0 * kQKV + head * kHD;
   auto load_kv = [&](int buf, int k0) {
@@ -232,21 +237,22 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       for (int h = 0; h < 2; ++h) {
         const int col = nt2 * 16 + h * 8 + 2 * (lane & 3);
         const int rlo = warp * 16 + (lane >> 2);
-        if (col < kRel) { s.r[rlo][col] = bf16_round(acc[h][0]) * 0.125f; s.r[rlo + 8][col] = bf16_round(acc[h][2]) * 0.125f; }
-        if (col + 1 < kRel) { s.r[rlo][col + 1] = bf16_round(acc[h][1]) * 0.125f; s.r[rlo + 8][col + 1] = bf16_round(acc[h][3]) * 0.125f; }
+        if (col < kRel) { s.r[rlo][col] = __float2bfloat16_rn(acc[h][0]); s.r[rlo + 8][col] = __float2bfloat16_rn(acc[h][2]); }
+        if (col + 1 < kRel) { s.r[rlo][col + 1] = __float2bfloat16_rn(acc[h][1]); s.r[rlo + 8][col + 1] = __float2bfloat16_rn(acc[h][3]); }
       }
     }
   }
-  __syncwarp();
+  __syncthreads();   // every warp is done with E before key tile 1 overwrites its staging area
   const int rloc0 = warp * 16 + (lane >> 2), rloc1 = rloc0 + 8;   // the two query rows of this thread
   const int qp0 = q0 + rloc0, qp1 = q0 + rloc1;
-  const float rl0 = s.r[rloc0][0], rr0 = s.r[rloc0][kRel - 1];
-  const float rl1 = s.r[rloc1][0], rr1 = s.r[rloc1][kRel - 1];
+  // everything below works in the log2 domain: t = (q.k + bf16(q.E_r)) * (log2e / 8), p = 2^(t - m)
+  constexpr float kScale = 0.125f * 1.4426950408889634f;
+  const float rl0 = __bfloat162float(s.r[rloc0][0]) * kScale, rr0 = __bfloat162float(s.r[rloc0][kRel - 1]) * kScale;
+  const float rl1 = __bfloat162float(s.r[rloc1][0]) * kScale, rr1 = __bfloat162float(s.r[rloc1][kRel - 1]) * kScale;
 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[8][4] = {};
   const int nkt = (nkeys + kKT - 1) / kKT;
-  constexpr float kLog2e = 1.4426950408889634f;
 
   for (int kt = 0; kt < nkt; ++kt) {
     const int buf = kt & 1, k0 = kt * kKT;
@@ -269,25 +275,40 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
         mma_bf16_16816(sc[nt2 * 2 + 1], qf[ks], b1);
       }
     }
-    // scale + relative-key bias + key mask
+    // scale + relative-key bias (constant per row outside the diagonal band) + key mask
     const int dmin = k0 - (q0 + warp * 16 + 15), dmax = (k0 + kKT - 1) - (q0 + warp * 16);
-    const bool all_left = dmax <= -kLeft, all_right = dmin >= kRight;
-    const bool tail = k0 + kKT > nkeys;
+    if (dmax <= -kLeft) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
+        sc[nt][0] = fmaf(sc[nt][0], kScale, rl0); sc[nt][1] = fmaf(sc[nt][1], kScale, rl0);
+        sc[nt][2] = fmaf(sc[nt][2], kScale, rl1); sc[nt][3] = fmaf(sc[nt][3], kScale, rl1);
+      }
+    } else if (dmin >= kRight) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int kj = k0 + nt * 8 + 2 * (lane & 3) + c;
-        float b0v, b1v;
-        if (all_left) { b0v = rl0; b1v = rl1; }
-        else if (all_right) { b0v = rr0; b1v = rr1; }
-        else {
-          b0v = s.r[rloc0][max(-kLeft, min(kRight, kj - qp0)) + kLeft];
-          b1v = s.r[rloc1][max(-kLeft, min(kRight, kj - qp1)) + kLeft];
+      for (int nt = 0; nt < 8; ++nt) {
+        sc[nt][0] = fmaf(sc[nt][0], kScale, rr0); sc[nt][1] = fmaf(sc[nt][1], kScale, rr0);
+        sc[nt][2] = fmaf(sc[nt][2], kScale, rr1); sc[nt][3] = fmaf(sc[nt][3], kScale, rr1);
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int kj = k0 + nt * 8 + 2 * (lane & 3) + c;
+          const float b0v = __bfloat162float(s.r[rloc0][max(-kLeft, min(kRight, kj - qp0)) + kLeft]);
+          const float b1v = __bfloat162float(s.r[rloc1][max(-kLeft, min(kRight, kj - qp1)) + kLeft]);
+          sc[nt][c] = (sc[nt][c] + b0v) * kScale;
+          sc[nt][2 + c] = (sc[nt][2 + c] + b1v) * kScale;
         }
-        float s0 = sc[nt][c] * 0.125f + b0v, s1 = sc[nt][2 + c] * 0.125f + b1v;
-        if (tail && kj >= nkeys) { s0 = -INFINITY; s1 = -INFINITY; }
-        sc[nt][c] = s0; sc[nt][2 + c] = s1;
+      }
+    }
+    if (k0 + kKT > nkeys) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (k0 + nt * 8 + 2 * (lane & 3) + c >= nkeys) { sc[nt][c] = -INFINITY; sc[nt][2 + c] = -INFINITY; }
+        }
       }
     }
     // online softmax (rows live in 4-lane groups)
@@ -300,14 +321,14 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float c0 = exp2f((m0 - mn0) * kLog2e), c1 = exp2f((m1 - mn1) * kLog2e);
+    const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);
     m0 = mn0; m1 = mn1;
     float ps0 = 0.f, ps1 = 0.f;
     uint32_t pf[4][4];   // P as A fragments: 4 k-steps (16 keys each)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      float p00 = exp2f((sc[nt][0] - mn0) * kLog2e), p01 = exp2f((sc[nt][1] - mn0) * kLog2e);
-      float p10 = exp2f((sc[nt][2] - mn1) * kLog2e), p11 = exp2f((sc[nt][3] - mn1) * kLog2e);
+      const float p00 = ex2_approx(sc[nt][0] - mn0), p01 = ex2_approx(sc[nt][1] - mn0);
+      const float p10 = ex2_approx(sc[nt][2] - mn1), p11 = ex2_approx(sc[nt][3] - mn1);
       ps0 += p00 + p01; ps1 += p10 + p11;
       const int ks = nt >> 1, hi = nt & 1;
       pf[ks][hi * 2 + 0] = pack_bf16(p00, p01);
@@ -322,7 +343,6 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 #pragma unroll
       for (int dt2 = 0; dt2 < 4; ++dt2) {
         uint32_t bfr[4];
-        // V rows (keys) ks*16 + (lane&7) + 8*((lane>>3)&1), dim chunk dt2*2 + (lane>>4)
         const int krow = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
         ldmatrix_x4_trans(bfr, sv[buf] + swz(krow, dt2 * 2 + (lane >> 4)));
         uint32_t b0[2] = {bfr[0], bfr[1]}, b1[2] = {bfr[2], bfr[3]};

@@ -1,15 +1,16 @@
 // Conformer convolution-module middle (HF modeling_wav2vec2_bert.py:213-221):
 //   causal depthwise conv1d (k=31, left pad 30 zeros, per clip) -> LayerNorm(1024) -> swish.
-// Work item = (clip, 16-row time tile); 512 threads, each owns a channel pair for all 16 rows:
-// 31x2 weights and 16x2 accumulators live in registers, the 46 input rows are streamed once
-// (coalesced 2 KB rows, re-reads between neighbouring tiles hit L2).  The LayerNorm needs the whole
+// Work item = (clip, 64-row time tile) processed as four 16-row sub-tiles; 512 threads, each owns a channel
+// pair: 31x2 weights (loaded once per work item, tap-major [31][1024] layout => coalesced) and 16x2
+// accumulators live in registers, the 46 input rows of a sub-tile are streamed (coalesced 2 KB rows, the
+// 30-row halo re-read hits L1/L2).  The LayerNorm needs the whole
 // 1024-channel row, so row statistics go through a two-level (warp shuffle, shared memory) reduction.
 // HBM-bound: 2 KB (bf16) read + 2 KB written per row.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kC = 1024, kK = 31, kTT = 16, kThreads = 512;
+constexpr int kC = 1024, kK = 31, kTT = 16, kSub = 4, kThreads = 512;   // work item = kSub * kTT = 64 rows
 
 template <typename T> B2T_DEVICE float2 ld2(const T* p);
 template <> B2T_DEVICE float2 ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
@@ -30,7 +31,7 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
                        const int32_t* __restrict__ ctile_t0, T* __restrict__ out) {
   __shared__ float s_red[16][kTT];
   __shared__ float s_stat[kTT];
-  const int clip = ctile_clip[blockIdx.x], t0 = ctile_t0[blockIdx.x];
+  const int clip = ctile_clip[blockIdx.x], tile0 = ctile_t0[blockIdx.x];
   const int r0 = row_off[clip], rows = row_off[clip + 1] - r0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = tid * 2;
@@ -38,9 +39,16 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
   float w0[kK], w1[kK];
 #pragma unroll
   for (int k = 0; k < kK; ++k) {
-    w0[k] = r16<kBF16>(__ldg(w_dw + (size_t)c * kK + k));
-    w1[k] = r16<kBF16>(__ldg(w_dw + (size_t)(c + 1) * kK + k));
+    const float2 wk = __ldg(reinterpret_cast<const float2*>(w_dw + (size_t)k * kC + c));   // [31][1024]
+    w0[k] = r16<kBF16>(wk.x);
+    w1[k] = r16<kBF16>(wk.y);
   }
+  const float g0 = __ldg(ln_w + c), g1 = __ldg(ln_w + c + 1);
+  const float b0 = __ldg(ln_b + c), b1 = __ldg(ln_b + c + 1);
+#pragma unroll 1
+  for (int sub = 0; sub < kSub; ++sub) {
+  const int t0 = tile0 + sub * kTT;
+  if (t0 >= rows) break;
   float a0[kTT], a1[kTT];
 #pragma unroll
   for (int t = 0; t < kTT; ++t) { a0[t] = 0.f; a1[t] = 0.f; }
@@ -100,8 +108,6 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
     s_stat[tid] = rsqrtf(s * (1.0f / kC) + 1e-5f);
   }
   __syncthreads();
-  const float g0 = __ldg(ln_w + c), g1 = __ldg(ln_w + c + 1);
-  const float b0 = __ldg(ln_b + c), b1 = __ldg(ln_b + c + 1);
 #pragma unroll
   for (int t = 0; t < kTT; ++t) {
     if (t0 + t < rows) {
@@ -112,6 +118,8 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
       y1 = swishf_(y1);
       st2<T>(out + (size_t)(r0 + t0 + t) * kC + c, y0, y1);
     }
+  }
+  __syncthreads();   // s_stat / s_red are reused by the next sub-tile
   }
 }
 

@@ -9,7 +9,7 @@
 //   L<i>.ffn1.ln.w/.b | L<i>.ffn1.w1 [4096,1024] act | .b1 [4096] | .w2 [1024,4096] act | .b2 [1024]
 //   L<i>.attn.ln.w/.b | L<i>.attn.wqkv [3072,1024] act (q|k|v rows) | .bqkv [3072] | .wo [1024,1024] act
 //   | .bo [1024] | .dist [73,64] act
-//   L<i>.conv.ln.w/.b | L<i>.conv.pw1 [2048,1024] act, rows interleaved (a0,g0,a1,g1,...) | .dw [1024,31]
+//   L<i>.conv.ln.w/.b | L<i>.conv.pw1 [2048,1024] act, rows interleaved (a0,g0,a1,g1,...) | .dw [31,1024] (tap-major)
 //   | .dwln.w/.b | .pw2 [1024,1024] act
 //   L<i>.ffn2.* (as ffn1) | L<i>.final.ln.w/.b
 #include <map>

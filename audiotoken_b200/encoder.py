@@ -80,7 +80,7 @@ class SemanticWeights:
             t[q + 'conv.ln.b'] = Fv(sd[c + 'layer_norm.bias'])
             pw1 = sd[c + 'pointwise_conv1.weight'].reshape(2048, 1024)
             t[q + 'conv.pw1'] = W(torch.stack([pw1[:1024], pw1[1024:]], 1).reshape(2048, 1024))
-            t[q + 'conv.dw'] = Fv(sd[c + 'depthwise_conv.weight'].reshape(1024, 31))
+            t[q + 'conv.dw'] = Fv(sd[c + 'depthwise_conv.weight'].reshape(1024, 31).t())   # tap-major [31, 1024]
             t[q + 'conv.dwln.w'] = Fv(sd[c + 'depthwise_layer_norm.weight'])
             t[q + 'conv.dwln.b'] = Fv(sd[c + 'depthwise_layer_norm.bias'])
             t[q + 'conv.pw2'] = W(sd[c + 'pointwise_conv2.weight'].reshape(1024, 1024))

@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 FRAME, HOP = 400, 160
-QTILE, CTILE = 64, 16
+QTILE, CTILE = 64, 64
 
 
 def n_frames(num_samples: int) -> int:

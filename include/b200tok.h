@@ -68,7 +68,7 @@ typedef struct {
   int32_t total_frames;        /* sum of valid log-mel frames                                */
   int32_t total_rows;          /* M: sum over clips of token rows computed                   */
   int32_t n_qtiles;            /* attention work items (64 query rows each)                  */
-  int32_t n_ctiles;            /* depthwise-conv work items (16 rows each)                   */
+  int32_t n_ctiles;            /* depthwise-conv work items (64 rows each)                   */
   int32_t max_rows;            /* longest clip, in rows                                      */
   const int64_t* wave_off;     /* [n_clips]   first sample of clip i in `wave`               */
   const int32_t* frame_off;    /* [n_clips+1] prefix sum of valid frames (1+floor((len-400)/160)) */
@@ -143,7 +143,8 @@ int b2t_relkey_attention(const void* qkv, const void* dist_emb, const b2t_batch*
                          void* out, int precision, int impl, void* stream);
 
 /* HF Wav2Vec2BertConvolutionModule (:213-221): causal depthwise conv k=31 (left pad 30, per
- * clip) -> LayerNorm(1024) -> swish.  x, out: [M, 1024] bf16/fp32; w_dw [1024, 31] fp32.       */
+ * clip) -> LayerNorm(1024) -> swish.  x, out: [M, 1024] bf16/fp32; w_dw fp32, TAP-MAJOR [31, 1024].
+ * Work items (b2t_batch.ctile_*) are 64-row tiles.                                                */
 int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float* ln_weight,
                         const float* ln_bias, const b2t_batch* batch, void* out, int precision,
                         void* stream);

@@ -259,7 +259,7 @@ def test_dwconv_ln_swish(cuda_device, precision):
         off += T
     ref = torch.cat(outs, 0)
     act = torch.bfloat16 if emu else torch.float32
-    out = ops.dwconv_ln_swish(x.to(cuda_device, act), wd.to(cuda_device), lw.to(cuda_device), lb.to(cuda_device), plan, precision)
+    out = ops.dwconv_ln_swish(x.to(cuda_device, act), wd.t().contiguous().to(cuda_device), lw.to(cuda_device), lb.to(cuda_device), plan, precision)
     assert rel_err(out.float(), bf(ref) if emu else ref) < (1e-2 if emu else 2e-5)
 
 
