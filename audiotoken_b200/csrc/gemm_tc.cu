@@ -14,6 +14,7 @@
 // The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Tiles are visited n-fastest so concurrently running CTAs share the A tile in L2.
 #include <cuda.h>
+#include <string>
 #include "gemm_epilogue.cuh"
 #include "vq_cand.cuh"
 
@@ -64,6 +65,21 @@ B2T_DEVICE void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, 
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// pair mode: the load fills THIS CTA's shared memory, the mbarrier may live in the peer (leader) CTA
+B2T_DEVICE void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank 0
+B2T_DEVICE uint32_t mapa_rank0(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+  return r;
+}
+B2T_DEVICE void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 B2T_DEVICE void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -85,6 +101,24 @@ B2T_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uin
 }
 B2T_DEVICE void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+B2T_DEVICE void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+B2T_DEVICE void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+B2T_DEVICE void tmem_alloc_pair(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+B2T_DEVICE void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 B2T_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 B2T_DEVICE void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
@@ -178,11 +212,11 @@ B2T_DEVICE void argmax_chunk(const EpiParams& p, Cand& cand, int col0, const flo
   }
 }
 
-template <int BN>
+template <int BN, bool kPair = false>
 struct SmemLayout {
-  static constexpr int kStageA = kBM * kBK * 2;         // 16 KB
-  static constexpr int kStageB = BN * kBK * 2;          // 32 KB (BN=256)
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStageA = kBM * kBK * 2;                       // 16 KB
+  static constexpr int kStageB = (kPair ? BN / 2 : BN) * kBK * 2;     // 32 KB (BN=256), 16 KB per CTA in pair mode
+  static constexpr int kStages = (BN == 256 && !kPair) ? 4 : 6;
   static constexpr int kTileBytes = kStages * (kStageA + kStageB);
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kEpiStage = 2048;                 // per epilogue warp: 16 rows x 32 fp32 (transposes)
@@ -192,11 +226,18 @@ struct SmemLayout {
 
 // kSplit3: A and W hold [hi | lo] bf16 halves (each Kd = K/3 wide); the K loop runs the three products
 // hi*hi, lo*hi, hi*lo back to back into one accumulator (error-compensated bf16x3 dot product).
-template <int BN, int EPI, bool kSplit3 = false>
+// kMC ("pair mode"): clusters of 2 CTAs (one TPC) run tcgen05.mma.cta_group::2 on a 256 x BN tile: CTA r holds
+// rows r*128.. of A and rows r*128.. of the W tile in ITS shared memory, the leader CTA (rank 0) issues the MMAs
+// for both, each CTA's TMEM receives its own 128 accumulator rows and each CTA runs its own epilogue.  With one
+// CTA per tile the tensor core's operand reads (96 B/clk) plus the TMA fill (96 B/clk) exceed the 128 B/clk of
+// shared-memory bandwidth; in pair mode both drop to 64 B/clk.  Barrier protocol: every TMA load signals the
+// LEADER's full barrier; the leader's tcgen05.commit (multicast) releases the stage / publishes the accumulator
+// in both CTAs; both CTAs' epilogue warps arrive on the leader's tmem-empty barrier.
+template <int BN, int EPI, bool kSplit3 = false, bool kMC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                int K, EpiParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, kMC>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -212,20 +253,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = p.N / BN;
   const int tiles_m = (p.M + kBM - 1) / kBM;
-  const int num_tiles = tiles_m * tiles_n;
+  uint32_t cta_rank = 0;
+  if constexpr (kMC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  // work items: single tiles, or (kMC) pairs of m-tiles handled by one cluster
+  const int w_first = kMC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_stride = kMC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_count = kMC ? ((tiles_m + 1) / 2) * tiles_n : tiles_m * tiles_n;
+  auto tile_m0 = [&](int w) { return (kMC ? 2 * (w / tiles_n) + (int)cta_rank : w / tiles_n) * kBM; };
+  auto tile_n0 = [&](int w) { return (w % tiles_n) * BN; };
   const int num_kb = (K + kBK - 1) / kBK;
   constexpr uint32_t kTmemCols = 2 * BN;   // 512 (BN=256) or 256 (BN=128): powers of two
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kMC ? 2 * kEpiWarps : kEpiWarps); }
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) { if constexpr (kMC) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kMC) {   // barrier inits must be visible to the peer before it multicasts into this CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -233,8 +285,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      for (int t = w_first; t < w_count; t += w_stride) {
+        const int m0 = tile_m0(t), n0 = tile_n0(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           int ka = kb * kBK, kw = kb * kBK;
           if constexpr (kSplit3) {
@@ -243,20 +295,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             kw = (seg == 2 ? nkd : 0) * kBK + j * kBK;     // W: hi, hi, lo
           }
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), L::kStageA + L::kStageB);
-          tma_load_2d(sA + stage * L::kStageA, &map_a, full_bar(stage), ka, m0);
-          tma_load_2d(sB + stage * L::kStageB, &map_w, full_bar(stage), kw, n0);
+          if constexpr (kMC) {
+            // both CTAs fill their own shared memory but signal the leader's barrier (it expects all 4 loads)
+            const uint32_t lead_full = mapa_rank0(full_bar(stage));
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * (L::kStageA + L::kStageB));
+            tma_load_2d_pair(sA + stage * L::kStageA, &map_a, lead_full, ka, m0);
+            tma_load_2d_pair(sB + stage * L::kStageB, &map_w, lead_full, kw, n0 + (int)cta_rank * (BN / 2));
+          } else {
+            mbar_expect_tx(full_bar(stage), L::kStageA + L::kStageB);
+            tma_load_2d(sA + stage * L::kStageA, &map_a, full_bar(stage), ka, m0);
+            tma_load_2d(sB + stage * L::kStageB, &map_w, full_bar(stage), kw, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
+    // ===== MMA issuer (pair mode: the leader CTA issues for both) =====
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(kMC ? 2 * kBM : kBM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = w_first; t < w_count; t += w_stride) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -268,12 +328,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 field
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kMC) umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));   // implies tcgen05.fence::before_thread_sync
+          if constexpr (kMC) umma_commit_pair(empty_bar(stage), (uint16_t)3);   // frees the slot in both CTAs
+          else umma_commit(empty_bar(stage));   // implies tcgen05.fence::before_thread_sync
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if constexpr (kMC) umma_commit_pair(tfull_bar(acc), (uint16_t)3);
+        else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -285,16 +348,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float4* stg = reinterpret_cast<float4*>(smem_raw + (base - smem_u32(smem_raw)) + L::kEpiOff + (warp - 2) * L::kEpiStage);
     static_assert(kChunks % 2 == 0, "chunks are processed in pairs");
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+    for (int t = w_first; t < w_count; t += w_stride) {
+      const int m0 = tile_m0(t), n0 = tile_n0(t);
       if constexpr (EPI == B2T_EPI_RESID) {
         // pull the residual region of the NEXT tile of this CTA into L2 while this tile is processed:
         // the read-modify-write below is otherwise a chain of exposed DRAM round trips
-        const int tn = (t == (int)blockIdx.x) ? t : t + (int)gridDim.x;   // first tile: prefetch itself
-        for (int tp = tn; tp <= t + (int)gridDim.x && tp < num_tiles; tp += gridDim.x) {
-          const int pr = (tp / tiles_n) * kBM + quad * 32 + lane;
+        const int tn = (t == w_first) ? t : t + w_stride;   // first tile: prefetch itself
+        for (int tp = tn; tp <= t + w_stride && tp < w_count; tp += w_stride) {
+          const int pr = tile_m0(tp) + quad * 32 + lane;
           if (pr < p.M) {
-            const float* base_p = p.resid + (size_t)pr * p.N + (tp % tiles_n) * BN + part * kChunks * 32;
+            const float* base_p = p.resid + (size_t)pr * p.N + tile_n0(tp) + part * kChunks * 32;
 #pragma unroll
             for (int i = 0; i < kChunks; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base_p + i * 32));
           }
@@ -315,7 +378,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // the accumulator is now in registers: hand the TMEM buffer back before the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if constexpr (kMC) mbar_arrive_cluster(mapa_rank0(tempty_bar(acc)));
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         float v[32];
 #pragma unroll
@@ -340,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if constexpr (EPI == kEpiArgmax) {
         // one partial record per (row, column slice): slice = n-tile * (warps per quadrant) + part
         if (row < p.M)
-          reinterpret_cast<Cand*>(p.out)[(size_t)row * p.ldo + (t % tiles_n) * (kEpiWarps / 4) + part] = cand;
+          reinterpret_cast<Cand*>(p.out)[(size_t)row * p.ldo + (n0 / BN) * (kEpiWarps / 4) + part] = cand;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -348,9 +414,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kMC) {   // the peer may still multicast into / arrive on this CTA's shared memory until it is done too
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kMC) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -387,15 +457,46 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box
   return B2T_OK;
 }
 
+// cluster-of-2 launch of a multicast kernel instance
+template <typename Kern>
+int launch_cluster2(Kern kern, int pairs, int smem, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mw, int K,
+                    const EpiParams& p) {
+  int grid = b2t_num_sms() & ~1;
+  if (2 * pairs < grid) grid = 2 * pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B2T_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, K, p));
+  b2t_count_launch();
+  return B2T_OK;
+}
+
+bool g_multicast = true;   // b2t_set_option("gemm_multicast", 0/1)
+
 template <int BN, int EPI>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st) {
   using L = SmemLayout<BN>;
+  const int tiles_m = (a->M + kBM - 1) / kBM, tiles_n = a->N / BN;
+  if constexpr (BN == 256) {
+    if (g_multicast && tiles_m >= 2) {
+      using LP = SmemLayout<BN, true>;
+      static bool cfg_mc = false;
+      if (!cfg_mc) {
+        B2T_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::kTotal));
+        cfg_mc = true;
+      }
+      return launch_cluster2(gemm_tc_kernel<BN, EPI, false, true>, ((tiles_m + 1) / 2) * tiles_n, LP::kTotal, st, ma, mw, a->K, p);
+    }
+  }
   static bool configured = false;
   if (!configured) {
     B2T_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int tiles = ((a->M + kBM - 1) / kBM) * (a->N / BN);
+  const int tiles = tiles_m * tiles_n;
   int grid = b2t_num_sms();
   if (tiles < grid) grid = tiles;
   gemm_tc_kernel<BN, EPI><<<grid, kThreads, L::kTotal, st>>>(ma, mw, a->K, p);
@@ -443,6 +544,13 @@ int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, i
   return B2T_OK;
 }
 
+extern "C" int b2t_set_option(const char* name, int value) {
+  B2T_REQUIRE(name, B2T_ERR_ARG, "b2t_set_option: null name");
+  if (std::string(name) == "gemm_multicast") { g_multicast = value != 0; return B2T_OK; }
+  b2t_set_error("b2t_set_option: unknown option '%s'", name);
+  return B2T_ERR_ARG;
+}
+
 int b2t_gemm_tensor(const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st) {
   B2T_REQUIRE(a->N % 128 == 0, B2T_ERR_ARG, "b2t_gemm(tensor): N must be a multiple of 128 (N=%d)", a->N);
   B2T_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->W % 16) == 0, B2T_ERR_ARG,
@@ -451,7 +559,8 @@ int b2t_gemm_tensor(const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st)
   const int bn = (a->N % 256 == 0) ? 256 : 128;
   int rc = make_map(&ma, a->A, a->M, a->K, a->lda, kBM);
   if (rc != B2T_OK) return rc;
-  rc = make_map(&mw, a->W, a->N, a->K, a->K, bn);
+  const bool mc = bn == 256 && g_multicast && (a->M + kBM - 1) / kBM >= 2;
+  rc = make_map(&mw, a->W, a->N, a->K, a->K, mc ? bn / 2 : bn);
   if (rc != B2T_OK) return rc;
   if (bn == 256) return dispatch_epi<256>(ma, mw, a, p, st);
   return dispatch_epi<128>(ma, mw, a, p, st);

@@ -20,7 +20,7 @@ EPI_BIAS, EPI_BIAS_SWISH, EPI_RESID, EPI_GLU, EPI_BIAS_MASK = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR = 0, 1, 2
 
 EXPORTS = [
-    'b2t_version', 'b2t_last_error', 'b2t_device_check', 'b2t_fbank_logmel', 'b2t_fbank_stats',
+    'b2t_version', 'b2t_last_error', 'b2t_device_check', 'b2t_set_option', 'b2t_fbank_logmel', 'b2t_fbank_stats',
     'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_dwconv_ln_swish',
     'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_vq_debug_stats', 'b2t_semantic_create', 'b2t_semantic_destroy',
     'b2t_semantic_set_tensor', 'b2t_semantic_workspace_bytes', 'b2t_semantic_encode',
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
     lib.b2t_version.restype = i32
     lib.b2t_last_error.restype = C.c_char_p
     lib.b2t_device_check.argtypes = [i32]
+    lib.b2t_set_option.argtypes = [C.c_char_p, i32]
     lib.b2t_fbank_logmel.argtypes = [vp, C.POINTER(Batch), C.POINTER(FbankTables), vp, i32, vp]
     lib.b2t_fbank_stats.argtypes = [vp, C.POINTER(Batch), vp, vp, vp]
     lib.b2t_fbank_stack_ln.argtypes = [vp, vp, vp, C.POINTER(Batch), vp, vp, vp, vp, vp, i32, vp]

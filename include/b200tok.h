@@ -61,6 +61,9 @@ int b2t_version(void);
 const char* b2t_last_error(void);
 /* B2T_OK iff `device` is compute capability 10.x. */
 int b2t_device_check(int device);
+/* Library-wide switches (A/B measurements): "gemm_multicast" 0/1 — run the tcgen05 GEMM as 2-CTA
+ * clusters issuing tcgen05.mma.cta_group::2 on 256 x 256 tiles (default 1) or one CTA per 128 x 256 tile. */
+int b2t_set_option(const char* name, int value);
 
 /* ---- batch descriptor (all arrays on the device, built by the host packer) --------------- */
 typedef struct {

@@ -313,3 +313,24 @@ def test_vq_argmin_near_ties_and_layernorm(cuda_device, impl):
     idx3, tie3 = quantize.nearest_centroid(emb, cb)
     _, o = ops.vq_argmin(h.to(cuda_device), cb.to(cuda_device), apply_ln=True, impl=impl)
     assert (o.cpu().long()[~tie3] == idx3[~tie3]).float().mean() > 0.995
+
+
+def test_gemm_multicast_clusters_bit_identical(cuda_device):
+    """2-CTA clusters with TMA multicast change data movement only: results equal the 1-CTA kernel bitwise."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(123)
+    for M, N, K, epi in [(5000, 4096, 1024, L.EPI_BIAS_SWISH), (4099, 1024, 4096, L.EPI_RESID), (300, 3072, 1024, L.EPI_BIAS),
+                         (129, 2048, 1024, L.EPI_GLU), (257, 1024, 160, L.EPI_BIAS_MASK)]:
+        A = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
+        W = (torch.randn(N, K, generator=g) * 0.05).to(cuda_device, torch.bfloat16)
+        bias = None if epi == L.EPI_GLU else bf(torch.randn(N, generator=g)).to(cuda_device)
+        resid = torch.randn(M, N, generator=g).to(cuda_device)
+        valid = (torch.arange(M) % 4 != 1).to(torch.uint8).to(cuda_device)
+        outs = []
+        for mc in (0, 1):
+            L.check(lib.b2t_set_option(b'gemm_multicast', mc), 'set_option')
+            o = ops.gemm(A, W, bias, epi, 'bf16', L.IMPL_TENSOR, resid=resid.clone(), row_valid=valid, alpha=0.5)
+            torch.cuda.synchronize()
+            outs.append(o.float().cpu())
+        L.check(lib.b2t_set_option(b'gemm_multicast', 1), 'set_option')
+        assert torch.equal(outs[0], outs[1]), (M, N, K, epi)

@@ -40,9 +40,10 @@ def main():
             W = (torch.randn(N, K, device=dev) * 0.03).to(torch.bfloat16)
             bias = None if epi == L.EPI_GLU else torch.zeros(N, device=dev)
             resid = torch.zeros(M, N, device=dev)
-            for impl, nm in ((L.IMPL_TENSOR, 'tc'), (L.IMPL_SIMT, 'simt')):
-                ms = timeit(lambda: ops.gemm(A, W, bias, epi, 'bf16', impl, resid=resid), iters=5 if impl == L.IMPL_SIMT else 20)
-                out[f'gemm_{nm}_N{N}_K{K}_e{epi}'] = dict(ms=ms, tflops=2.0 * M * N * K / ms / 1e9)
+            for mc in (0, 1):
+                L.load().b2t_set_option(b'gemm_multicast', mc)
+                ms = timeit(lambda: ops.gemm(A, W, bias, epi, 'bf16', L.IMPL_TENSOR, resid=resid), iters=20)
+                out[f'gemm_tc_mc{mc}_N{N}_K{K}_e{epi}'] = dict(ms=ms, tflops=2.0 * M * N * K / ms / 1e9)
             # cuBLAS reference point (library; not used by the product)
             ms = timeit(lambda: torch.matmul(A, W.t()), iters=20)
             out[f'gemm_cublas_N{N}_K{K}'] = dict(ms=ms, tflops=2.0 * M * N * K / ms / 1e9)
