@@ -253,16 +253,19 @@ rvq_kernel(const float* __restrict__ emb, int rows, const float* __restrict__ co
       const float ch = cmax_half[q];
       const float delta = 2.0f * 128.0f * 5.9604645e-8f * ((float)sqrt(rr) * sqrtf(2.0f * ch) + ch);
       int best;
-      if (!(c.v3 >= c.v1 - 2.0f * delta)) {
-        double d1 = 0.0, d2 = 0.0;
-        const float* e1 = E + (size_t)c.i1 * 128;
-        const float* e2 = E + (size_t)c.i2 * 128;
-        for (int d = 0; d < 128; ++d) {
-          const double r = (double)s.rT[d][tid];
-          const double a1 = r - (double)e1[d], a2 = r - (double)e2[d];
-          d1 += a1 * a1; d2 += a2 * a2;
+      if (!(c.v4 >= c.v1 - 2.0f * delta)) {
+        const int ci[3] = {c.i1, c.i2, c.i3};
+        const float cv[3] = {c.v1, c.v2, c.v3};
+        double bd = INFINITY;
+        best = c.i1;
+        for (int u = 0; u < 3; ++u) {
+          if (u > 0 && !(cv[u] >= c.v1 - 2.0f * delta)) break;
+          if (ci[u] >= 1024) break;
+          const float* e = E + (size_t)ci[u] * 128;
+          double dd = 0.0;
+          for (int d = 0; d < 128; ++d) { const double a_ = (double)s.rT[d][tid] - (double)e[d]; dd += a_ * a_; }
+          if (dd < bd || (dd == bd && ci[u] < best)) { bd = dd; best = ci[u]; }
         }
-        best = (d2 < d1 || (d2 == d1 && c.i2 < c.i1)) ? c.i2 : c.i1;
       } else {
         float run = -INFINITY;
         double bd = INFINITY;

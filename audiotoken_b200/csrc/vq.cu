@@ -149,8 +149,9 @@ vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const flo
   for (int o = 16; o > 0; o >>= 1) {
     Cand other;
     other.v1 = __shfl_xor_sync(0xffffffffu, c.v1, o); other.v2 = __shfl_xor_sync(0xffffffffu, c.v2, o);
-    other.v3 = __shfl_xor_sync(0xffffffffu, c.v3, o); other.i1 = __shfl_xor_sync(0xffffffffu, c.i1, o);
-    other.i2 = __shfl_xor_sync(0xffffffffu, c.i2, o);
+    other.v3 = __shfl_xor_sync(0xffffffffu, c.v3, o); other.v4 = __shfl_xor_sync(0xffffffffu, c.v4, o);
+    other.i1 = __shfl_xor_sync(0xffffffffu, c.i1, o); other.i2 = __shfl_xor_sync(0xffffffffu, c.i2, o);
+    other.i3 = __shfl_xor_sync(0xffffffffu, c.i3, o);
     cand_merge(c, other);
   }
   // |x|: bound on the fast-pass error  delta = rel_eps * (|x| |c|max + 0.5 |c|max^2)
@@ -163,10 +164,19 @@ vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const flo
   int best;
   if (K == 1) {
     best = 0;
-  } else if (!(c.v3 >= c.v1 - 2.0f * delta) && c.i1 < K) {
+  } else if (!(c.v4 >= c.v1 - 2.0f * delta) && c.i1 < K) {
+    // certified: only the three candidates can be the exact winner; skip those the bound already excludes
     const double d1 = exact_dist(xr, cb + (size_t)c.i1 * D, D, lane);
-    const double d2 = c.i2 < K ? exact_dist(xr, cb + (size_t)c.i2 * D, D, lane) : INFINITY;
-    best = (d2 < d1 || (d2 == d1 && c.i2 < c.i1)) ? c.i2 : c.i1;
+    best = c.i1;
+    double bd = d1;
+    if (c.i2 < K && c.v2 >= c.v1 - 2.0f * delta) {
+      const double d2 = exact_dist(xr, cb + (size_t)c.i2 * D, D, lane);
+      if (d2 < bd || (d2 == bd && c.i2 < best)) { bd = d2; best = c.i2; }
+    }
+    if (c.i3 < K && c.v3 >= c.v1 - 2.0f * delta) {
+      const double d3 = exact_dist(xr, cb + (size_t)c.i3 * D, D, lane);
+      if (d3 < bd || (d3 == bd && c.i3 < best)) { bd = d3; best = c.i3; }
+    }
     if (lane == 0 && max_err) {
       // observed fast-pass error on the best candidate, in units of the bound's scale
       const float obs = fabsf(c.v1 - (float)(0.5 * (xx - d1))) / ((float)sqrt(xx) * cmax + cmax_half);
@@ -174,30 +184,35 @@ vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const flo
     }
   } else {
     if (lane == 0 && n_fallback) atomicAdd(n_fallback, 1u);
-    // re-scan: lane-strided centroids, fp32 filter, fp64 re-score of everything near the running max
+    // re-scan, warp-cooperative and coalesced: 4 centroids per round, lanes stride the dimension; fp32
+    // filter against the running maximum, fp64 re-score of everything within the bound
     float run = -INFINITY;
     double bd = INFINITY;
     int bi = 0x7fffffff;
-    for (int k = lane; k < K; k += 32) {
-      const float* ck = cb + (size_t)k * D;
-      float a = 0.f;
-      for (int d = 0; d < D; d += 4) {
-        float4 xv = *reinterpret_cast<const float4*>(xr + d), cv = *reinterpret_cast<const float4*>(ck + d);
-        a = fmaf(xv.x, cv.x, a); a = fmaf(xv.y, cv.y, a); a = fmaf(xv.z, cv.z, a); a = fmaf(xv.w, cv.w, a);
-      }
-      a -= __ldg(hn + k);
-      if (a >= run - 2.0f * delta) {
-        double dd = 0.0;
-        for (int d = 0; d < D; ++d) { double t = (double)xr[d] - (double)ck[d]; dd += t * t; }
-        if (dd < bd || (dd == bd && k < bi)) { bd = dd; bi = k; }
-      }
-      run = fmaxf(run, a);
-    }
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int d = lane * 4; d < D; d += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + d);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double od = __shfl_xor_sync(0xffffffffu, bd, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        for (int u = 0; u < 4; ++u) {
+          if (k0 + u < K) {
+            const float4 cv = *reinterpret_cast<const float4*>(cb + (size_t)(k0 + u) * D + d);
+            a4[u] = fmaf(xv.x, cv.x, a4[u]); a4[u] = fmaf(xv.y, cv.y, a4[u]);
+            a4[u] = fmaf(xv.z, cv.z, a4[u]); a4[u] = fmaf(xv.w, cv.w, a4[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        if (k >= K) break;
+        const float a = warp_sum(a4[u]) - __ldg(hn + k);
+        if (a >= run - 2.0f * delta) {
+          const double dd = exact_dist(xr, cb + (size_t)k * D, D, lane);
+          if (dd < bd || (dd == bd && k < bi)) { bd = dd; bi = k; }
+        }
+        run = fmaxf(run, a);
+      }
     }
     best = bi;
   }
@@ -262,8 +277,8 @@ extern "C" int b2t_vq_argmin(const float* x, int ldx, int rows, int dim, const f
                              const float* half_norm, int codebook_size, int apply_ln, int impl, int16_t* out,
                              int32_t* out_i32, void* workspace, size_t workspace_bytes, void* stream) {
   B2T_REQUIRE(x && codebook && (out || out_i32) && workspace, B2T_ERR_ARG, "b2t_vq_argmin: null argument");
-  B2T_REQUIRE(dim % 32 == 0 && dim >= 32 && ldx % 4 == 0 && ldx >= dim, B2T_ERR_ARG,
-              "b2t_vq_argmin: dim must be a multiple of 32 and ldx a multiple of 4 (dim=%d ldx=%d)", dim, ldx);
+  B2T_REQUIRE(dim % 32 == 0 && dim >= 32 && ldx % 4 == 0 && ldx >= dim && ((uintptr_t)x % 16) == 0 && ((uintptr_t)codebook % 16) == 0, B2T_ERR_ARG,
+              "b2t_vq_argmin: dim must be a multiple of 32, ldx a multiple of 4, pointers 16-byte aligned (dim=%d ldx=%d)", dim, ldx);
   B2T_REQUIRE(codebook_size >= 1 && codebook_size <= 32768, B2T_ERR_ARG,
               "b2t_vq_argmin: codebook_size must be in [1, 32768] for int16 tokens (got %d)", codebook_size);
   B2T_REQUIRE(!apply_ln || dim == 1024, B2T_ERR_ARG, "b2t_vq_argmin: fused LayerNorm needs dim == 1024");
