@@ -8,7 +8,8 @@
 // Two implementations:
 //   attention_simt_kernel : CUDA-core, fp32 maths, any activation type — B2T_PREC_FP32 path and the
 //                           on-device cross-check of the tensor-core kernel.
-//   attention_mma_kernel  : bf16 mma.sync m16n8k16 flash-style kernel (B2T_PREC_BF16).
+//   attention_mma_kernel  : bf16 mma.sync m16n8k16 flash-style kernel (B2T_IMPL_MMA_SYNC; kept as a cross-check).
+//   attention_tc_kernel   : tcgen05 / TMEM / TMA kernel in attention_tc.cu (B2T_PREC_BF16 default).
 #include "common.cuh"
 
 namespace {
@@ -368,6 +369,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 
 }  // namespace
 
+int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, cudaStream_t st);  // attention_tc.cu
+
 extern "C" int b2t_relkey_attention(const void* qkv, const void* dist_emb, const b2t_batch* b,
                                     void* out, int precision, int impl, void* stream) {
   B2T_REQUIRE(qkv && dist_emb && b && out, B2T_ERR_ARG, "b2t_relkey_attention: null argument");
@@ -388,6 +391,8 @@ extern "C" int b2t_relkey_attention(const void* qkv, const void* dist_emb, const
     attention_simt_kernel<__nv_bfloat16, true><<<grid, 256, sizeof(SimtSmem), st>>>(
         (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dist_emb, b->row_off, b->valid_rows, b->qtile_clip, b->qtile_q0,
         (__nv_bfloat16*)out);
+  } else if (impl != B2T_IMPL_MMA_SYNC) {
+    return b2t_attention_tensor_tc(qkv, dist_emb, b, out, st);
   } else {
     static bool cfg = false;
     if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem))); cfg = true; }

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libb200tok.so')
 
 PREC_BF16, PREC_FP32 = 0, 1
 EPI_BIAS, EPI_BIAS_SWISH, EPI_RESID, EPI_GLU, EPI_BIAS_MASK = 0, 1, 2, 3, 4
-IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR, IMPL_MMA_SYNC = 0, 1, 2, 3
 
 EXPORTS = [
     'b2t_version', 'b2t_last_error', 'b2t_device_check', 'b2t_set_option', 'b2t_fbank_logmel', 'b2t_fbank_stats',
@@ -40,7 +40,8 @@ class Batch(C.Structure):
                 ('n_qtiles', C.c_int32), ('n_ctiles', C.c_int32), ('max_rows', C.c_int32),
                 ('wave_off', C.c_void_p), ('frame_off', C.c_void_p), ('stack_frames', C.c_void_p),
                 ('row_off', C.c_void_p), ('valid_rows', C.c_void_p), ('qtile_clip', C.c_void_p),
-                ('qtile_q0', C.c_void_p), ('ctile_clip', C.c_void_p), ('ctile_t0', C.c_void_p)]
+                ('qtile_q0', C.c_void_p), ('ctile_clip', C.c_void_p), ('ctile_t0', C.c_void_p),
+                ('n_qtiles128', C.c_int32), ('qtile128_clip', C.c_void_p), ('qtile128_q0', C.c_void_p)]
 
 
 class FbankTables(C.Structure):

@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 FRAME, HOP = 400, 160
-QTILE, CTILE = 64, 64
+QTILE, CTILE, QTILE128 = 64, 64, 128
 
 
 def n_frames(num_samples: int) -> int:
@@ -56,6 +56,8 @@ class SemanticPlan:
     qtile_q0: np.ndarray
     ctile_clip: np.ndarray
     ctile_t0: np.ndarray
+    qtile128_clip: np.ndarray
+    qtile128_q0: np.ndarray
 
     @property
     def total_rows(self) -> int:
@@ -109,11 +111,14 @@ def plan_semantic(lengths: Sequence[int], wave_offsets: Sequence[int], padded_sa
         raise ValueError('batch too large for int32 offsets')
     # attention work items, heaviest (most keys) first so the tail of the grid is made of short clips
     order = np.argsort(-valid_rows, kind='stable')
-    qc, qq = [], []
+    qc, qq, qc8, qq8 = [], [], [], []
     for i in order:
         q0 = np.arange(0, rows_arr[i], QTILE, dtype=np.int32)
         qc.append(np.full(q0.shape, i, dtype=np.int32))
         qq.append(q0)
+        q8 = np.arange(0, rows_arr[i], QTILE128, dtype=np.int32)
+        qc8.append(np.full(q8.shape, i, dtype=np.int32))
+        qq8.append(q8)
     cc, ct = [], []
     for i in range(n):
         t0 = np.arange(0, rows_arr[i], CTILE, dtype=np.int32)
@@ -125,7 +130,8 @@ def plan_semantic(lengths: Sequence[int], wave_offsets: Sequence[int], padded_sa
         frame_off=frame_off.astype(np.int32), stack_frames=stack.astype(np.int32),
         row_off=row_off.astype(np.int32), valid_rows=valid_rows.astype(np.int32),
         qtile_clip=np.concatenate(qc), qtile_q0=np.concatenate(qq),
-        ctile_clip=np.concatenate(cc), ctile_t0=np.concatenate(ct))
+        ctile_clip=np.concatenate(cc), ctile_t0=np.concatenate(ct),
+        qtile128_clip=np.concatenate(qc8), qtile128_q0=np.concatenate(qq8))
 
 
 class DeviceBatch:
@@ -136,7 +142,7 @@ class DeviceBatch:
         from . import lib as L
         self.plan = plan
         i32 = [plan.frame_off, plan.stack_frames, plan.row_off, plan.valid_rows, plan.qtile_clip,
-               plan.qtile_q0, plan.ctile_clip, plan.ctile_t0]
+               plan.qtile_q0, plan.ctile_clip, plan.ctile_t0, plan.qtile128_clip, plan.qtile128_q0]
         # one pinned staging buffer, one H2D copy; int64 wave offsets first (8-byte aligned)
         n64 = plan.wave_off.size
         sizes = [a.size for a in i32]
@@ -163,7 +169,8 @@ class DeviceBatch:
         b.max_rows = int(plan.rows.max()) if plan.n_clips else 0
         b.wave_off = base
         (b.frame_off, b.stack_frames, b.row_off, b.valid_rows, b.qtile_clip, b.qtile_q0,
-         b.ctile_clip, b.ctile_t0) = p
+         b.ctile_clip, b.ctile_t0, b.qtile128_clip, b.qtile128_q0) = p
+        b.n_qtiles128 = int(plan.qtile128_clip.size)
         self.c = b
 
     @property

@@ -54,7 +54,7 @@ typedef enum {
   B2T_EPI_BIAS_MASK = 4    /* out = row_valid ? r16(acc + bias) : 0, written to the fp32 stream */
 } b2t_epilogue;
 
-typedef enum { B2T_IMPL_AUTO = 0, B2T_IMPL_SIMT = 1, B2T_IMPL_TENSOR = 2 } b2t_impl;
+typedef enum { B2T_IMPL_AUTO = 0, B2T_IMPL_SIMT = 1, B2T_IMPL_TENSOR = 2 /* tcgen05 */, B2T_IMPL_MMA_SYNC = 3 /* legacy mma.sync (attention only) */ } b2t_impl;
 
 /* ---- library --------------------------------------------------------------------------- */
 int b2t_version(void);
@@ -82,6 +82,9 @@ typedef struct {
   const int32_t* qtile_q0;     /* [n_qtiles]  first query row (within the clip)              */
   const int32_t* ctile_clip;   /* [n_ctiles]                                                 */
   const int32_t* ctile_t0;     /* [n_ctiles]                                                 */
+  int32_t n_qtiles128;         /* attention work items of the tcgen05 kernel (128 query rows each) */
+  const int32_t* qtile128_clip; /* [n_qtiles128]                                              */
+  const int32_t* qtile128_q0;  /* [n_qtiles128]                                              */
 } b2t_batch;
 
 /* ---- front end: reference audiotoken/processors.py ------------------------------------------ */

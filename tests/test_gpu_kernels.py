@@ -223,8 +223,8 @@ def test_attention_simt_fp32(cuda_device, rows, valid):
     assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
 
 
-@pytest.mark.parametrize('impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
-@pytest.mark.parametrize('rows,valid', ATTN_CASES)
+@pytest.mark.parametrize('impl', [L.IMPL_SIMT, L.IMPL_TENSOR, L.IMPL_MMA_SYNC])
+@pytest.mark.parametrize('rows,valid', ATTN_CASES + [([1500, 300, 129], [1499, 257, 128])])
 def test_attention_bf16(cuda_device, impl, rows, valid):
     qkv, E = _attn_case(10 + len(rows), rows, valid)
     qkv, E = bf(qkv), bf(E)

@@ -56,7 +56,7 @@ def test_fp32_pipeline_matches_reference_golden(cuda_device, golden_dir, n_layer
 
 
 @pytest.mark.parametrize('gemm_impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
-@pytest.mark.parametrize('attn_impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
+@pytest.mark.parametrize('attn_impl', [L.IMPL_SIMT, L.IMPL_TENSOR, L.IMPL_MMA_SYNC])
 def test_bf16_pipeline_matches_autocast_oracle(cuda_device, golden_dir, gemm_impl, attn_impl):
     g, wave, mask, lengths = golden_batch(golden_dir)
     n_layers = 2
