@@ -1,14 +1,14 @@
 // Relative-key flash attention on tcgen05 / TMEM / TMA (sm_100a)
 // (reference audiotoken/modeling_wav2vec2_bert.py:37-77; see attention.cu for the maths).
 //
-// One CTA = one (clip, 128-query tile, head); 192 threads:
+// One CTA = one (clip, 128-query tile), persistent over the 16 heads; 576 threads:
 //   warp 0    TMA producer : Q tile + distance embedding E once, then a 3-stage ring of 128-key K and V tiles
 //                            (all boxes 64 x rows out of the packed qkv matrix, SWIZZLE_128B).
 //   warp 1    MMA issuer   : R = Q.E^T (128x80), then per key tile S = Q.K^T (128x128x64, 4 tcgen05.mma) and
 //                            O_tile = P.V (128x64x128, 8 tcgen05.mma, V consumed MN-major straight from the TMA
 //                            layout); S and O_tile are double-buffered in TMEM so QK^T of tile i+1 overlaps the
 //                            softmax of tile i.
-//   warps 2-5 softmax      : thread = query row = TMEM lane.  tcgen05.ld the S row, scale + relative-key bias
+//   warps 2-9 softmax      : thread = (query row = TMEM lane, 64-key half).  tcgen05.ld the S half row, scale + relative-key bias
 //                            (gathered from the thread's own R row only inside the diagonal band, a per-row
 //                            constant elsewhere) + key mask, row max / exp2 / row sum without any shuffle,
 //                            P -> bf16 -> shared memory in the K-major SWIZZLE_128B layout the PV MMA reads,
@@ -20,21 +20,29 @@ namespace {
 
 constexpr int kHeads = 16, kHD = 64, kRel = 73, kLeft = 64, kRight = 8;
 constexpr int kQKV = 3 * kHeads * kHD, kH = kHeads * kHD;
-constexpr int kQT = 128, kKT = 128, kStages = 3;
-constexpr int kThreadsAttn = 192;
+constexpr int kQT = 128, kKT = 64, kStages = 2;
+constexpr int kSoftmaxWarps = 8;                 // two warps per TMEM lane quadrant: each owns a 32-key slice of S
+constexpr int kThreadsAttn = 64 + 32 * kSoftmaxWarps;
 
+// Two CTAs are resident per SM (<= 113 KB shared memory, 256 TMEM columns, 320 threads each): while one CTA
+// sits in a TMEM-load / barrier / proxy-fence latency the other one computes — the two softmax pipelines
+// interleave without any explicit ping-pong protocol.
 struct AttnSmem {
   static constexpr int kQ = 0;                                  // 16 KB
-  static constexpr int kKV = kQ + kQT * 128;                    // kStages x (K 16 KB + V 16 KB)
-  static constexpr int kP = kKV + kStages * 2 * kKT * 128;      // 2 x 32 KB
-  static constexpr int kE = kP + 2 * 2 * kQT * 128;             // 80 x 128 B = 10 KB (1024-aligned)
-  static constexpr int kR = kE + 80 * 128;                      // [128][80] bf16 = 20 KB
-  static constexpr int kBars = kR + kQT * 80 * 2;
+  static constexpr int kKV = kQ + kQT * 128;                    // kStages x (K 8 KB + V 8 KB)
+  static constexpr int kP = kKV + kStages * 2 * kKT * 128;      // 2 x 16 KB; buffer 1 first stages E (80 x 128 B)
+  static constexpr int kE = kP + kQT * 128;                     // = P buffer 1 (E is dead once R has been computed)
+  static constexpr int kR = kP + 2 * kQT * 128;                 // [128][80] bf16 = 20 KB
+  static constexpr int kMax = kR + kQT * 80 * 2;                // row-max exchange [2 slots][kWG][128] fp32
+  static constexpr int kSum = kMax + 2 * 4 * kQT * 4;           // final row-sum exchange [kWG][128] fp32
+  static constexpr int kBars = kSum + 4 * kQT * 4;
   static constexpr int kTotal = kBars + 256 + 1024;
 };
+static_assert(2 * AttnSmem::kTotal <= 227 * 1024, "two CTAs per SM");
 // barrier slots (8 bytes each)
-enum { B_QFULL = 0, B_RFULL, B_KVFULL, B_KVEMPTY = B_KVFULL + kStages, B_SFULL = B_KVEMPTY + kStages, B_SEMPTY = B_SFULL + 2,
-       B_PFULL = B_SEMPTY + 2, B_PEMPTY = B_PFULL + 2, B_PVFULL = B_PEMPTY + 2, B_PVEMPTY = B_PVFULL + 2, B_COUNT = B_PVEMPTY + 2 };
+enum { B_EFULL = 0, B_QFULL, B_QEMPTY = B_QFULL + 2, B_RFULL = B_QEMPTY + 2, B_REMPTY, B_KVFULL, B_KVEMPTY = B_KVFULL + kStages,
+       B_SFULL = B_KVEMPTY + kStages, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2, B_PEMPTY = B_PFULL + 2,
+       B_PVFULL = B_PEMPTY + 2, B_PVEMPTY = B_PVFULL + 2, B_COUNT = B_PVEMPTY + 2 };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area");
 
 B2T_DEVICE float ex2a(float x) {
@@ -54,12 +62,18 @@ B2T_DEVICE void tmem_ld_32x32_x16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+B2T_DEVICE void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32_nowait(taddr, r); }
+B2T_DEVICE void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32_x16_nowait(taddr, r); }
 
-__global__ void __launch_bounds__(kThreadsAttn, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_e,
+// The CTA is persistent over the 16 heads of its (clip, query tile): barriers, the TMEM allocation and E are
+// set up once, the producer prefetches the next head's Q and K/V while the softmax warps finish the current
+// head.  g = head * nkt + i is the running key-tile counter that drives every ring / phase.
+__global__ void __launch_bounds__(kThreadsAttn, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
+                    const __grid_constant__ CUtensorMap map_e,
                     const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
                     const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
-                    __nv_bfloat16* __restrict__ out) {
+                    __nv_bfloat16* __restrict__ out, int hpc /* heads per CTA: blockIdx.y selects the group */) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -70,41 +84,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + AttnSmem::kBars + 8 * B_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int clip = qtile_clip[blockIdx.x], q0 = qtile_q0[blockIdx.x], head = blockIdx.y;
+  const int clip = qtile_clip[blockIdx.x], q0 = qtile_q0[blockIdx.x];
   const int r0 = row_off[clip], rows = row_off[clip + 1] - r0, nkeys = valid_rows[clip];
   const int nkt = (nkeys + kKT - 1) / kKT;
+  const int head0 = blockIdx.y * hpc;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(B_QFULL), 1); mbar_init(bar(B_RFULL), 1);
+    mbar_init(bar(B_EFULL), 1); mbar_init(bar(B_RFULL), 1); mbar_init(bar(B_REMPTY), kSoftmaxWarps);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(B_QFULL + s), 1); mbar_init(bar(B_QEMPTY + s), 1); }
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(B_KVFULL + s), 1); mbar_init(bar(B_KVEMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar(B_SFULL + b), 1); mbar_init(bar(B_SEMPTY + b), 4);
-      mbar_init(bar(B_PFULL + b), 4); mbar_init(bar(B_PEMPTY + b), 1);
-      mbar_init(bar(B_PVFULL + b), 1); mbar_init(bar(B_PVEMPTY + b), 4);
+      mbar_init(bar(B_SFULL + b), 1); mbar_init(bar(B_SEMPTY + b), kSoftmaxWarps);
+      mbar_init(bar(B_PFULL + b), kSoftmaxWarps); mbar_init(bar(B_PEMPTY + b), 1);
+      mbar_init(bar(B_PVFULL + b), 1); mbar_init(bar(B_PVEMPTY + b), kSoftmaxWarps);
     }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_e); }
-  if (warp == 1) tmem_alloc(bars + 8u * B_COUNT, 512);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_e); }
+  if (warp == 1) tmem_alloc(bars + 8u * B_COUNT, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base, tPV = tmem_base + 256, tR = tmem_base + 384;
+  // S double buffer [0,128), PV double buffer [128,256); R (80 columns) borrows the PV region before the first PV MMA
+  const uint32_t tS = tmem_base, tPV = tmem_base + 128, tR = tmem_base + 128;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(bar(B_QFULL), kQT * 128 + 80 * 128);
-      tma_load_2d(sQ, &map_qkv, bar(B_QFULL), head * kHD, r0 + q0);
-      tma_load_2d(sE, &map_e, bar(B_QFULL), 0, 0);
-      for (int i = 0; i < nkt; ++i) {
-        const int st = i % kStages;
-        mbar_wait(bar(B_KVEMPTY + st), ((i / kStages) & 1) ^ 1u);
-        mbar_expect_tx(bar(B_KVFULL + st), 2 * kKT * 128);
-        tma_load_2d(sKV + st * 2 * kKT * 128, &map_qkv, bar(B_KVFULL + st), kH + head * kHD, r0 + i * kKT);
-        tma_load_2d(sKV + st * 2 * kKT * 128 + kKT * 128, &map_qkv, bar(B_KVFULL + st), 2 * kH + head * kHD, r0 + i * kKT);
+      mbar_expect_tx(bar(B_EFULL), 80 * 128);
+      tma_load_2d(sE, &map_e, bar(B_EFULL), 0, 0);
+      for (int h = 0; h < hpc; ++h) {
+        const int qb = 0, head = head0 + h;
+        mbar_wait(bar(B_QEMPTY + qb), (h & 1) ^ 1u);
+        mbar_expect_tx(bar(B_QFULL + qb), kQT * 128);
+        tma_load_2d(sQ + qb * kQT * 128, &map_qkv, bar(B_QFULL + qb), head * kHD, r0 + q0);
+        for (int i = 0; i < nkt; ++i) {
+          const int g = h * nkt + i, st = g % kStages;
+          mbar_wait(bar(B_KVEMPTY + st), ((g / kStages) & 1) ^ 1u);
+          mbar_expect_tx(bar(B_KVFULL + st), 2 * kKT * 128);
+          tma_load_2d(sKV + st * 2 * kKT * 128, &map_kv, bar(B_KVFULL + st), kH + head * kHD, r0 + i * kKT);
+          tma_load_2d(sKV + st * 2 * kKT * 128 + kKT * 128, &map_kv, bar(B_KVFULL + st), 2 * kH + head * kHD, r0 + i * kKT);
+        }
       }
     }
   } else if (warp == 1) {
@@ -113,21 +135,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T   (both K-major)
       constexpr uint32_t idesc_r = make_idesc(128, 80);           // R = Q E^T
       constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O = P V     (V MN-major)
-      mbar_wait(bar(B_QFULL), 0);
-      tc_fence_after();
-      const uint64_t dq = make_smem_desc(sQ), de = make_smem_desc(sE);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tR, dq + (uint64_t)(2 * k), de + (uint64_t)(2 * k), idesc_r, k != 0);
-      umma_commit(bar(B_RFULL));
-      auto issue_pv = [&](int j) {
-        const int st = j % kStages, b = j & 1;
-        mbar_wait(bar(B_PFULL + b), (j >> 1) & 1);
-        mbar_wait(bar(B_PVEMPTY + b), ((j >> 1) & 1) ^ 1u);
+      const uint64_t de = make_smem_desc(sE);
+      auto issue_pv = [&](int g) {
+        const int st = g % kStages, b = g & 1;
+        mbar_wait(bar(B_PFULL + b), (g >> 1) & 1);
+        mbar_wait(bar(B_PVEMPTY + b), ((g >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t sv = sKV + st * 2 * kKT * 128 + kKT * 128;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t dp = make_smem_desc(sP + b * 2 * kQT * 128 + (kk >> 2) * kQT * 128) + (uint64_t)(2 * (kk & 3));
+        for (int kk = 0; kk < kKT / 16; ++kk) {
+          const uint64_t dp = make_smem_desc(sP + b * kQT * 128) + (uint64_t)(2 * kk);
           const uint64_t dv = make_smem_desc(sv + kk * 16 * 128);
           umma_bf16(tPV + (uint32_t)(b * kHD), dp, dv, idesc_o, kk != 0);
         }
@@ -135,150 +152,182 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         umma_commit(bar(B_PEMPTY + b));
         umma_commit(bar(B_KVEMPTY + st));
       };
-      for (int i = 0; i < nkt; ++i) {
-        const int st = i % kStages, b = i & 1;
-        mbar_wait(bar(B_KVFULL + st), (i / kStages) & 1);
-        mbar_wait(bar(B_SEMPTY + b), ((i >> 1) & 1) ^ 1u);
+      mbar_wait(bar(B_EFULL), 0);
+      for (int h = 0; h < hpc; ++h) {
+        const int qb = 0;
+        mbar_wait(bar(B_QFULL + qb), h & 1);
+        mbar_wait(bar(B_REMPTY), (h & 1) ^ 1u);          // softmax warps have read the previous head's R
         tc_fence_after();
-        const uint64_t dk = make_smem_desc(sKV + st * 2 * kKT * 128);
+        const uint64_t dq = make_smem_desc(sQ + qb * kQT * 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tS + (uint32_t)(b * kKT), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
-        umma_commit(bar(B_SFULL + b));
-        if (i > 0) issue_pv(i - 1);
+        for (int k = 0; k < 4; ++k) umma_bf16(tR, dq + (uint64_t)(2 * k), de + (uint64_t)(2 * k), idesc_r, k != 0);
+        umma_commit(bar(B_RFULL));
+        for (int i = 0; i < nkt; ++i) {
+          const int g = h * nkt + i, st = g % kStages, b = g & 1;
+          mbar_wait(bar(B_KVFULL + st), (g / kStages) & 1);
+          mbar_wait(bar(B_SEMPTY + b), ((g >> 1) & 1) ^ 1u);
+          tc_fence_after();
+          const uint64_t dk = make_smem_desc(sKV + st * 2 * kKT * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS + (uint32_t)(b * kKT), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
+          umma_commit(bar(B_SFULL + b));
+          if (i == nkt - 1) umma_commit(bar(B_QEMPTY + qb));     // last use of this head's Q
+          if (g > 0) issue_pv(g - 1);
+        }
       }
-      issue_pv(nkt - 1);
+      issue_pv(hpc * nkt - 1);
     }
   } else {
-    // ===== softmax / output warps: thread = query row = TMEM lane =====
+    // ===== softmax / output warps: thread = (query row = TMEM lane, key slice wg of kKW keys) =====
+    constexpr int kWG = kSoftmaxWarps / 4;          // warps per TMEM lane quadrant
+    constexpr int kKW = kKT / kWG;                  // keys of each S tile handled by one thread (32 or 64)
+    constexpr int kDW = kHD / kWG;                  // head dims of the output handled by one thread
     const int quad = warp & 3;
+    const int wg = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const int qpos = q0 + r;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
-
-    // R row -> bf16 (the reference's einsum output dtype) -> shared memory (this thread's row only)
-    mbar_wait(bar(B_RFULL), 0);
-    tc_fence_after();
-    {
-      uint32_t a[32], b2[32], c[16];
-      tmem_ld_32x32_nowait(tR + lane_base, a);
-      tmem_ld_32x32_nowait(tR + lane_base + 32, b2);
-      tmem_ld_32x32_x16_nowait(tR + lane_base + 64, c);
-      tmem_ld_wait();
-      __nv_bfloat16* rr = sR + r * 80;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { rr[i] = __float2bfloat16_rn(__uint_as_float(a[i])); rr[32 + i] = __float2bfloat16_rn(__uint_as_float(b2[i])); }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) rr[64 + i] = __float2bfloat16_rn(__uint_as_float(c[i]));
-    }
+    float* smax = reinterpret_cast<float*>(gbase + AttnSmem::kMax);   // [slot][wg][row]
+    float* ssum = reinterpret_cast<float*>(gbase + AttnSmem::kSum);
     const __nv_bfloat16* myR = sR + r * 80;
-    const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
 
-    float m = -INFINITY, l = 0.f, corr_prev = 1.f;
-    float o[kHD];
-#pragma unroll
-    for (int d = 0; d < kHD; ++d) o[d] = 0.f;
-
-    auto absorb_pv = [&](int j) {   // O = O * corr_j + PV_j
-      const int b = j & 1;
-      mbar_wait(bar(B_PVFULL + b), (j >> 1) & 1);
+    float corr_prev = 1.f;
+    float o[kDW];
+    // O = O * corr + PV of global tile g; on the first tile of a head the accumulator restarts
+    auto absorb_pv = [&](int g, bool first) {
+      const int b = g & 1;
+      mbar_wait(bar(B_PVFULL + b), (g >> 1) & 1);
       tc_fence_after();
-      uint32_t x[32], y[32];
-      tmem_ld_32x32_nowait(tPV + lane_base + (uint32_t)(b * kHD), x);
-      tmem_ld_32x32_nowait(tPV + lane_base + (uint32_t)(b * kHD) + 32, y);
+      uint32_t x[kDW];
+      tmem_ld_cols(tPV + lane_base + (uint32_t)(b * kHD + wg * kDW), x);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_PVEMPTY + b));
 #pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        o[d] = fmaf(o[d], corr_prev, __uint_as_float(x[d]));
-        o[32 + d] = fmaf(o[32 + d], corr_prev, __uint_as_float(y[d]));
-      }
+      for (int d = 0; d < kDW; ++d) o[d] = first ? __uint_as_float(x[d]) : fmaf(o[d], corr_prev, __uint_as_float(x[d]));
     };
 
-    for (int i = 0; i < nkt; ++i) {
-      const int b = i & 1, k0 = i * kKT;
-      mbar_wait(bar(B_SFULL + b), (i >> 1) & 1);
+    for (int h = 0; h < hpc; ++h) {
+      // R row -> bf16 (the reference's einsum output dtype) -> shared memory; the warps of a row split the columns
+      mbar_wait(bar(B_RFULL), h & 1);
       tc_fence_after();
-      const uint32_t ts = tS + lane_base + (uint32_t)(b * kKT);
-      const int dlo = k0 - qpos, dhi = k0 + kKT - 1 - qpos;
-      const int mode = dhi <= -kLeft ? 0 : (dlo >= kRight ? 1 : 2);   // all-left / all-right / diagonal band
-      const float cb = mode == 0 ? rl : rrt;
-      auto score = [&](float s, int kj) -> float {
-        float t;
-        if (mode == 2) {
-          const int idx = max(-kLeft, min(kRight, kj - qpos)) + kLeft;
-          t = (s + __bfloat162float(myR[idx])) * kScale;
-        } else {
-          t = fmaf(s, kScale, cb);
-        }
-        return kj < nkeys ? t : -INFINITY;
-      };
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kKT; c += 64) {
-        uint32_t x[32], y[32];
-        tmem_ld_32x32_nowait(ts + c, x);
-        tmem_ld_32x32_nowait(ts + c + 32, y);
-        tmem_ld_wait();
+      {
+        __nv_bfloat16* rr = sR + r * 80;
+        if (wg < 2) {
+          uint32_t a[32];
+          tmem_ld_32x32_nowait(tR + lane_base + wg * 32, a);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          mx = fmaxf(mx, score(__uint_as_float(x[e]), k0 + c + e));
-          mx = fmaxf(mx, score(__uint_as_float(y[e]), k0 + c + 32 + e));
+          for (int i = 0; i < 32; ++i) rr[wg * 32 + i] = __float2bfloat16_rn(__uint_as_float(a[i]));
+        }
+        if (wg == kWG - 1) {
+          uint32_t c[16];
+          tmem_ld_32x32_x16_nowait(tR + lane_base + 64, c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rr[64 + i] = __float2bfloat16_rn(__uint_as_float(c[i]));
         }
       }
-      const float mn = fmaxf(m, mx);
-      const float corr = ex2a(m - mn);
-      m = mn;
-      // pass 2: P = 2^(t - m) -> bf16 -> shared memory (K-major, 128B swizzle, two 64-key halves)
-      mbar_wait(bar(B_PEMPTY + b), ((i >> 1) & 1) ^ 1u);
-      float ls = 0.f;
-      uint8_t* pbuf = gbase + AttnSmem::kP + b * 2 * kQT * 128 + r * 128;
-#pragma unroll 1
-      for (int c = 0; c < kKT; c += 64) {
-        uint32_t x[32], y[32];
-        tmem_ld_32x32_nowait(ts + c, x);
-        tmem_ld_32x32_nowait(ts + c + 32, y);
-        tmem_ld_wait();
-        float p[64];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          p[e] = ex2a(score(__uint_as_float(x[e]), k0 + c + e) - mn);
-          p[32 + e] = ex2a(score(__uint_as_float(y[e]), k0 + c + 32 + e) - mn);
-        }
-#pragma unroll
-        for (int e = 0; e < 64; ++e) ls += p[e];
-        uint8_t* half = pbuf + (c >> 6) * kQT * 128;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint4 v;
-          v.x = pack_bf16x2(p[ch * 8 + 0], p[ch * 8 + 1]); v.y = pack_bf16x2(p[ch * 8 + 2], p[ch * 8 + 3]);
-          v.z = pack_bf16x2(p[ch * 8 + 4], p[ch * 8 + 5]); v.w = pack_bf16x2(p[ch * 8 + 6], p[ch * 8 + 7]);
-          *reinterpret_cast<uint4*>(half + ((ch ^ (r & 7)) << 4)) = v;
-        }
-      }
-      l = l * corr + ls;
-      // S buffer drained, P visible to the tensor core (generic -> async proxy)
       tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(B_SEMPTY + b)); mbar_arrive(bar(B_PFULL + b)); }
-      if (i > 0) absorb_pv(i - 1);
-      corr_prev = corr;
-    }
-    absorb_pv(nkt - 1);
-    if (qpos < rows) {
-      const float inv = 1.0f / l;
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(r0 + qpos) * kH + head * kHD);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");   // every R row is complete
+      if (lane == 0) mbar_arrive(bar(B_REMPTY));
+      const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
+      float m = -INFINITY, l = 0.f;
+
+      for (int i = 0; i < nkt; ++i) {
+        const int g = h * nkt + i, b = g & 1, k0 = i * kKT + wg * kKW;      // first key of this thread's slice
+        mbar_wait(bar(B_SFULL + b), (g >> 1) & 1);
+        tc_fence_after();
+        float t[kKW];
+        {
+          const uint32_t ts = tS + lane_base + (uint32_t)(b * kKT + wg * kKW);
+          uint32_t x[kKW / 32][32];
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 v;
-        v.x = pack_bf16x2(o[ch * 8 + 0] * inv, o[ch * 8 + 1] * inv); v.y = pack_bf16x2(o[ch * 8 + 2] * inv, o[ch * 8 + 3] * inv);
-        v.z = pack_bf16x2(o[ch * 8 + 4] * inv, o[ch * 8 + 5] * inv); v.w = pack_bf16x2(o[ch * 8 + 6] * inv, o[ch * 8 + 7] * inv);
-        dst[ch] = v;
+          for (int u = 0; u < kKW / 32; ++u) tmem_ld_32x32_nowait(ts + 32 * u, x[u]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < kKW / 32; ++u)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) t[32 * u + e] = __uint_as_float(x[u][e]);
+        }
+        // the S slice is in registers now: hand the buffer back to the MMA warp early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_SEMPTY + b));
+        // t = (q.k + bias) * log2e/8; outside the diagonal band the bias is one constant per row
+        const int dlo = k0 - qpos, dhi = k0 + kKW - 1 - qpos;
+        if (dhi <= -kLeft) {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) t[e] = fmaf(t[e], kScale, rl);
+        } else if (dlo >= kRight) {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) t[e] = fmaf(t[e], kScale, rrt);
+        } else {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) {
+            const int idx = max(-kLeft, min(kRight, dlo + e)) + kLeft;
+            t[e] = (t[e] + __bfloat162float(myR[idx])) * kScale;
+          }
+        }
+        if (k0 + kKW > nkeys) {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) mx = fmaxf(mx, t[e]);
+        // combine the row maximum with the warps that own the other key slices of this row
+        smax[((g & 1) * kWG + wg) * kQT + r] = mx;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+#pragma unroll
+        for (int u = 0; u < kWG; ++u) mx = fmaxf(mx, smax[((g & 1) * kWG + u) * kQT + r]);
+        const float mn = fmaxf(m, mx);
+        const float corr = ex2a(m - mn);
+        m = mn;
+        // P = 2^(t - m) -> bf16 -> shared memory (K-major, 128B swizzle, two 64-key halves)
+        mbar_wait(bar(B_PEMPTY + b), ((g >> 1) & 1) ^ 1u);
+        float ls = 0.f;
+        const int kcol = wg * kKW;                                   // key column within the tile
+        uint8_t* half = gbase + AttnSmem::kP + b * kQT * 128 + r * 128;
+        const int ch0 = (kcol & 63) >> 3;
+#pragma unroll
+        for (int ch = 0; ch < kKW / 8; ++ch) {
+          float pv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { pv[e] = ex2a(t[ch * 8 + e] - mn); ls += pv[e]; }
+          uint4 v;
+          v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]);
+          v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);
+          *reinterpret_cast<uint4*>(half + (((ch0 + ch) ^ (r & 7)) << 4)) = v;
+        }
+        l = l * corr + ls;
+        fence_proxy_async();          // P visible to the tensor core (generic -> async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_PFULL + b));
+        if (i > 0) absorb_pv(g - 1, i == 1);
+        corr_prev = corr;
       }
+      absorb_pv(h * nkt + nkt - 1, nkt == 1);
+      // row sum = sum over the key slices (same running maximum in all warps of a row)
+      ssum[wg * kQT + r] = l;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+      l = 0.f;
+#pragma unroll
+      for (int u = 0; u < kWG; ++u) l += ssum[u * kQT + r];
+      if (qpos < rows) {
+        const float inv = 1.0f / l;
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(r0 + qpos) * kH + (head0 + h) * kHD + wg * kDW);
+#pragma unroll
+        for (int ch = 0; ch < kDW / 8; ++ch) {
+          uint4 v;
+          v.x = pack_bf16x2(o[ch * 8 + 0] * inv, o[ch * 8 + 1] * inv); v.y = pack_bf16x2(o[ch * 8 + 2] * inv, o[ch * 8 + 3] * inv);
+          v.z = pack_bf16x2(o[ch * 8 + 4] * inv, o[ch * 8 + 5] * inv); v.w = pack_bf16x2(o[ch * 8 + 6] * inv, o[ch * 8 + 7] * inv);
+          dst[ch] = v;
+        }
+      }
+      // ssum is rewritten only after the next head's R barrier; sR likewise (bar.sync at the top of the loop)
     }
   }
 
@@ -286,18 +335,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
 }  // namespace
 
+int g_attn_heads_per_cta = 1;   // kept for the option plumbing; the kernel needs 1 (E and R borrow per-head buffers)
+
 // host entry used by b2t_relkey_attention (attention.cu)
 int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, cudaStream_t st) {
   B2T_REQUIRE(b->n_qtiles128 > 0 && b->qtile128_clip && b->qtile128_q0, B2T_ERR_ARG,
               "b2t_relkey_attention(tcgen05): the batch has no 128-row query tiles");
-  CUtensorMap mq, me;
-  int rc = make_map(&mq, qkv, b->total_rows, kQKV, kQKV, 128);
+  CUtensorMap mq, mk, me;
+  int rc = make_map(&mq, qkv, b->total_rows, kQKV, kQKV, kQT);
+  if (rc != B2T_OK) return rc;
+  rc = make_map(&mk, qkv, b->total_rows, kQKV, kQKV, kKT);
   if (rc != B2T_OK) return rc;
   rc = make_map(&me, dist_emb, kRel, kHD, kHD, 80);
   if (rc != B2T_OK) return rc;
@@ -306,9 +359,10 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
     B2T_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal));
     cfg = true;
   }
-  dim3 grid(b->n_qtiles128, kHeads);
-  attention_tc_kernel<<<grid, kThreadsAttn, AttnSmem::kTotal, st>>>(mq, me, b->row_off, b->valid_rows, b->qtile128_clip,
-                                                                   b->qtile128_q0, (__nv_bfloat16*)out);
+  const int hpc = 1;
+  dim3 grid(b->n_qtiles128, kHeads / hpc);
+  attention_tc_kernel<<<grid, kThreadsAttn, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
+                                                                   b->qtile128_q0, (__nv_bfloat16*)out, hpc);
   B2T_LAUNCH_CHECK();
   return B2T_OK;
 }

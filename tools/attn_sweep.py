@@ -1,0 +1,30 @@
+"""Time the tcgen05 attention kernel alone for several heads-per-CTA settings and clip lengths."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from audiotoken_b200 import lib as L, ops, packing
+dev = torch.device('cuda:0')
+lib = L.load()
+def plan_for(rows):
+    lengths = [400 + 160 * (2 * r - 1) for r in rows]
+    offs = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+    return packing.plan_semantic(lengths, offs, lengths, rows=rows)
+for name, rows in (('64x500', [500] * 64), ('24x1500', [1500] * 24), ('mix', list(np.random.default_rng(0).integers(100, 1500, 60)))):
+    plan = plan_for([int(r) for r in rows])
+    M = plan.total_rows
+    qkv = (torch.randn(M, 3072, device=dev) * 0.7).to(torch.bfloat16)
+    E = torch.randn(73, 64, device=dev).to(torch.bfloat16)
+    flops = sum(4096.0 * r * r for r in rows)
+    for impl, hpcs in ((L.IMPL_TENSOR, (1, 2, 4, 16)), (L.IMPL_MMA_SYNC, (1,))):
+        for hpc in hpcs:
+            lib.b2t_set_option(b'attn_heads_per_cta', hpc)
+            for _ in range(2): ops.relkey_attention(qkv, E, plan, 'bf16', impl)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            db = packing.DeviceBatch(plan, dev); out = torch.empty(M, 1024, device=dev, dtype=torch.bfloat16)
+            torch.cuda.synchronize(); s.record()
+            for _ in range(10):
+                L.check(lib.b2t_relkey_attention(qkv.data_ptr(), E.data_ptr(), db.byref(), out.data_ptr(), L.PREC_BF16, impl, L.stream_ptr()), 'attn')
+            e.record(); torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / 10
+            print(f'{name} impl={impl} hpc={hpc}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s', flush=True)
+lib.b2t_set_option(b'attn_heads_per_cta', 1)
