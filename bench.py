@@ -292,6 +292,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def sum_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     def max_over_ranks(ms: float) -> float:
         if dist is None:
             return ms
@@ -377,9 +384,10 @@ def main():
         flops = float(rows.sum()) * (39.73e6 + enc.num_codebooks * 2 * 1024 * 128)
         ach = flops / (ms_res / 1e3) / 1e12
 
+    total_audio_s = sum_over_ranks(audio_s)           # units all ranks processed per step
     if rank == 0:
-        value = world * audio_s / (ms_res / 1e3)
-        e2e = world * audio_s / (ms_e2e / 1e3)
+        value = total_audio_s / (ms_res / 1e3)
+        e2e = total_audio_s / (ms_e2e / 1e3)
         line = {
             'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_res, 'higher_is_better': True,
