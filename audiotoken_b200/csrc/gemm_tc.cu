@@ -80,6 +80,60 @@ B2T_DEVICE void resid_chunk_coalesced(const EpiParams& p, float4* stg, int row_b
   }
 }
 
+// bf16 epilogues (BIAS / SWISH / GLU): values of 32 accumulator columns -> packed bf16 (uint32 pairs)
+template <int EPI>
+B2T_DEVICE void epi_pack32(const EpiParams& p, int col0, const float (&acc)[32], uint32_t* pk) {
+  float v[32];
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      v[i] = bf16_round(acc[i] + b.x); v[i + 1] = bf16_round(acc[i + 1] + b.y);
+      v[i + 2] = bf16_round(acc[i + 2] + b.z); v[i + 3] = bf16_round(acc[i + 3] + b.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(acc[i]);
+  }
+  if constexpr (EPI == B2T_EPI_GLU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pk[i] = pack2_bf16(v[4 * i] * sigmoidf_(v[4 * i + 1]), v[4 * i + 2] * sigmoidf_(v[4 * i + 3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float a = v[2 * i], b = v[2 * i + 1];
+      if constexpr (EPI == B2T_EPI_BIAS_SWISH) { a = swishf_(a); b = swishf_(b); }
+      pk[i] = pack2_bf16(a, b);
+    }
+  }
+}
+
+// Coalesced store of a 32-row x 128-byte bf16 block held one row per lane (8 x uint4): transposed through the
+// per-warp 16 x 128 B staging tile (16-byte chunks XOR-swizzled by row) so that 8 lanes cover one row and every
+// store instruction writes 4 full 128-byte lines instead of 32 partial ones.
+B2T_DEVICE void store_rows_coalesced(uint4* stg, __nv_bfloat16* out, int ldo, int M, int row_base, int col, int lane,
+                                     const uint4 (&pk)[8]) {
+  const int q = lane & 7;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if ((lane >> 4) == half) {
+      const int rl = lane & 15;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) stg[rl * 8 + (i ^ (rl & 7))] = pk[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rl = j * 4 + (lane >> 3);
+      const int grow = row_base + half * 16 + rl;
+      const uint4 v = stg[rl * 8 + (q ^ (rl & 7))];
+      if (grow < M) *reinterpret_cast<uint4*>(out + (size_t)grow * ldo + col + q * 8) = v;
+    }
+    __syncwarp();
+  }
+}
+
 // nearest-centroid epilogue: score = acc - 0.5|c|^2 (p.bias = half norms, +inf beyond the codebook)
 B2T_DEVICE void argmax_chunk(const EpiParams& p, Cand& cand, int col0, const float (&acc)[32]) {
 #pragma unroll
@@ -248,7 +302,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kChunks * 32);
       Cand cand = cand_empty();
-#pragma unroll 1
+      uint32_t glu_pk[32];      // packed bf16 outputs of one store unit (32 words = 8 x uint4 = 128 B per row)
+#pragma unroll
       for (int c = 0; c < kChunks; c += 2) {
         uint32_t r0[32], r1[32];
         tmem_ld_32x32_nowait(taddr + (uint32_t)(c * 32), r0);
@@ -266,21 +321,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
-        if constexpr (EPI == kEpiArgmax) {
-          argmax_chunk(p, cand, n0 + (part * kChunks + c) * 32, v);
-        } else if constexpr (EPI == B2T_EPI_RESID) {
-          resid_chunk_coalesced(p, stg, m0 + quad * 32, n0 + (part * kChunks + c) * 32, lane, v);
-        } else {
-          epilogue_store<EPI, true, 32>(p, row, n0 + (part * kChunks + c) * 32, v);
-        }
+        constexpr bool kPacked = (EPI == B2T_EPI_BIAS || EPI == B2T_EPI_BIAS_SWISH || (EPI == B2T_EPI_GLU && BN == 256));
+        const int col_a = n0 + (part * kChunks + c) * 32;
+        if constexpr (kPacked) {
+          // 64 accumulator columns -> 128 B (BIAS/SWISH) or 64 B (GLU) of bf16 per row, stored coalesced
+          constexpr int kW = (EPI == B2T_EPI_GLU) ? 8 : 16;          // uint32 words produced per 32 columns
+          epi_pack32<EPI>(p, col_a, v, glu_pk + ((EPI == B2T_EPI_GLU) ? c * kW : 0));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r1[i]);
-        if constexpr (EPI == kEpiArgmax) {
-          argmax_chunk(p, cand, n0 + (part * kChunks + c + 1) * 32, v);
-        } else if constexpr (EPI == B2T_EPI_RESID) {
-          resid_chunk_coalesced(p, stg, m0 + quad * 32, n0 + (part * kChunks + c + 1) * 32, lane, v);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r1[i]);
+          epi_pack32<EPI>(p, col_a + 32, v, glu_pk + ((EPI == B2T_EPI_GLU) ? c * kW : 0) + kW);
+          if (EPI != B2T_EPI_GLU || c + 2 >= kChunks) {
+            uint4 pk4[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk4[i] = make_uint4(glu_pk[4 * i], glu_pk[4 * i + 1], glu_pk[4 * i + 2], glu_pk[4 * i + 3]);
+            const int ocol = (EPI == B2T_EPI_GLU) ? (n0 + part * kChunks * 32) / 2 : col_a;
+            store_rows_coalesced(reinterpret_cast<uint4*>(stg), reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, p.M,
+                                 m0 + quad * 32, ocol, lane, pk4);
+          }
         } else {
-          epilogue_store<EPI, true, 32>(p, row, n0 + (part * kChunks + c + 1) * 32, v);
+          if constexpr (EPI == kEpiArgmax) {
+            argmax_chunk(p, cand, col_a, v);
+          } else if constexpr (EPI == B2T_EPI_RESID) {
+            resid_chunk_coalesced(p, stg, m0 + quad * 32, col_a, lane, v);
+          } else {
+            epilogue_store<EPI, true, 32>(p, row, col_a, v);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r1[i]);
+          if constexpr (EPI == kEpiArgmax) {
+            argmax_chunk(p, cand, col_a + 32, v);
+          } else if constexpr (EPI == B2T_EPI_RESID) {
+            resid_chunk_coalesced(p, stg, m0 + quad * 32, col_a + 32, lane, v);
+          } else {
+            epilogue_store<EPI, true, 32>(p, row, col_a + 32, v);
+          }
         }
       }
       if constexpr (EPI == kEpiArgmax) {
