@@ -80,7 +80,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
   float* logmel; float* mean; float* std_; uint8_t* row_valid; void* a160; float* x; void* ln_out;
-  void* big; void* att; void* vq; size_t vq_bytes; size_t total;
+  void* big; void* att; void* d; void* vq; size_t vq_bytes; size_t total;
 };
 
 Workspace carve(void* base, int M, int F, int n_clips, int K, int precision) {
@@ -98,6 +98,7 @@ Workspace carve(void* base, int M, int F, int n_clips, int K, int precision) {
   w.ln_out = take((size_t)M * 1024 * act);
   w.big = take((size_t)M * 4096 * act);
   w.att = take((size_t)M * 1024 * act);
+  w.d = take((size_t)M * 1024 * act);
   w.vq_bytes = b2t_vq_workspace_bytes(M, 1024, K);
   w.vq = take(w.vq_bytes);
   w.total = off;
@@ -196,42 +197,66 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
   RUN(gemm(w.a160, 160, fpw, fpb, nullptr, 0, w.x, 1024, 160, B2T_EPI_BIAS_MASK, 1.f, 0));
   if (tap_layer == 0 && tap_out) B2T_CUDA(cudaMemcpyAsync(tap_out, w.x, (size_t)M * 4096, cudaMemcpyDeviceToDevice, st));
 
+  // Every residual add of the conformer layer is followed by a LayerNorm, so the Linear that produces the
+  // branch output writes it as a plain activation `d` and one fused kernel does x += alpha*d and the LayerNorm
+  // (b2t_add_layernorm) — no read-modify-write epilogue on the fp32 stream.
+  auto add_ln = [&](float alpha, int rr, const void* w1, const void* b1, const void* w2, const void* b2,
+                    const uint8_t* rv, void* out) -> int {
+    Scope sc(PC_LN, st);
+    return b2t_add_layernorm(w.x, w.d, alpha, rr, (const float*)w1, (const float*)b1, (const float*)w2, (const float*)b2, rv,
+                             out, M, prec, stream);
+  };
+  if (m->n_layers > 0) {
+    const void* lw = T("L0.ffn1.ln.w"); const void* lb = T("L0.ffn1.ln.b");
+    NEED();
+    RUN(ln(w.x, lw, lb, nullptr, w.ln_out, prec));
+  }
   for (int i = 0; i < m->n_layers; ++i) {
     const std::string L = "L" + std::to_string(i) + ".";
     const int rr = (bf && i == 0) ? 1 : 0;   // layer 0 of the autocast path keeps a bf16 residual stream
-    for (int f = 0; f < 2; ++f) {
-      if (f == 1) {
-        // ---- self attention
-        const void* lw = T(L + "attn.ln.w"); const void* lb = T(L + "attn.ln.b");
-        const void* wqkv = T(L + "attn.wqkv"); const void* bqkv = T(L + "attn.bqkv");
-        const void* wo = T(L + "attn.wo"); const void* bo = T(L + "attn.bo"); const void* dist = T(L + "attn.dist");
-        NEED();
-        RUN(ln(w.x, lw, lb, nullptr, w.ln_out, prec));
-        RUN(gemm(w.ln_out, 1024, wqkv, bqkv, w.big, 3072, nullptr, 3072, 1024, B2T_EPI_BIAS, 1.f, 0));
-        { Scope sc(PC_ATTN, st); RUN(b2t_relkey_attention(w.big, dist, b, w.att, prec, bf ? m->attn_impl : B2T_IMPL_SIMT, stream)); }
-        RUN(gemm(w.att, 1024, wo, bo, nullptr, 0, w.x, 1024, 1024, B2T_EPI_RESID, 1.f, rr));
-        // ---- convolution module
-        const void* clw = T(L + "conv.ln.w"); const void* clb = T(L + "conv.ln.b");
-        const void* pw1 = T(L + "conv.pw1"); const void* dw = T(L + "conv.dw");
-        const void* dlw = T(L + "conv.dwln.w"); const void* dlb = T(L + "conv.dwln.b"); const void* pw2 = T(L + "conv.pw2");
-        NEED();
-        RUN(ln(w.x, clw, clb, w.row_valid, w.ln_out, prec));
-        RUN(gemm(w.ln_out, 1024, pw1, nullptr, w.big, 1024, nullptr, 2048, 1024, B2T_EPI_GLU, 1.f, 0));
-        { Scope sc(PC_DWCONV, st); RUN(b2t_dwconv_ln_swish(w.big, (const float*)dw, (const float*)dlw, (const float*)dlb, b, w.att, prec, stream)); }
-        RUN(gemm(w.att, 1024, pw2, nullptr, nullptr, 0, w.x, 1024, 1024, B2T_EPI_RESID, 1.f, rr));
-      }
-      // ---- half-step feed forward (ffn1 before attention, ffn2 after the conv module)
-      const std::string F = L + (f == 0 ? "ffn1." : "ffn2.");
-      const void* lw = T(F + "ln.w"); const void* lb = T(F + "ln.b");
-      const void* w1 = T(F + "w1"); const void* b1 = T(F + "b1"); const void* w2 = T(F + "w2"); const void* b2 = T(F + "b2");
+    // ---- half-step feed forward 1 (ln_out already holds LN_ffn1(x))
+    {
+      const void* w1 = T(L + "ffn1.w1"); const void* b1 = T(L + "ffn1.b1"); const void* w2 = T(L + "ffn1.w2"); const void* b2 = T(L + "ffn1.b2");
+      const void* nlw = T(L + "attn.ln.w"); const void* nlb = T(L + "attn.ln.b");
       NEED();
-      RUN(ln(w.x, lw, lb, nullptr, w.ln_out, prec));
       RUN(gemm(w.ln_out, 1024, w1, b1, w.big, 4096, nullptr, 4096, 1024, B2T_EPI_BIAS_SWISH, 1.f, 0));
-      RUN(gemm(w.big, 4096, w2, b2, nullptr, 0, w.x, 1024, 4096, B2T_EPI_RESID, 0.5f, rr));
+      RUN(gemm(w.big, 4096, w2, b2, w.d, 1024, nullptr, 1024, 4096, B2T_EPI_BIAS, 1.f, 0));
+      RUN(add_ln(0.5f, rr, nlw, nlb, nullptr, nullptr, nullptr, w.ln_out));
     }
-    const void* flw = T(L + "final.ln.w"); const void* flb = T(L + "final.ln.b");
-    NEED();
-    RUN(ln(w.x, flw, flb, nullptr, w.x, B2T_PREC_FP32));
+    // ---- self attention
+    {
+      const void* wqkv = T(L + "attn.wqkv"); const void* bqkv = T(L + "attn.bqkv");
+      const void* wo = T(L + "attn.wo"); const void* bo = T(L + "attn.bo"); const void* dist = T(L + "attn.dist");
+      const void* nlw = T(L + "conv.ln.w"); const void* nlb = T(L + "conv.ln.b");
+      NEED();
+      RUN(gemm(w.ln_out, 1024, wqkv, bqkv, w.big, 3072, nullptr, 3072, 1024, B2T_EPI_BIAS, 1.f, 0));
+      { Scope sc(PC_ATTN, st); RUN(b2t_relkey_attention(w.big, dist, b, w.att, prec, bf ? m->attn_impl : B2T_IMPL_SIMT, stream)); }
+      RUN(gemm(w.att, 1024, wo, bo, w.d, 1024, nullptr, 1024, 1024, B2T_EPI_BIAS, 1.f, 0));
+      RUN(add_ln(1.f, rr, nlw, nlb, nullptr, nullptr, w.row_valid, w.ln_out));    // conv-module LN, padded rows zeroed
+    }
+    // ---- convolution module
+    {
+      const void* pw1 = T(L + "conv.pw1"); const void* dw = T(L + "conv.dw");
+      const void* dlw = T(L + "conv.dwln.w"); const void* dlb = T(L + "conv.dwln.b"); const void* pw2 = T(L + "conv.pw2");
+      const void* nlw = T(L + "ffn2.ln.w"); const void* nlb = T(L + "ffn2.ln.b");
+      NEED();
+      RUN(gemm(w.ln_out, 1024, pw1, nullptr, w.big, 1024, nullptr, 2048, 1024, B2T_EPI_GLU, 1.f, 0));
+      { Scope sc(PC_DWCONV, st); RUN(b2t_dwconv_ln_swish(w.big, (const float*)dw, (const float*)dlw, (const float*)dlb, b, w.att, prec, stream)); }
+      RUN(gemm(w.att, 1024, pw2, nullptr, w.d, 1024, nullptr, 1024, 1024, B2T_EPI_BIAS, 1.f, 0));
+      RUN(add_ln(1.f, rr, nlw, nlb, nullptr, nullptr, nullptr, w.ln_out));
+    }
+    // ---- half-step feed forward 2, final LayerNorm, next layer's first LayerNorm
+    {
+      const void* w1 = T(L + "ffn2.w1"); const void* b1 = T(L + "ffn2.b1"); const void* w2 = T(L + "ffn2.w2"); const void* b2 = T(L + "ffn2.b2");
+      const void* flw = T(L + "final.ln.w"); const void* flb = T(L + "final.ln.b");
+      const bool last = i + 1 == m->n_layers;
+      const std::string N = "L" + std::to_string(i + 1) + ".";
+      const void* nlw = last ? nullptr : T(N + "ffn1.ln.w"); const void* nlb = last ? nullptr : T(N + "ffn1.ln.b");
+      NEED();
+      RUN(gemm(w.ln_out, 1024, w1, b1, w.big, 4096, nullptr, 4096, 1024, B2T_EPI_BIAS_SWISH, 1.f, 0));
+      RUN(gemm(w.big, 4096, w2, b2, w.d, 1024, nullptr, 1024, 4096, B2T_EPI_BIAS, 1.f, 0));
+      RUN(add_ln(0.5f, rr, flw, flb, nlw, nlb, nullptr, last ? nullptr : w.ln_out));
+    }
     if (tap_layer == i + 1 && tap_out)
       B2T_CUDA(cudaMemcpyAsync(tap_out, w.x, (size_t)M * 4096, cudaMemcpyDeviceToDevice, st));
   }

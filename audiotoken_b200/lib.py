@@ -21,7 +21,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR, IMPL_MMA_SYNC = 0, 1, 2, 3
 
 EXPORTS = [
     'b2t_version', 'b2t_last_error', 'b2t_device_check', 'b2t_set_option', 'b2t_fbank_logmel', 'b2t_fbank_stats',
-    'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_dwconv_ln_swish',
+    'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_add_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_dwconv_ln_swish',
     'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_vq_debug_stats', 'b2t_semantic_create', 'b2t_semantic_destroy',
     'b2t_semantic_set_tensor', 'b2t_semantic_workspace_bytes', 'b2t_semantic_encode',
     'b2t_last_launch_count', 'b2t_profile_enable', 'b2t_profile_read',
@@ -88,6 +88,7 @@ def load() -> C.CDLL:
     lib.b2t_fbank_stack_ln.argtypes = [vp, vp, vp, C.POINTER(Batch), vp, vp, vp, vp, vp, i32, vp]
     lib.b2t_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.b2t_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+    lib.b2t_add_layernorm.argtypes = [vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.b2t_relkey_attention.argtypes = [vp, vp, C.POINTER(Batch), vp, i32, i32, vp]
     lib.b2t_dwconv_ln_swish.argtypes = [vp, vp, vp, vp, C.POINTER(Batch), vp, i32, vp]
     lib.b2t_vq_workspace_bytes.argtypes = [i32, i32, i32]

@@ -124,6 +124,16 @@ int b2t_layernorm(const float* x, const float* weight, const float* bias,
                   const uint8_t* row_valid, void* out, int rows, int cols, int out_precision,
                   void* stream);
 
+/* Fused residual add + LayerNorm(1024) (HF Wav2Vec2BertEncoderLayer.forward :435-458: every residual add
+ * is followed by a LayerNorm):  t = x + alpha * delta  [rounded to bf16 if round_x_bf16];
+ *   w2 == NULL:  x <- t,              out <- LN(t; w1, b1)   (rows with row_valid == 0 written as 0)
+ *   w2 != NULL:  x <- LN(t; w1, b1),  out <- LN(x; w2, b2)   (final_layer_norm + next ffn1_layer_norm;
+ *                with w2 == NULL and out == NULL only x is updated)
+ * delta and out are bf16 / fp32 per `precision`; x is the fp32 residual stream.                   */
+int b2t_add_layernorm(float* x, const void* delta, float alpha, int round_x_bf16, const float* w1,
+                      const float* b1, const float* w2, const float* b2, const uint8_t* row_valid,
+                      void* out, int rows, int precision, void* stream);
+
 typedef struct {
   const void* A; int32_t lda;        /* [M, K] row-major, bf16 (BF16) or fp32 (FP32)           */
   const void* W;                     /* [N, K] row-major (torch Linear layout), same type      */
