@@ -256,19 +256,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_SEMPTY + b));
-        // t = (q.k + bias) * log2e/8; outside the diagonal band the bias is one constant per row
+        // scores in the log2 domain: t = (q.k + bias) * log2e/8.  Outside the diagonal band the bias is one
+        // constant per row, so the row maximum is taken on the raw q.k and scale, bias and -max fold into a
+        // single FMA in front of the exp2.
         const int dlo = k0 - qpos, dhi = k0 + kKW - 1 - qpos;
-        if (dhi <= -kLeft) {
-#pragma unroll
-          for (int e = 0; e < kKW; ++e) t[e] = fmaf(t[e], kScale, rl);
-        } else if (dlo >= kRight) {
-#pragma unroll
-          for (int e = 0; e < kKW; ++e) t[e] = fmaf(t[e], kScale, rrt);
-        } else {
+        const bool band = !(dhi <= -kLeft || dlo >= kRight);
+        const float cb = dhi <= -kLeft ? rl : rrt;
+        if (band) {
 #pragma unroll
           for (int e = 0; e < kKW; ++e) {
             const int idx = max(-kLeft, min(kRight, dlo + e)) + kLeft;
-            t[e] = (t[e] + __bfloat162float(myR[idx])) * kScale;
+            t[e] = t[e] + __bfloat162float(myR[idx]);
           }
         }
         if (k0 + kKW > nkeys) {
@@ -278,6 +276,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         float mx = -INFINITY;
 #pragma unroll
         for (int e = 0; e < kKW; ++e) mx = fmaxf(mx, t[e]);
+        mx = band ? mx * kScale : fmaf(mx, kScale, cb);          // this slice's maximum in the log2 domain
         // combine the row maximum with the warps that own the other key slices of this row
         smax[((g & 1) * kWG + wg) * kQT + r] = mx;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
@@ -286,7 +285,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const float mn = fmaxf(m, mx);
         const float corr = ex2a(m - mn);
         m = mn;
-        // P = 2^(t - m) -> bf16 -> shared memory (K-major, 128B swizzle, two 64-key halves)
+        const float off = (band ? 0.f : cb) - mn;                  // p = 2^(raw * kScale + off)
+        // P -> bf16 -> shared memory (K-major, 128B swizzle)
         mbar_wait(bar(B_PEMPTY + b), ((g >> 1) & 1) ^ 1u);
         float ls = 0.f;
         const int kcol = wg * kKW;                                   // key column within the tile
@@ -296,7 +296,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         for (int ch = 0; ch < kKW / 8; ++ch) {
           float pv[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { pv[e] = ex2a(t[ch * 8 + e] - mn); ls += pv[e]; }
+          for (int e = 0; e < 8; ++e) { pv[e] = ex2a(fmaf(t[ch * 8 + e], kScale, off)); ls += pv[e]; }
           uint4 v;
           v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]);
           v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);

@@ -23,6 +23,60 @@ template <> B2T_DEVICE void st2<__nv_bfloat16>(__nv_bfloat16* p, float a, float 
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
+// packed fp32 FMA (Blackwell FFMA2): both channels of the thread in one instruction
+B2T_DEVICE float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp with a halving butterfly: after step s every lane keeps
+// half of the remaining values (31 shuffles instead of 16 x 5).  On return lane l holds in v[0] the total of
+// value index (l & 15) — the bit-reversed bookkeeping is folded into which half is kept.
+B2T_DEVICE float warp_sum16(float (&v)[16], int lane) {
+  // step 1: lanes with bit 4 clear keep values 0..7, the others 8..15
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8];
+      const float keep = up ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];   // lane l: total of value index ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
+}
+B2T_DEVICE int warp_sum16_index(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
 template <typename T, bool kBF16>
 __global__ void __launch_bounds__(kThreads)
 dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
@@ -36,12 +90,11 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = tid * 2;
 
-  float w0[kK], w1[kK];
+  float2 wv[kK];
 #pragma unroll
   for (int k = 0; k < kK; ++k) {
     const float2 wk = __ldg(reinterpret_cast<const float2*>(w_dw + (size_t)k * kC + c));   // [31][1024]
-    w0[k] = r16<kBF16>(wk.x);
-    w1[k] = r16<kBF16>(wk.y);
+    wv[k] = make_float2(r16<kBF16>(wk.x), r16<kBF16>(wk.y));
   }
   const float g0 = __ldg(ln_w + c), g1 = __ldg(ln_w + c + 1);
   const float b0 = __ldg(ln_b + c), b1 = __ldg(ln_b + c + 1);
@@ -49,9 +102,9 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
   for (int sub = 0; sub < kSub; ++sub) {
   const int t0 = tile0 + sub * kTT;
   if (t0 >= rows) break;
-  float a0[kTT], a1[kTT];
+  float2 av[kTT];
 #pragma unroll
-  for (int t = 0; t < kTT; ++t) { a0[t] = 0.f; a1[t] = 0.f; }
+  for (int t = 0; t < kTT; ++t) av[t] = make_float2(0.f, 0.f);
 
   // input row (t0 - 30 + j), j = 0..45, contributes to output t with tap k = j - t  (0 <= k <= 30)
 #pragma unroll
@@ -62,24 +115,20 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
 #pragma unroll
     for (int t = 0; t < kTT; ++t) {
       const int k = j - t;
-      if (k >= 0 && k < kK) {
-        a0[t] = fmaf(w0[k], v.x, a0[t]);
-        a1[t] = fmaf(w1[k], v.y, a1[t]);
-      }
+      if (k >= 0 && k < kK) av[t] = ffma2(wv[k], v, av[t]);
     }
   }
-  // LayerNorm over channels, all 16 rows at once
-  float part[kTT];
+  // LayerNorm over channels, all 16 rows at once (two-pass: mean, then centred sum of squares)
+  float a0[kTT], a1[kTT], part[kTT];
 #pragma unroll
   for (int t = 0; t < kTT; ++t) {
-    a0[t] = r16<kBF16>(a0[t]);
-    a1[t] = r16<kBF16>(a1[t]);
-    part[t] = warp_sum(a0[t] + a1[t]);
+    a0[t] = r16<kBF16>(av[t].x);
+    a1[t] = r16<kBF16>(av[t].y);
+    part[t] = a0[t] + a1[t];
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int t = 0; t < kTT; ++t) s_red[warp][t] = part[t];
-  }
+  const int ridx = warp_sum16_index(lane);
+  float tot = warp_sum16(part, lane);
+  if ((lane & 1) == 0) s_red[warp][ridx] = tot;
   __syncthreads();
   if (tid < kTT) {
     float s = 0.f;
@@ -93,13 +142,11 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
   for (int t = 0; t < kTT; ++t) {
     mu[t] = s_stat[t];
     float d0 = a0[t] - mu[t], d1 = a1[t] - mu[t];
-    part[t] = warp_sum(d0 * d0 + d1 * d1);
+    part[t] = d0 * d0 + d1 * d1;
   }
+  tot = warp_sum16(part, lane);
   __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int t = 0; t < kTT; ++t) s_red[warp][t] = part[t];
-  }
+  if ((lane & 1) == 0) s_red[warp][ridx] = tot;
   __syncthreads();
   if (tid < kTT) {
     float s = 0.f;
