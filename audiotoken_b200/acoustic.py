@@ -35,6 +35,9 @@ class AcousticPlan:
     tile_t0: List[np.ndarray]
     order: np.ndarray             # int32 [n]
     active: np.ndarray            # int32 [t_max]
+    rank: np.ndarray              # int32 [n]   inverse of order
+    toff: np.ndarray              # int32 [t_max + 1]   prefix sums of active
+    aligned320: bool              # every virtual length is a multiple of 320 samples (tensor-core path)
 
     @property
     def frames(self) -> np.ndarray:
@@ -45,9 +48,11 @@ class AcousticPlan:
         return int(self.offs[4][-1])
 
 
-def plan_acoustic(true_lens: Sequence[int], wave_offsets: Sequence[int], virt_lens: Sequence[int]) -> AcousticPlan:
+def plan_acoustic(true_lens: Sequence[int], wave_offsets: Sequence[int], virt_lens: Sequence[int],
+                  tiles: bool = True) -> AcousticPlan:
     """true_lens[i] samples are read from the wave buffer, the clip behaves as a signal of virt_lens[i]
-    samples (zeros after true_len) — the reference's right zero-padding (datasets.py:99-103)."""
+    samples (zeros after true_len) — the reference's right zero-padding (datasets.py:99-103).
+    tiles=False skips the 64-row work lists only the fp32 kernels use."""
     n = len(true_lens)
     tl = np.asarray(true_lens, dtype=np.int64)
     vl = np.asarray(virt_lens, dtype=np.int64)
@@ -63,8 +68,8 @@ def plan_acoustic(true_lens: Sequence[int], wave_offsets: Sequence[int], virt_le
         if o[-1] >= 2 ** 31:
             raise ValueError('batch too large for int32 offsets')
         offs.append(o.astype(np.int32))
-        cl, t0 = [], []
-        for i in range(n):
+        cl, t0 = [np.zeros(0, dtype=np.int32)], [np.zeros(0, dtype=np.int32)]
+        for i in range(n if tiles else 0):
             t = np.arange(0, lens[l][i], TILE, dtype=np.int32)
             cl.append(np.full(t.shape, i, dtype=np.int32))
             t0.append(t)
@@ -74,13 +79,21 @@ def plan_acoustic(true_lens: Sequence[int], wave_offsets: Sequence[int], virt_le
     t_max = int(lens[4].max())
     sorted_len = lens[4][order]
     active = (sorted_len[None, :] > np.arange(t_max)[:, None]).sum(axis=1).astype(np.int32)
+    rank = np.empty(n, dtype=np.int32)
+    rank[order] = np.arange(n, dtype=np.int32)
+    toff = np.zeros(t_max + 1, dtype=np.int32)
+    toff[1:] = np.cumsum(active)
+    if not tiles and not np.all(vl % HOP == 0):
+        raise ValueError('tiles=False requires clip lengths that are multiples of 320 samples')
     return AcousticPlan(n, np.asarray(wave_offsets, dtype=np.int64), tl.astype(np.int32),
-                        [x.astype(np.int32) for x in lens], offs, tc, tt, order, active)
+                        [x.astype(np.int32) for x in lens], offs, tc, tt, order, active, rank, toff,
+                        bool(np.all(vl % HOP == 0)))
 
 
 class DeviceAcousticBatch:
     def __init__(self, plan: AcousticPlan, device):
-        arrays = [plan.true_len] + plan.lens + plan.offs + plan.tile_clip + plan.tile_t0 + [plan.order]
+        arrays = ([plan.true_len] + plan.lens + plan.offs + plan.tile_clip + plan.tile_t0 +
+                  [plan.order, plan.rank, plan.toff])
         n64 = plan.wave_off.size
         total = 2 * n64 + sum(a.size for a in arrays)
         host = torch.empty(total, dtype=torch.int32, pin_memory=torch.cuda.is_available())
@@ -108,6 +121,11 @@ class DeviceAcousticBatch:
         b.wave_off = base
         b.true_len = p[0]
         b.order = p[21]
+        b.rank = p[22]
+        b.toff = p[23]
+        self.frames = np.ascontiguousarray(plan.lens[4], dtype=np.int32)
+        b.frames_host = self.frames.ctypes.data
+        b.aligned320 = int(plan.aligned320)
         self.c = b
         self.active = np.ascontiguousarray(plan.active)
 
@@ -138,17 +156,56 @@ class AcousticWeights:
         t['rvq.codebooks'] = cb.to(device).contiguous()
         t['rvq.half_norm'] = hn.float().to(device).contiguous()
         t['rvq.cmax_half'] = hn.max(dim=1).values.float().to(device).contiguous()
+        # tensor-core path (csrc/seanet_tc.cu): bf16 weights, K padded to 64, tap-major; weight-norm is evaluated in
+        # fp32 and then rounded, as autocast does
+        def tapmajor(i):
+            name, cin, cout, k, _s = SEANET_CONVS[i]
+            return weight_norm_weight(sd, name).float().permute(0, 2, 1).reshape(cout, k * cin), sd[name + '.bias'].float()
+
+        def pad64(w):
+            kp = (w.shape[1] + 63) // 64 * 64
+            out = torch.zeros(w.shape[0], kp)
+            out[:, :w.shape[1]] = w
+            return out.to(torch.bfloat16).to(device).contiguous()
+
+        for l in range(4):
+            w3, b3 = tapmajor(1 + 4 * l)
+            wk1, bk1 = tapmajor(2 + 4 * l)
+            wsc, bsc = tapmajor(3 + 4 * l)
+            wd, bd = tapmajor(4 + 4 * l)
+            t[f'tc.k3{l}.w'], t[f'tc.k3{l}.b'] = pad64(w3), b3.to(device).contiguous()
+            t[f'tc.res{l}.w'] = pad64(torch.cat([wsc, wk1], dim=1))
+            t[f'tc.res{l}.b'] = (bsc + bk1).to(device).contiguous()
+            t[f'tc.down{l}.w'], t[f'tc.down{l}.b'] = pad64(wd), bd.to(device).contiguous()
+        wf, bf = tapmajor(17)
+        t['tc.final.w'], t['tc.final.b'] = pad64(wf), bf.to(device).contiguous()
+        for layer in range(2):
+            p = 'encoder.layers.13.lstm.'
+            w = torch.cat([sd[p + f'weight_ih_l{layer}'].float(), sd[p + f'weight_hh_l{layer}'].float()], dim=1)
+            bsum = (sd[p + f'bias_ih_l{layer}'] + sd[p + f'bias_hh_l{layer}']).float()
+            # row 4*u + g  <-  gate g (i, f, g, o) of hidden unit u
+            t[f'tc.lstm{layer}.w'] = w.view(4, 512, 1024).permute(1, 0, 2).reshape(2048, 1024).to(torch.bfloat16).to(device).contiguous()
+            t[f'tc.lstm{layer}.b'] = bsum.view(4, 512).t().reshape(2048).to(device).contiguous()
         self.tensors = t
 
 
 class AcousticEncoder(torch.nn.Module):
-    """Same call shape as reference audiotoken/encoder.py:29-57; fp32 numerics (the reference's CPU path)."""
+    """Same call shape as reference audiotoken/encoder.py:29-57.
 
-    max_rows_per_batch = 75 * 1200          # frames per ragged batch (~26 GB of fp32 activations)
+    precision='bf16' (default): tcgen05 encoder, bf16 operands / fp32 accumulation — the reference's GPU numerics
+    (autocast, encoder.py:45); batches whose clip lengths are not multiples of 320 samples run the fp32 kernels.
+    precision='fp32': CUDA-core fp32 kernels — the reference's CPU numerics (BASELINE config 1).
+    The residual VQ is exact (fp32 residuals, fp64-checked argmin) in both."""
 
     def __init__(self, config: Optional[AcousticEncoderConfig] = None, device: str = 'cuda:0',
-                 state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0, **_unused):
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0, precision: str = 'bf16',
+                 **_unused):
         super().__init__()
+        assert precision in ('bf16', 'fp32')
+        self.precision = precision
+        # frames per ragged batch: the fp32 path keeps every level of the whole batch resident (~290 KB/frame);
+        # the tensor path streams the strided front end in sub-batches and keeps only 75 Hz tensors (~4 KB/frame)
+        self.max_rows_per_batch = 75 * 1200 if precision == 'fp32' else 75 * 40000
         self.config = config if config is not None else AcousticEncoderConfig()
         self.device = torch.device(device)
         L.require_device(self.device)
@@ -185,13 +242,17 @@ class AcousticEncoder(torch.nn.Module):
         assert wave.is_cuda and wave.dtype == torch.float32 and wave.is_contiguous()
         with torch.cuda.device(self.device):
             db = DeviceAcousticBatch(plan, self.device)
-            need = self.lib.b2t_acoustic_workspace_bytes(db.byref())
+            prec = L.PREC_BF16 if (self.precision == 'bf16' and plan.aligned320) else L.PREC_FP32
+            if prec == L.PREC_FP32 and plan.tile_clip[0].size == 0:
+                raise ValueError('plan was built with tiles=False but the fp32 kernels are needed')
+            self.last_precision = 'bf16' if prec == L.PREC_BF16 else 'fp32'
+            need = self.lib.b2t_acoustic_workspace_bytes(db.byref(), prec)
             if self._ws is None or self._ws.numel() < need:
                 self._ws = None
                 self._ws = torch.empty(int(need * 1.05) + 1024, dtype=torch.uint8, device=self.device)
             codes = torch.empty(self.num_codebooks, plan.total_frames, dtype=torch.int16, device=self.device)
             emb = torch.empty(plan.total_frames, 128, device=self.device) if want_emb else None
-            L.check(self.lib.b2t_acoustic_encode(self.handle, wave.data_ptr(), db.byref(), self.num_codebooks,
+            L.check(self.lib.b2t_acoustic_encode(self.handle, wave.data_ptr(), db.byref(), self.num_codebooks, prec,
                                                  self._ws.data_ptr(), self._ws.numel(), codes.data_ptr(), L.ptr(emb),
                                                  db.active.ctypes.data, L.stream_ptr()), 'b2t_acoustic_encode')
             self.last_launches = self.lib.b2t_last_launch_count()
@@ -203,7 +264,8 @@ class AcousticEncoder(torch.nn.Module):
         assert input_batch.dim() == 2
         B, Lp = input_batch.shape
         wave = input_batch.to(self.device, torch.float32).contiguous()
-        plan = plan_acoustic([Lp] * B, np.arange(B, dtype=np.int64) * Lp, [Lp] * B)
+        plan = plan_acoustic([Lp] * B, np.arange(B, dtype=np.int64) * Lp, [Lp] * B,
+                             tiles=not (self.precision == 'bf16' and Lp % HOP == 0))
         codes, emb = self.encode_plan(wave.view(-1), plan, want_emb)
         T = plan.total_frames // B
         out = codes.view(self.num_codebooks, B, T).transpose(0, 1).contiguous()
@@ -221,7 +283,7 @@ class AcousticEncoder(torch.nn.Module):
         offs = np.zeros(len(clips), dtype=np.int64)
         offs[1:] = np.cumsum(lengths)[:-1]
         wave = torch.cat([c.reshape(-1).to(torch.float32) for c in clips]).to(self.device)
-        plan = plan_acoustic(lengths, offs, virt)
+        plan = plan_acoustic(lengths, offs, virt, tiles=self.precision != 'bf16')
         codes, _ = self.encode_plan(wave, plan)
         fo = plan.offs[4]
         return [codes[:, fo[i]:fo[i] + rows[i]] for i in range(len(clips))]

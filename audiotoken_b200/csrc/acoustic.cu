@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include "vq_cand.cuh"
+#include "seanet_tc.h"
 
 void b2t_reset_launch_count();
 
@@ -343,13 +344,64 @@ AcWs ac_carve(void* base, const b2t_acoustic_batch* b) {
 }
 }  // namespace
 
-extern "C" size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* b) {
+extern "C" size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* b, int precision) {
   if (!b) return 0;
+  if (precision == B2T_PREC_BF16) return b2t_seanet_tc_workspace_bytes(b);
   return ac_carve(nullptr, b).total;
 }
 
+namespace {
+int rvq_launch(const b2t_acoustic_model* m, const float* emb, int rows, int n_q, int16_t* codes, cudaStream_t st) {
+  const char* names[3] = {"rvq.codebooks", "rvq.half_norm", "rvq.cmax_half"};
+  const float* t[3];
+  for (int i = 0; i < 3; ++i) {
+    auto it = m->t.find(names[i]);
+    B2T_REQUIRE(it != m->t.end(), B2T_ERR_STATE, "b2t_acoustic_encode: tensor '%s' not set", names[i]);
+    t[i] = (const float*)it->second;
+  }
+  static bool cfg = false;
+  if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RvqSmem))); cfg = true; }
+  rvq_kernel<<<(rows + 63) / 64, 256, sizeof(RvqSmem), st>>>(emb, rows, t[0], t[1], t[2], n_q, codes);
+  B2T_LAUNCH_CHECK();
+  return B2T_OK;
+}
+
+int encode_tc(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic_batch* b, int n_q, void* workspace,
+              size_t workspace_bytes, int16_t* codes, float* emb_out, const int32_t* active_host, cudaStream_t st) {
+  SeanetTcWeights wt{};
+  bool missing = false;
+  std::string miss;
+  auto T = [&](const std::string& n) -> const void* {
+    auto it = m->t.find(n);
+    if (it == m->t.end()) { if (!missing) miss = n; missing = true; return nullptr; }
+    return it->second;
+  };
+  wt.conv0_w = (const float*)T("conv0.w"); wt.conv0_b = (const float*)T("conv0.b");
+  const int ch[4] = {32, 64, 128, 256}, st_[4] = {2, 4, 5, 8};
+  for (int l = 0; l < 4; ++l) {
+    const std::string s = std::to_string(l);
+    wt.k3_w[l] = (const __nv_bfloat16*)T("tc.k3" + s + ".w"); wt.k3_b[l] = (const float*)T("tc.k3" + s + ".b");
+    wt.res_w[l] = (const __nv_bfloat16*)T("tc.res" + s + ".w"); wt.res_b[l] = (const float*)T("tc.res" + s + ".b");
+    wt.down_w[l] = (const __nv_bfloat16*)T("tc.down" + s + ".w"); wt.down_b[l] = (const float*)T("tc.down" + s + ".b");
+    wt.k3_kpad[l] = (3 * ch[l] + 63) / 64 * 64;
+    wt.res_kpad[l] = (ch[l] * 3 / 2 + 63) / 64 * 64;
+    wt.down_kpad[l] = 2 * st_[l] * ch[l];
+  }
+  for (int j = 0; j < 2; ++j) {
+    wt.lstm_w[j] = (const __nv_bfloat16*)T("tc.lstm" + std::to_string(j) + ".w");
+    wt.lstm_b[j] = (const float*)T("tc.lstm" + std::to_string(j) + ".b");
+  }
+  wt.final_w = (const __nv_bfloat16*)T("tc.final.w"); wt.final_b = (const float*)T("tc.final.b");
+  B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_encode(bf16): tensor '%s' not set", miss.c_str());
+  float* emb = emb_out ? emb_out : b2t_seanet_tc_emb(workspace, b);
+  int rc = b2t_seanet_tc_encode(wt, wave, b, workspace, workspace_bytes, emb, active_host, st);
+  if (rc != B2T_OK) return rc;
+  return rvq_launch(m, emb, b->total[4], n_q, codes, st);
+}
+}  // namespace
+
 extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic_batch* b,
-                                   int n_q, void* workspace, size_t workspace_bytes, int16_t* codes,
+                                   int n_q, int precision, void* workspace, size_t workspace_bytes, int16_t* codes,
                                    float* emb_out, const int32_t* active_host, void* stream) {
   B2T_REQUIRE(m && wave && b && workspace && codes && active_host, B2T_ERR_ARG, "b2t_acoustic_encode: null argument");
   B2T_REQUIRE(n_q >= 1 && n_q <= 32, B2T_ERR_ARG, "b2t_acoustic_encode: n_q must be in [1, 32]");
@@ -357,6 +409,8 @@ extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wav
   if (rc != B2T_OK) return rc;
   b2t_reset_launch_count();
   if (b->n_clips <= 0 || b->total[4] <= 0) return B2T_OK;
+  if (precision == B2T_PREC_BF16)
+    return encode_tc(m, wave, b, n_q, workspace, workspace_bytes, codes, emb_out, active_host, (cudaStream_t)stream);
   AcWs w = ac_carve(workspace, b);
   B2T_REQUIRE(workspace_bytes >= w.total, B2T_ERR_WORKSPACE, "b2t_acoustic_encode: workspace %zu < %zu", workspace_bytes, w.total);
   cudaStream_t st = (cudaStream_t)stream;
@@ -425,13 +479,6 @@ extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wav
   float* emb = emb_out ? emb_out : w.emb;
   RUN(conv(17, 4, 4, w.s2, emb, nullptr, 1));
   // residual VQ
-  const float* cbs = T("rvq.codebooks"); const float* hns = T("rvq.half_norm"); const float* cmx = T("rvq.cmax_half");
-  B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_encode: tensor '%s' not set", miss.c_str());
-  static bool cfg = false;
-  if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RvqSmem))); cfg = true; }
-  rvq_kernel<<<(t4 + 63) / 64, 256, sizeof(RvqSmem), st>>>(emb, t4, cbs, hns, cmx, n_q, codes);
-  B2T_LAUNCH_CHECK();
-  (void)t4;
-  return B2T_OK;
+  return rvq_launch(m, emb, t4, n_q, codes, st);
 #undef RUN
 }

@@ -1,0 +1,590 @@
+// Acoustic path on tensor cores (bf16 operands, fp32 accumulation = the reference's GPU numerics under
+// torch.amp.autocast('cuda', bfloat16), audiotoken/encoder.py:45-52):
+//
+//   seanet_conv0_kernel   Conv(1->32, k7): CUDA cores, one thread per (row, 8 channels); HBM-bound.
+//   seanet_tc_kernel      every other contraction of the SEANet encoder as a tcgen05 GEMM:
+//                           * causal convs read their im2col matrix straight from the channels-last activation
+//                             buffer through an OVERLAPPING-ROW tensor map (row stride = stride*C_in elements,
+//                             row width = k*C_in), so no im2col copy and no per-tap loop exists;
+//                           * the residual block's 1x1 convs (shortcut on x, k1 on ELU(h)) are one GEMM over the
+//                             combined rows [x | ELU(h)];
+//                           * reflect padding lives in per-clip halo rows that the PRODUCER's epilogue fills
+//                             (row t in 1..H is mirrored to row -t; ELU commutes with the mirror);
+//                           * the LSTM step is a GEMM [x_t | h_{t-1}] . [W_ih | W_hh]^T over all still-active clips
+//                             with the cell update fused into the epilogue (gate-interleaved weight rows).
+//                         Structure as gemm_tc.cu: persistent CTAs, warp 0 = TMA producer (SWIZZLE_128B, 4-stage
+//                         ring), warp 1 = tcgen05.mma issuer, fp32 accumulators double-buffered in TMEM, 8 epilogue
+//                         warps (tcgen05.ld, one accumulator row per lane).
+//
+// Row spaces.  Clip c has F_c frames (off4 = prefix sum).  Level l (rows per frame R = 320,160,40,8,1) stores clip
+// c at padded row  R*(off4[c]-off4[c0]) + H*(c-c0)  with H halo rows first (H = 2,4,5,8 = the next stride; 6 at
+// level 4 for the k7 conv).  A GEMM's M index runs over such a space; the epilogue maps m -> (clip, t) by binary
+// search and writes to the output level's space.  Requires every clip length to be a multiple of 320 samples
+// (the host zero-extends; exact because all convs are causal — SURVEY A.6).
+#include <vector>
+#include "tc_ptx.cuh"
+#include "gemm_epilogue.cuh"
+#include "seanet_tc.h"
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kStages = 4;
+
+B2T_DEVICE float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+B2T_DEVICE float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+B2T_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+B2T_DEVICE void tmem_ld_32x32_x16_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+
+// ---- epilogue parameter blocks ---------------------------------------------------------------------
+struct ConvEpi {
+  const int32_t* off4;       // [n_clips + 1] frame prefix sums
+  const int32_t* rank;       // [n_clips] position of the clip in the length-sorted order (time-major output)
+  const int32_t* toff;       // [t_max + 1] prefix sums of the active-clip counts (time-major output)
+  const float* bias;         // [N]
+  __nv_bfloat16* out_raw; int ld_raw;    // bf16(acc + bias)            (nullable)
+  __nv_bfloat16* out_elu; int ld_elu;    // bf16(ELU(bf16(acc + bias)))  (nullable)
+  float* out_f32; int ld_f32;            // acc + bias in fp32           (nullable)
+  int c0, nsub;              // clips [c0, c0 + nsub) make up the M space
+  int r, h_in;               // M space: clip starts at r*(off4[c]-off4[c0]) + h_in*(c-c0), first h_in rows are halo
+  int h_out, c0_out;         // output space: row = r*(off4[c]-off4[c0_out]) + h_out*(c-c0_out) + h_out + t
+  int mirror;                // mirror rows 1..h_out of out_elu into the halo (and zero what a short clip leaves)
+  int tm_out;                // out_raw row = toff[t] + rank[c]  (time-major, for the LSTM)
+};
+
+struct LstmEpi {
+  const float* bias;         // [2048], gate-interleaved: index 4*u + g
+  const int32_t* order;      // [n_clips] clip ids, longest first
+  const int32_t* off4;
+  float* c;                  // [n_clips, 512] cell state, indexed by sorted position
+  __nv_bfloat16* h_out;      // time-major [total4, 512]
+  const __nv_bfloat16* skip; // time-major x4 (last layer) or null
+  __nv_bfloat16* s2e;        // clip-major padded (halo 6) ELU(h + skip) for the final conv (last layer) or null
+  int t, toff_t, n_active;
+};
+
+struct RowInfo { int clip, t, len; bool valid; };
+
+B2T_DEVICE RowInfo map_row(const ConvEpi& p, int m, int M) {
+  RowInfo ri{0, -1, 0, false};
+  if (m >= M) return ri;
+  const int f0 = __ldg(p.off4 + p.c0);
+  int lo = 0, hi = p.nsub;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    const int start = p.r * (__ldg(p.off4 + p.c0 + mid) - f0) + p.h_in * mid;
+    if (start <= m) lo = mid; else hi = mid;
+  }
+  ri.clip = p.c0 + lo;
+  const int fa = __ldg(p.off4 + ri.clip), fb = __ldg(p.off4 + ri.clip + 1);
+  ri.t = m - (p.r * (fa - f0) + p.h_in * lo) - p.h_in;
+  ri.len = p.r * (fb - fa);
+  ri.valid = ri.t >= 0 && ri.t < ri.len;
+  return ri;
+}
+
+template <int CW>
+B2T_DEVICE void store_bf16(__nv_bfloat16* dst, const uint32_t* pk) {
+#pragma unroll
+  for (int i = 0; i < CW / 8; ++i)
+    *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+}
+
+// one chunk of CW accumulator columns [col, col + CW) of the row described by ri
+template <int CW>
+B2T_DEVICE void conv_epilogue_chunk(const ConvEpi& p, const RowInfo& ri, int col, const uint32_t* acc) {
+  if (!ri.valid) return;
+  float v[CW];
+#pragma unroll
+  for (int i = 0; i < CW; i += 4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+    v[i] = __uint_as_float(acc[i]) + b.x; v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
+    v[i + 2] = __uint_as_float(acc[i + 2]) + b.z; v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+  }
+  const long long orow = (long long)p.r * (__ldg(p.off4 + ri.clip) - __ldg(p.off4 + p.c0_out)) +
+                         (long long)p.h_out * (ri.clip - p.c0_out) + p.h_out + ri.t;
+  if (p.out_f32) {
+    float* o = p.out_f32 + orow * p.ld_f32 + col;
+#pragma unroll
+    for (int i = 0; i < CW; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  uint32_t pk[CW / 2];
+  if (p.out_raw) {
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) pk[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
+    const long long rr = p.tm_out ? (long long)__ldg(p.toff + ri.t) + __ldg(p.rank + ri.clip) : orow;
+    store_bf16<CW>(p.out_raw + rr * p.ld_raw + col, pk);
+  }
+  if (p.out_elu) {
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i)
+      pk[i] = pack2_bf16(elu_fast(bf16_round(v[2 * i])), elu_fast(bf16_round(v[2 * i + 1])));
+    __nv_bfloat16* o = p.out_elu + orow * p.ld_elu + col;
+    store_bf16<CW>(o, pk);
+    if (p.mirror) {
+      if (ri.t >= 1 && ri.t <= p.h_out) store_bf16<CW>(o - 2LL * ri.t * p.ld_elu, pk);
+      if (ri.t == 0 && ri.len <= p.h_out) {        // short clip: halo rows the mirror does not reach read as zero
+        uint32_t z[CW / 2];
+#pragma unroll
+        for (int i = 0; i < CW / 2; ++i) z[i] = 0u;
+        for (int j = ri.len; j <= p.h_out; ++j) store_bf16<CW>(o - (long long)j * p.ld_elu, z);
+      }
+    }
+  }
+}
+
+// LSTM cell for 8 hidden units (32 gate columns, order i f g o per unit) of sorted clip b
+B2T_DEVICE void lstm_epilogue_chunk(const LstmEpi& p, int b, int col, const uint32_t* acc) {
+  if (b >= p.n_active) return;
+  const int u0 = col >> 2;
+  float* cp = p.c + (size_t)b * 512 + u0;
+  float cs[8];
+  if (p.t > 0) {
+    const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
+    cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+  }
+  float h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * j));
+    const float gi = __uint_as_float(acc[4 * j]) + bb.x, gf = __uint_as_float(acc[4 * j + 1]) + bb.y;
+    const float gg = __uint_as_float(acc[4 * j + 2]) + bb.z, go = __uint_as_float(acc[4 * j + 3]) + bb.w;
+    cs[j] = sigmoid_fast(gf) * cs[j] + sigmoid_fast(gi) * tanh_fast(gg);
+    h[j] = sigmoid_fast(go) * tanh_fast(cs[j]);
+  }
+  *reinterpret_cast<float4*>(cp) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+  *reinterpret_cast<float4*>(cp + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pk[j] = pack2_bf16(h[2 * j], h[2 * j + 1]);
+  const size_t trow = (size_t)p.toff_t + b;
+  store_bf16<8>(p.h_out + trow * 512 + u0, pk);
+  if (p.s2e) {
+    const uint4 sk = *reinterpret_cast<const uint4*>(p.skip + trow * 512 + u0);
+    const uint32_t sw[4] = {sk.x, sk.y, sk.z, sk.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&sw[j]);
+      const float a = bf16_round(bf16_round(h[2 * j]) + __low2float(s2));
+      const float c = bf16_round(bf16_round(h[2 * j + 1]) + __high2float(s2));
+      pk[j] = pack2_bf16(elu_fast(a), elu_fast(c));
+    }
+    const int clip = __ldg(p.order + b);
+    const int fa = __ldg(p.off4 + clip), len = __ldg(p.off4 + clip + 1) - fa;
+    __nv_bfloat16* o = p.s2e + ((size_t)fa + 6 * (size_t)clip + 6 + p.t) * 512 + u0;
+    store_bf16<8>(o, pk);
+    if (p.t >= 1 && p.t <= 6) store_bf16<8>(o - 2LL * p.t * 512, pk);
+    if (p.t == 0 && len <= 6) {
+      const uint32_t z[4] = {0u, 0u, 0u, 0u};
+      for (int j = len; j <= 6; ++j) store_bf16<8>(o - (long long)j * 512, z);
+    }
+  }
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int kStageA = kBM * kBK * 2;
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kTileBytes = kStages * (kStageA + kStageB);
+  static constexpr int kTotal = kTileBytes + 256 + 1024;
+};
+
+// out[m, n] = sum_k A[m, k] W[n, k];  A's k-blocks [0, kb0) come from map_a0 (rows row0 + m), the following kb1
+// blocks from map_a1 (rows row1 + m); W k-block index runs over both.
+template <int BN, typename Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+seanet_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_w, int kb0, int kb1, int row0, int row1, int M, int N, Epi p) {
+  using L = Smem<BN>;
+  constexpr bool kLstm = std::is_same<Epi, LstmEpi>::value;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + kStages * L::kStageA;
+  const uint32_t bars = base + L::kTileBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = N / BN;
+  const int tiles = ((M + kBM - 1) / kBM) * tiles_n;
+  const int num_kb = kb0 + kb1;
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_w); }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), L::kStageA + L::kStageB);
+          if (kb < kb0) tma_load_2d(sA + stage * L::kStageA, &map_a0, full_bar(stage), kb * kBK, row0 + m0);
+          else tma_load_2d(sA + stage * L::kStageA, &map_a1, full_bar(stage), (kb - kb0) * kBK, row1 + m0);
+          tma_load_2d(sB + stage * L::kStageB, &map_w, full_bar(stage), kb * kBK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(sA + stage * L::kStageA);
+          const uint64_t db = make_smem_desc(sB + stage * L::kStageB);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // epilogue: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the columns when BN >= 64
+    const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
+    constexpr int kParts = BN >= 64 ? 2 : 1;
+    constexpr int kColsPerPart = BN / kParts;
+    constexpr int kCW = kColsPerPart >= 32 ? 32 : 16;
+    constexpr int kChunks = kColsPerPart / kCW;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      const int m = m0 + quad * 32 + lane;
+      RowInfo ri{0, -1, 0, false};
+      if constexpr (!kLstm) { if (part < kParts) ri = map_row(p, m, M); }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (part < kParts) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kColsPerPart);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t r[32];
+          if constexpr (kCW == 32) tmem_ld_32x32_nowait(taddr + (uint32_t)(c * 32), r);
+          else tmem_ld_32x32_x16_nowait(taddr + (uint32_t)(c * 16), r);
+          tmem_ld_wait();
+          if (c == kChunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          const int col = n0 + part * kColsPerPart + c * kCW;
+          if constexpr (kLstm) lstm_epilogue_chunk(p, m, col, r);
+          else conv_epilogue_chunk<kCW>(p, ri, col, r);
+        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// Conv(1 -> 32, k = 7) on the raw waveform: 4 threads per output row, 8 channels each.
+// xh row = [x (32) | ELU(h) (16)] (ld 48), xe = ELU(x) (ld 32) with the two mirrored halo rows.
+__global__ void __launch_bounds__(256)
+seanet_conv0_kernel(const float* __restrict__ wave, const int64_t* __restrict__ wave_off,
+                    const int32_t* __restrict__ true_len, const int32_t* __restrict__ off4, int c0, int nsub, int M,
+                    const float* __restrict__ w /*[32][16]*/, const float* __restrict__ bias,
+                    __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xe) {
+  const int m = blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int cg = (threadIdx.x & 3) * 8;
+  float wr[8][7], br[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = __ldg(bias + cg + c);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) wr[c][j] = __ldg(w + (cg + c) * 16 + j);
+  }
+  if (m >= M) return;
+  ConvEpi q{};
+  q.off4 = off4; q.c0 = c0; q.nsub = nsub; q.r = 320; q.h_in = 2;
+  const RowInfo ri = map_row(q, m, M);
+  if (!ri.valid) return;
+  const float* x = wave + wave_off[ri.clip];
+  const int tl = true_len[ri.clip];
+  float s[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    int i = ri.t + j - 6;
+    i = i < 0 ? -i : i;
+    s[j] = i < tl ? __ldg(x + i) : 0.f;
+  }
+  uint32_t raw[4], el[4];
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float a = br[c];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) a = fmaf(wr[c][j], s[j], a);
+    v[c] = a;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    raw[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
+    el[i] = pack2_bf16(elu_fast(bf16_round(v[2 * i])), elu_fast(bf16_round(v[2 * i + 1])));
+  }
+  store_bf16<8>(xh + (size_t)m * 48 + cg, raw);
+  store_bf16<8>(xe + (size_t)m * 32 + cg, el);
+  if (ri.t >= 1 && ri.t <= 2) store_bf16<8>(xe + ((size_t)m - 2 * ri.t) * 32 + cg, el);
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+int make_map_k(CUtensorMap* map, const void* ptr, long long rows, int K, long long ld_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2T_REQUIRE(fn != nullptr, B2T_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2T_REQUIRE(r == CUDA_SUCCESS, B2T_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d ld=%lld", (int)r, rows, K, ld_elems);
+  return B2T_OK;
+}
+
+template <int BN, typename Epi>
+int launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, int kb0, int kb1, int row0, int row1,
+              int M, int N, const Epi& p, cudaStream_t st) {
+  using L = Smem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    B2T_CUDA(cudaFuncSetAttribute(seanet_tc_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = ((M + kBM - 1) / kBM) * (N / BN);
+  if (tiles <= 0) return B2T_OK;
+  int occ = (227 * 1024) / (L::kTotal + 1024);
+  const int tmem_occ = 512 / ((2 * BN < 32) ? 32 : 2 * BN);
+  if (occ > tmem_occ) occ = tmem_occ;
+  if (occ > 3) occ = 3;
+  if (occ < 1) occ = 1;
+  int grid = b2t_num_sms() * occ;
+  if (tiles < grid) grid = tiles;
+  seanet_tc_kernel<BN, Epi><<<grid, kThreads, L::kTotal, st>>>(a0, a1, w, kb0, kb1, row0, row1, M, N, p);
+  B2T_LAUNCH_CHECK();
+  return B2T_OK;
+}
+
+int launch_conv(const CUtensorMap& a, const CUtensorMap& w, int K, int M, int N, const ConvEpi& p, cudaStream_t st) {
+  const int kb = (K + kBK - 1) / kBK;
+  switch (N) {
+    case 16: return launch_bn<16, ConvEpi>(a, a, w, kb, 0, 0, 0, M, N, p, st);
+    case 32: return launch_bn<32, ConvEpi>(a, a, w, kb, 0, 0, 0, M, N, p, st);
+    case 64: return launch_bn<64, ConvEpi>(a, a, w, kb, 0, 0, 0, M, N, p, st);
+    case 128: return launch_bn<128, ConvEpi>(a, a, w, kb, 0, 0, 0, M, N, p, st);
+    default:
+      B2T_REQUIRE(N % 256 == 0, B2T_ERR_ARG, "seanet_tc: unsupported N=%d", N);
+      return launch_bn<256, ConvEpi>(a, a, w, kb, 0, 0, 0, M, N, p, st);
+  }
+}
+
+constexpr int kR[5] = {320, 160, 40, 8, 1};      // rows per frame at level l
+constexpr int kH[5] = {2, 4, 5, 8, 6};           // halo rows in front of every clip at level l
+constexpr int kC[5] = {32, 64, 128, 256, 512};
+constexpr int kS[4] = {2, 4, 5, 8};
+constexpr int kGuard = 16;                       // rows in front of every buffer (windows of row 0 reach back)
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct TcWs {
+  __nv_bfloat16* xe[4]; __nv_bfloat16* xh[4]; __nv_bfloat16* ye[4];   // sub-batch buffers (point past the guard)
+  __nv_bfloat16* x4t; __nv_bfloat16* s1t; __nv_bfloat16* h2t; __nv_bfloat16* s2e;
+  float* emb; float* c;
+  size_t total;
+};
+
+TcWs tc_carve(void* base, long long sub_frames, int sub_clips, long long total4, int n_clips) {
+  TcWs w{};
+  uint8_t* p = (uint8_t*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* r = p ? p + off : nullptr; off += align256(bytes); return r; };
+  for (int l = 0; l < 4; ++l) {
+    const size_t rows = (size_t)kR[l] * sub_frames + (size_t)kH[l] * sub_clips + kGuard + kBM;
+    const size_t g = (size_t)kGuard;
+    uint8_t* a = take(rows * kC[l] * 2); uint8_t* b = take(rows * (kC[l] * 3 / 2) * 2); uint8_t* c = take(rows * kC[l] * 2);
+    w.xe[l] = a ? (__nv_bfloat16*)a + g * kC[l] : nullptr;
+    w.xh[l] = b ? (__nv_bfloat16*)b + g * (kC[l] * 3 / 2) : nullptr;
+    w.ye[l] = c ? (__nv_bfloat16*)c + g * kC[l] : nullptr;
+  }
+  const size_t t4 = (size_t)total4 + kBM;
+  w.x4t = (__nv_bfloat16*)take(t4 * 512 * 2);
+  w.s1t = (__nv_bfloat16*)take(t4 * 512 * 2);
+  w.h2t = (__nv_bfloat16*)take(t4 * 512 * 2);
+  uint8_t* s = take((t4 + 6 * (size_t)n_clips + kGuard) * 512 * 2);
+  w.s2e = s ? (__nv_bfloat16*)s + (size_t)kGuard * 512 : nullptr;
+  w.emb = (float*)take((size_t)total4 * 128 * 4);
+  w.c = (float*)take((size_t)n_clips * 512 * 4);
+  w.total = off;
+  return w;
+}
+
+// greedy split of the clip list into front-end sub-batches of at most kSubFrames frames
+constexpr long long kSubFrames = 24576;
+struct SubBatch { int c0, c1; long long frames; };
+std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* max_frames, int* max_clips) {
+  std::vector<SubBatch> v;
+  long long mf = 0; int mc = 0;
+  int c = 0;
+  while (c < n) {
+    SubBatch s{c, c, 0};
+    while (s.c1 < n && (s.c1 == s.c0 || s.frames + frames_host[s.c1] <= kSubFrames)) { s.frames += frames_host[s.c1]; ++s.c1; }
+    if (s.frames > mf) mf = s.frames;
+    if (s.c1 - s.c0 > mc) mc = s.c1 - s.c0;
+    v.push_back(s);
+    c = s.c1;
+  }
+  *max_frames = mf; *max_clips = mc;
+  return v;
+}
+
+}  // namespace
+
+size_t b2t_seanet_tc_workspace_bytes(const b2t_acoustic_batch* b) {
+  if (!b->frames_host) return 0;
+  long long mf; int mc;
+  split_clips(b->frames_host, b->n_clips, &mf, &mc);
+  return tc_carve(nullptr, mf, mc, b->total[4], b->n_clips).total;
+}
+
+// Encoder on tensor cores: wave -> emb fp32 [total4, 128] (dense frame order).  `T(name)` resolves model tensors.
+int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t_acoustic_batch* b, void* workspace,
+                         size_t workspace_bytes, float* emb, const int32_t* active_host, cudaStream_t st) {
+  B2T_REQUIRE(b->frames_host && b->rank && b->toff, B2T_ERR_ARG, "seanet_tc: batch lacks frames_host / rank / toff");
+  B2T_REQUIRE(b->aligned320, B2T_ERR_ARG, "seanet_tc: every clip length must be a multiple of 320 samples");
+  long long mf; int mc;
+  std::vector<SubBatch> subs = split_clips(b->frames_host, b->n_clips, &mf, &mc);
+  TcWs w = tc_carve(workspace, mf, mc, b->total[4], b->n_clips);
+  B2T_REQUIRE(workspace_bytes >= w.total, B2T_ERR_WORKSPACE, "seanet_tc: workspace %zu < %zu", workspace_bytes, w.total);
+  B2T_REQUIRE((long long)kR[0] * mf + (long long)kH[0] * mc < (1LL << 31) - 256, B2T_ERR_ARG, "seanet_tc: sub-batch too large");
+  const int total4 = b->total[4], n = b->n_clips;
+#define RUN(call) do { int rc__ = (call); if (rc__ != B2T_OK) return rc__; } while (0)
+
+  // ---- strided-conv front end, one sub-batch of clips at a time (levels 0-3 reuse the same buffers) ----
+  for (const SubBatch& sb : subs) {
+    const int ns = sb.c1 - sb.c0;
+    long long Ml[5];
+    for (int l = 0; l < 5; ++l) Ml[l] = (long long)kR[l] * sb.frames + (long long)kH[l] * ns;
+    {
+      const int M0 = (int)Ml[0];
+      seanet_conv0_kernel<<<(M0 + 63) / 64, 256, 0, st>>>(wave, b->wave_off, b->true_len, b->off[4], sb.c0, ns, M0,
+                                                            wt.conv0_w, wt.conv0_b, w.xh[0], w.xe[0]);
+      B2T_LAUNCH_CHECK();
+    }
+    for (int l = 0; l < 4; ++l) {
+      const int C = kC[l], s = kS[l], M = (int)Ml[l];
+      CUtensorMap ma, mw;
+      ConvEpi e{};
+      e.off4 = b->off[4]; e.rank = b->rank; e.toff = b->toff; e.c0 = sb.c0; e.nsub = ns; e.c0_out = sb.c0;
+      // (1) ELU -> Conv(C -> C/2, k3): window of row m = rows m-2 .. m of xe (3C contiguous elements)
+      RUN(make_map_k(&ma, w.xe[l] - 2 * C, M, 3 * C, C, kBM));
+      RUN(make_map_k(&mw, wt.k3_w[l], C / 2, wt.k3_kpad[l], wt.k3_kpad[l], C / 2));
+      e.bias = wt.k3_b[l]; e.out_raw = nullptr; e.out_f32 = nullptr;
+      e.out_elu = w.xh[l] + C; e.ld_elu = C * 3 / 2; e.r = kR[l]; e.h_in = kH[l]; e.h_out = kH[l]; e.mirror = 0; e.tm_out = 0;
+      RUN(launch_conv(ma, mw, 3 * C, M, C / 2, e, st));
+      // (2) shortcut(x) + Conv(C/2 -> C, k1)(ELU(h)) as one GEMM over [x | ELU(h)], then ELU for the strided conv
+      RUN(make_map_k(&ma, w.xh[l], M, C * 3 / 2, C * 3 / 2, kBM));
+      RUN(make_map_k(&mw, wt.res_w[l], C, wt.res_kpad[l], wt.res_kpad[l], C > 256 ? 256 : C));
+      e.bias = wt.res_b[l]; e.out_elu = w.ye[l]; e.ld_elu = C; e.mirror = 1;
+      RUN(launch_conv(ma, mw, C * 3 / 2, M, C, e, st));
+      // (3) Conv(C -> 2C, k = 2s, stride s): super-rows of s input rows; window of output row m' = super-rows m'-1, m'
+      const int Mo = (int)(Ml[l] / s);        // = R[l+1]*frames + 1*ns  (one halo super-row per clip)
+      RUN(make_map_k(&ma, w.ye[l] - s * C, Mo, 2 * s * C, (long long)s * C, kBM));
+      RUN(make_map_k(&mw, wt.down_w[l], 2 * C, wt.down_kpad[l], wt.down_kpad[l], 2 * C > 256 ? 256 : 2 * C));
+      e.bias = wt.down_b[l]; e.r = kR[l + 1]; e.h_in = 1; e.mirror = 1;
+      if (l < 3) {
+        e.out_raw = w.xh[l + 1]; e.ld_raw = 3 * C; e.out_elu = w.xe[l + 1]; e.ld_elu = 2 * C; e.h_out = kH[l + 1];
+      } else {
+        e.out_raw = w.x4t; e.ld_raw = 512; e.out_elu = nullptr; e.tm_out = 1; e.h_out = 0; e.mirror = 0;
+      }
+      RUN(launch_conv(ma, mw, 2 * s * C, Mo, 2 * C, e, st));
+    }
+  }
+
+  // ---- LSTM: per step one GEMM [x_t | h_{t-1}] . [W_ih | W_hh]^T with the cell update in the epilogue ----
+  std::vector<int> toff(b->t_max + 1, 0);
+  for (int t = 0; t < b->t_max; ++t) toff[t + 1] = toff[t] + active_host[t];
+  for (int layer = 0; layer < 2; ++layer) {
+    const __nv_bfloat16* xin = layer == 0 ? w.x4t : w.s1t;
+    __nv_bfloat16* hout = layer == 0 ? w.s1t : w.h2t;
+    CUtensorMap mx, mh, mw;
+    RUN(make_map_k(&mx, xin, (long long)total4 + kBM, 512, 512, kBM));
+    RUN(make_map_k(&mh, hout, (long long)total4 + kBM, 512, 512, kBM));
+    RUN(make_map_k(&mw, wt.lstm_w[layer], 2048, 1024, 1024, 256));
+    LstmEpi e{};
+    e.bias = wt.lstm_b[layer]; e.order = b->order; e.off4 = b->off[4]; e.c = w.c; e.h_out = hout;
+    e.skip = layer == 1 ? w.x4t : nullptr; e.s2e = layer == 1 ? w.s2e : nullptr;
+    for (int t = 0; t < b->t_max; ++t) {
+      const int na = active_host[t];
+      if (na <= 0) break;
+      e.t = t; e.toff_t = toff[t]; e.n_active = na;
+      RUN((launch_bn<256, LstmEpi>(mx, mh, mw, 8, t > 0 ? 8 : 0, toff[t], t > 0 ? toff[t - 1] : 0, na, 2048, e, st)));
+    }
+  }
+
+  // ---- ELU -> Conv(512 -> 128, k7) over the clip-major padded rows (halo 6) -> dense fp32 embeddings ----
+  {
+    CUtensorMap ma, mw;
+    const long long M = (long long)total4 + 6LL * n;
+    RUN(make_map_k(&ma, w.s2e - 6 * 512, M, 7 * 512, 512, kBM));
+    RUN(make_map_k(&mw, wt.final_w, 128, 7 * 512, 7 * 512, 128));
+    ConvEpi e{};
+    e.off4 = b->off[4]; e.rank = b->rank; e.toff = b->toff; e.c0 = 0; e.nsub = n; e.c0_out = 0;
+    e.bias = wt.final_b; e.out_f32 = emb ? emb : w.emb; e.ld_f32 = 128; e.r = 1; e.h_in = 6; e.h_out = 0;
+    RUN(launch_conv(ma, mw, 7 * 512, (int)M, 128, e, st));
+  }
+#undef RUN
+  return B2T_OK;
+}
+
+float* b2t_seanet_tc_emb(void* workspace, const b2t_acoustic_batch* b) {
+  long long mf; int mc;
+  split_clips(b->frames_host, b->n_clips, &mf, &mc);
+  return tc_carve(workspace, mf, mc, b->total[4], b->n_clips).emb;
+}

@@ -54,7 +54,8 @@ class AcousticBatch(C.Structure):
     """b2t_acoustic_batch"""
     _fields_ = [('n_clips', C.c_int32), ('t_max', C.c_int32), ('total', C.c_int32 * 5), ('n_tiles', C.c_int32 * 5),
                 ('wave_off', C.c_void_p), ('true_len', C.c_void_p), ('len', C.c_void_p * 5), ('off', C.c_void_p * 5),
-                ('tile_clip', C.c_void_p * 5), ('tile_t0', C.c_void_p * 5), ('order', C.c_void_p)]
+                ('tile_clip', C.c_void_p * 5), ('tile_t0', C.c_void_p * 5), ('order', C.c_void_p),
+                ('rank', C.c_void_p), ('toff', C.c_void_p), ('frames_host', C.c_void_p), ('aligned320', C.c_int32)]
 
 
 class GemmArgs(C.Structure):
@@ -109,9 +110,9 @@ def load() -> C.CDLL:
     lib.b2t_acoustic_destroy.argtypes = [vp]
     lib.b2t_acoustic_destroy.restype = None
     lib.b2t_acoustic_set_tensor.argtypes = [vp, C.c_char_p, vp]
-    lib.b2t_acoustic_workspace_bytes.argtypes = [C.POINTER(AcousticBatch)]
+    lib.b2t_acoustic_workspace_bytes.argtypes = [C.POINTER(AcousticBatch), i32]
     lib.b2t_acoustic_workspace_bytes.restype = sz
-    lib.b2t_acoustic_encode.argtypes = [vp, vp, C.POINTER(AcousticBatch), i32, vp, sz, vp, vp, vp, vp]
+    lib.b2t_acoustic_encode.argtypes = [vp, vp, C.POINTER(AcousticBatch), i32, i32, vp, sz, vp, vp, vp, vp]
     lib.b2t_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double)]
     _lib = lib
     return lib

@@ -226,6 +226,12 @@ typedef struct {
   const int32_t* tile_clip[5];
   const int32_t* tile_t0[5];
   const int32_t* order;          /* [n_clips] clip ids sorted by len[4] descending (LSTM active prefix) */
+  /* tensor-core (bf16) path only: */
+  const int32_t* rank;           /* [n_clips] inverse of `order` (device)                              */
+  const int32_t* toff;           /* [t_max+1] prefix sums of the active-clip count per frame index (device):
+                                    time-major row of (frame t, sorted clip b) = toff[t] + b           */
+  const int32_t* frames_host;    /* [n_clips] HOST copy of len[4]; sizes the front-end sub-batches      */
+  int32_t aligned320;            /* 1 iff every len[0] is a multiple of 320 samples                    */
 } b2t_acoustic_batch;
 
 typedef struct b2t_acoustic_model b2t_acoustic_model;
@@ -233,15 +239,23 @@ b2t_acoustic_model* b2t_acoustic_create(void);
 void b2t_acoustic_destroy(b2t_acoustic_model* m);
 /* fp32 tensors: conv<i>.w [C_out, pad16(k*C_in)] (tap-major, weight-norm applied) and conv<i>.b for the 18
  * convs in forward order, lstm<l>.w_ih / .w_hh [2048,512], lstm<l>.b (= b_ih + b_hh), rvq.codebooks
- * [n_q_total,1024,128], rvq.half_norm [n_q_total,1024], rvq.cmax_half [n_q_total].                    */
+ * [n_q_total,1024,128], rvq.half_norm [n_q_total,1024], rvq.cmax_half [n_q_total].
+ * B2T_PREC_BF16 additionally needs (bf16 unless noted; l = 0..3 = resolution level, C = 32 << l):
+ *   tc.k3<l>.w [C/2, pad64(3C)] + tc.k3<l>.b fp32;  tc.res<l>.w [C, pad64(1.5C)] = [shortcut | k1] + tc.res<l>.b
+ *   fp32 (= sum of both biases);  tc.down<l>.w [2C, 2*s*C] + tc.down<l>.b fp32;  tc.final.w [128, 3584] +
+ *   tc.final.b fp32;  tc.lstm<j>.w [2048, 1024] = [W_ih | W_hh] with row 4*u+g = gate g of unit u, tc.lstm<j>.b
+ *   fp32 in the same row order.                                                                       */
 int b2t_acoustic_set_tensor(b2t_acoustic_model* m, const char* name, const void* ptr);
-size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* batch);
+size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* batch, int precision);
 /* codes: int16 [n_q, total[4]] (stage-major over the packed frames).  emb_out (optional): fp32
  * [total[4], 128] encoder output.  active_host[t] (HOST array, t_max entries) = number of clips with
  * more than t frames; it sizes the per-step LSTM launches.                                           */
+/* precision: B2T_PREC_FP32 = CUDA-core fp32 kernels (the reference's CPU numerics, any clip length);
+ * B2T_PREC_BF16 = tcgen05 encoder with bf16 operands / fp32 accumulation (the reference's GPU autocast
+ * numerics); needs batch->aligned320.  The residual VQ is exact (fp32 residuals, fp64-checked) in both. */
 int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic_batch* batch,
-                        int n_q, void* workspace, size_t workspace_bytes, int16_t* codes, float* emb_out,
-                        const int32_t* active_host, void* stream);
+                        int n_q, int precision, void* workspace, size_t workspace_bytes, int16_t* codes,
+                        float* emb_out, const int32_t* active_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,12 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope='module')
 def enc(cuda_device):
-    return AcousticEncoder(device='cuda:0', state_dict=synthetic_encodec_state_dict(0))
+    return AcousticEncoder(device='cuda:0', state_dict=synthetic_encodec_state_dict(0), precision='fp32')
+
+
+@pytest.fixture(scope='module')
+def enc16(cuda_device):
+    return AcousticEncoder(device='cuda:0', state_dict=synthetic_encodec_state_dict(0), precision='bf16')
 
 
 @pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
@@ -40,7 +45,52 @@ def test_acoustic_matches_golden(enc, cuda_device, golden_dir, tag):
     assert torch.equal(codes.cpu().long(), want)
 
 
-def test_acoustic_packed_equals_padded(enc, cuda_device):
+@pytest.mark.parametrize('tag', ['a', 'c'])
+def test_acoustic_bf16_tensor_path_matches_golden(enc16, cuda_device, golden_dir, tag):
+    """tcgen05 encoder (bf16 operands, fp32 accumulation = the reference's GPU autocast numerics) against the fp32
+    EnCodec stand-in goldens: embeddings within 1e-2 relative (north star, bf16); the RVQ stage is exact given the
+    kernel's own embeddings; the first codebooks agree with the fp32 reference up to the embedding noise."""
+    g = np.load(os.path.join(golden_dir, 'acoustic.npz'))
+    lengths = g[f'lengths_{tag}']
+    w = torch.stack([synthetic_waveform(20 + i, int(n), 24000) for i, n in enumerate(lengths)])
+    codes, emb = enc16(w.to(cuda_device), None, want_emb=True)
+    torch.cuda.synchronize()
+    assert enc16.last_precision == 'bf16'
+    ref = torch.from_numpy(g[f'emb_{tag}'])
+    assert emb.shape == ref.shape and codes.dtype == torch.int16
+    err = float((emb.cpu() - ref).norm() / ref.norm())
+    print(f'bf16 tensor path, golden {tag}: embedding rel err {err:.3e}')
+    assert err < 1e-2, err
+    want = seanet.rvq_codes(emb.cpu().float(), synthetic_encodec_state_dict(0), 16).transpose(0, 1)
+    assert torch.equal(codes.cpu().long(), want)
+    agree0 = float((codes.cpu().numpy()[:, 0] == g[f'codes_{tag}'][:, 0]).mean())
+    print(f'first-codebook agreement with the fp32 reference: {agree0:.4f}')
+    assert agree0 >= 0.9, agree0
+
+
+def test_acoustic_bf16_matches_fp32_kernels_incl_tiny_clips(enc, enc16, cuda_device):
+    """Ragged batch with 1-frame and 6-frame clips (halo rows the mirror cannot fill must read as zeros: the
+    short-input rule of EncodecConv1d._pad1d) — the tensor path against the fp32 CUDA-core path."""
+    lengths = [320, 320 * 6, 320 * 7, 320 * 40, 320 * 2, 320 * 133]
+    clips = [synthetic_waveform(80 + i, n, 24000) for i, n in enumerate(lengths)]
+    offs = np.zeros(len(clips), dtype=np.int64)
+    offs[1:] = np.cumsum(lengths)[:-1]
+    wave = torch.cat(clips).to(cuda_device)
+    plan = plan_acoustic(lengths, offs, lengths)
+    _, e32 = enc.encode_plan(wave, plan, want_emb=True)
+    _, e16 = enc16.encode_plan(wave, plan, want_emb=True)
+    torch.cuda.synchronize()
+    assert enc16.last_precision == 'bf16' and enc.last_precision == 'fp32'
+    fo = plan.offs[4]
+    for i in range(len(lengths)):
+        a, b = e32[fo[i]:fo[i + 1]].cpu(), e16[fo[i]:fo[i + 1]].cpu()
+        err = float((a - b).norm() / a.norm())
+        assert err < 1.5e-2, (i, err)
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_acoustic_packed_equals_padded(enc, enc16, cuda_device, prec):
+    enc = enc if prec == 'fp32' else enc16
     lengths = [24000, 7777, 3200, 15001]
     clips = [synthetic_waveform(40 + i, n, 24000) for i, n in enumerate(lengths)]
     total = 24000
