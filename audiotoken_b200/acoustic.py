@@ -156,6 +156,11 @@ class AcousticWeights:
         t['rvq.codebooks'] = cb.to(device).contiguous()
         t['rvq.half_norm'] = hn.float().to(device).contiguous()
         t['rvq.cmax_half'] = hn.max(dim=1).values.float().to(device).contiguous()
+        # tensor-core RVQ (csrc/rvq_tc.cu): error-compensated bf16 pair of every codebook, [n_q*1024, hi(128) | lo(128)]
+        hi = cb.to(torch.bfloat16)
+        lo = (cb - hi.float()).to(torch.bfloat16)
+        t['rvq.c2'] = torch.cat([hi, lo], dim=-1).reshape(-1, 256).to(device).contiguous()
+        t['rvq.stats'] = torch.zeros(2, dtype=torch.int32, device=device)
         # tensor-core path (csrc/seanet_tc.cu): bf16 weights, K padded to 64, tap-major; weight-norm is evaluated in
         # fp32 and then rounded, as autocast does
         def tapmajor(i):
@@ -258,6 +263,23 @@ class AcousticEncoder(torch.nn.Module):
             self.last_launches = self.lib.b2t_last_launch_count()
             self._keep = db
         return codes, emb
+
+    def rvq_encode(self, emb: torch.Tensor, impl: int = L.IMPL_AUTO, n_q: Optional[int] = None) -> torch.Tensor:
+        """emb fp32 [rows, 128] (device) -> codes int16 [n_q, rows]; the quantiser stage alone."""
+        assert emb.is_cuda and emb.dtype == torch.float32 and emb.is_contiguous() and emb.shape[1] == 128
+        n_q = self.num_codebooks if n_q is None else n_q
+        codes = torch.empty(n_q, emb.shape[0], dtype=torch.int16, device=emb.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.b2t_rvq_encode(self.handle, emb.data_ptr(), emb.shape[0], n_q, impl, codes.data_ptr(),
+                                            L.stream_ptr()), 'b2t_rvq_encode')
+        return codes
+
+    def rvq_stats(self):
+        """(fp64 re-scores, exhaustive re-scans) taken by the tensor RVQ kernel since the last call."""
+        s = self.weights.tensors['rvq.stats']
+        out = tuple(int(v) for v in s.cpu())
+        s.zero_()
+        return out
 
     def forward(self, input_batch: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, want_emb: bool = False):
         """input_batch [B, L] fp32 -> int16 [B, n_q, ceil(L/320)]; attention_mask is ignored (encoder.py:44)."""

@@ -19,6 +19,9 @@
 #include "seanet_tc.h"
 
 void b2t_reset_launch_count();
+int b2t_rvq_tensor(const float* emb, int rows, const void* c2, int n_q_total, const float* codebooks,
+                   const float* half_norm, const float* cmax_half, int n_q, int16_t* codes, unsigned int* stats,
+                   cudaStream_t st);   // rvq_tc.cu
 
 namespace {
 
@@ -350,8 +353,11 @@ extern "C" size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* b, int 
   return ac_carve(nullptr, b).total;
 }
 
+bool g_rvq_tensor = true;   // b2t_set_option("rvq_tensor", 0/1)
+
 namespace {
-int rvq_launch(const b2t_acoustic_model* m, const float* emb, int rows, int n_q, int16_t* codes, cudaStream_t st) {
+int rvq_launch(const b2t_acoustic_model* m, const float* emb, int rows, int n_q, int16_t* codes, cudaStream_t st,
+               int impl = B2T_IMPL_AUTO) {
   const char* names[3] = {"rvq.codebooks", "rvq.half_norm", "rvq.cmax_half"};
   const float* t[3];
   for (int i = 0; i < 3; ++i) {
@@ -359,6 +365,11 @@ int rvq_launch(const b2t_acoustic_model* m, const float* emb, int rows, int n_q,
     B2T_REQUIRE(it != m->t.end(), B2T_ERR_STATE, "b2t_acoustic_encode: tensor '%s' not set", names[i]);
     t[i] = (const float*)it->second;
   }
+  auto c2 = m->t.find("rvq.c2");
+  B2T_REQUIRE(impl != B2T_IMPL_TENSOR || c2 != m->t.end(), B2T_ERR_STATE, "b2t_rvq_encode: tensor 'rvq.c2' not set");
+  if ((impl == B2T_IMPL_TENSOR || (impl == B2T_IMPL_AUTO && g_rvq_tensor)) && c2 != m->t.end())
+    return b2t_rvq_tensor(emb, rows, c2->second, n_q, t[0], t[1], t[2], n_q, codes,
+                          (unsigned int*)(m->t.count("rvq.stats") ? m->t.at("rvq.stats") : nullptr), st);
   static bool cfg = false;
   if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RvqSmem))); cfg = true; }
   rvq_kernel<<<(rows + 63) / 64, 256, sizeof(RvqSmem), st>>>(emb, rows, t[0], t[1], t[2], n_q, codes);
@@ -399,6 +410,16 @@ int encode_tc(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic
   return rvq_launch(m, emb, b->total[4], n_q, codes, st);
 }
 }  // namespace
+
+extern "C" int b2t_rvq_encode(const b2t_acoustic_model* m, const float* emb, int rows, int n_q, int impl,
+                              int16_t* codes, void* stream) {
+  B2T_REQUIRE(m && emb && codes, B2T_ERR_ARG, "b2t_rvq_encode: null argument");
+  B2T_REQUIRE(n_q >= 1 && n_q <= 32 && rows >= 0, B2T_ERR_ARG, "b2t_rvq_encode: bad n_q / rows");
+  int rc = b2t_arch_ok();
+  if (rc != B2T_OK) return rc;
+  if (rows == 0) return B2T_OK;
+  return rvq_launch(m, emb, rows, n_q, codes, (cudaStream_t)stream, impl);
+}
 
 extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic_batch* b,
                                    int n_q, int precision, void* workspace, size_t workspace_bytes, int16_t* codes,

@@ -240,6 +240,8 @@ void b2t_acoustic_destroy(b2t_acoustic_model* m);
 /* fp32 tensors: conv<i>.w [C_out, pad16(k*C_in)] (tap-major, weight-norm applied) and conv<i>.b for the 18
  * convs in forward order, lstm<l>.w_ih / .w_hh [2048,512], lstm<l>.b (= b_ih + b_hh), rvq.codebooks
  * [n_q_total,1024,128], rvq.half_norm [n_q_total,1024], rvq.cmax_half [n_q_total].
+ * Optional rvq.c2 bf16 [n_q_total*1024, 256] = [bf16(E) | bf16(E - bf16(E))] enables the tcgen05 residual-VQ
+ * kernel (exact result, see csrc/rvq_tc.cu) and rvq.stats uint32[2] counts its fp64 re-scores / re-scans.
  * B2T_PREC_BF16 additionally needs (bf16 unless noted; l = 0..3 = resolution level, C = 32 << l):
  *   tc.k3<l>.w [C/2, pad64(3C)] + tc.k3<l>.b fp32;  tc.res<l>.w [C, pad64(1.5C)] = [shortcut | k1] + tc.res<l>.b
  *   fp32 (= sum of both biases);  tc.down<l>.w [2C, 2*s*C] + tc.down<l>.b fp32;  tc.final.w [128, 3584] +
@@ -247,6 +249,12 @@ void b2t_acoustic_destroy(b2t_acoustic_model* m);
  *   fp32 in the same row order.                                                                       */
 int b2t_acoustic_set_tensor(b2t_acoustic_model* m, const char* name, const void* ptr);
 size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* batch, int precision);
+/* Residual VQ alone (reference encoder.py:50-52 `quantizer.encode`): emb fp32 [rows, 128] -> codes int16
+ * [n_q, rows].  Stage rule: idx = argmin_k |r - E_q[k]|^2 (first index on ties), r -= E_q[idx] in fp32.
+ * impl: B2T_IMPL_TENSOR = tcgen05 bf16x3 scores + certified / fp64-resolved winner (needs rvq.c2),
+ * B2T_IMPL_SIMT = fp32 CUDA cores + fp64 check; both return the exact argmin of every stage.        */
+int b2t_rvq_encode(const b2t_acoustic_model* m, const float* emb, int rows, int n_q, int impl,
+                   int16_t* codes, void* stream);
 /* codes: int16 [n_q, total[4]] (stage-major over the packed frames).  emb_out (optional): fp32
  * [total[4], 128] encoder output.  active_host[t] (HOST array, t_max entries) = number of clips with
  * more than t frames; it sizes the per-step LSTM launches.                                           */

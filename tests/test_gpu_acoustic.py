@@ -88,6 +88,33 @@ def test_acoustic_bf16_matches_fp32_kernels_incl_tiny_clips(enc, enc16, cuda_dev
         assert err < 1.5e-2, (i, err)
 
 
+def test_rvq_tensor_exact(cuda_device):
+    """Residual-VQ stage alone: tcgen05 kernel == CUDA-core kernel == fp64 oracle, on random residuals, on rows that
+    ARE codewords (zero residual afterwards), with duplicated codewords (first index wins) and a ragged row count."""
+    from audiotoken_b200 import lib as L
+    sd = synthetic_encodec_state_dict(0)
+    sd = {k: v.clone() for k, v in sd.items()}
+    e0 = sd['quantizer.layers.0.codebook.embed']
+    e0[700] = e0[13]                         # exact duplicate: index 13 must win
+    e0[901] = e0[900] * (1 + 2 ** -20)       # near-duplicate inside the error band
+    enc = AcousticEncoder(device='cuda:0', state_dict=sd, precision='bf16')
+    g = torch.Generator().manual_seed(7)
+    emb = torch.randn(1000, 128, generator=g) * 0.9
+    emb[:64] = e0[torch.arange(64) * 3 % 1024]                 # exact codewords
+    emb[64:96] = e0[13] + 1e-4 * torch.randn(32, 128, generator=g)
+    emb[96:128] = e0[900] + 1e-5 * torch.randn(32, 128, generator=g)
+    want = seanet.rvq_codes(emb.t().unsqueeze(0), sd, 16)[:, 0]            # [16, 1000]
+    dev = emb.to(cuda_device).contiguous()
+    enc.rvq_stats()
+    tc = enc.rvq_encode(dev, L.IMPL_TENSOR).cpu().long()
+    rescored, rescans = enc.rvq_stats()
+    simt = enc.rvq_encode(dev, L.IMPL_SIMT).cpu().long()
+    print(f'tensor RVQ: {rescored} fp64 re-scores, {rescans} exhaustive re-scans of {16 * 1000} (row, stage) pairs')
+    assert torch.equal(simt, want)
+    assert torch.equal(tc, want)
+    assert rescored > 0
+
+
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
 def test_acoustic_packed_equals_padded(enc, enc16, cuda_device, prec):
     enc = enc if prec == 'fp32' else enc16
