@@ -467,10 +467,12 @@ int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, i
 
 extern int g_attn_heads_per_cta;   // attention_tc.cu
 extern bool g_rvq_tensor;          // acoustic.cu
+extern int g_rvq_dbg;              // rvq_tc.cu
 
 extern "C" int b2t_set_option(const char* name, int value) {
   B2T_REQUIRE(name, B2T_ERR_ARG, "b2t_set_option: null name");
   if (std::string(name) == "gemm_multicast") { g_multicast = value != 0; return B2T_OK; }
+  if (std::string(name) == "rvq_dbg") { g_rvq_dbg = value; return B2T_OK; }
   if (std::string(name) == "rvq_tensor") { g_rvq_tensor = value != 0; return B2T_OK; }
   if (std::string(name) == "attn_heads_per_cta") {
     B2T_REQUIRE(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, B2T_ERR_ARG, "attn_heads_per_cta must divide 16");

@@ -54,6 +54,12 @@ B2T_DEVICE void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t 
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
 }
+// multicast: the box lands at the same shared-memory offset in every CTA of `mask` and signals each one's mbarrier
+B2T_DEVICE void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
 // shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank 0
 B2T_DEVICE uint32_t mapa_rank0(uint32_t addr) {
   uint32_t r;
@@ -84,6 +90,11 @@ B2T_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uin
 }
 B2T_DEVICE void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// single-CTA MMAs, arrival multicast to the same barrier offset in every CTA of `mask`
+B2T_DEVICE void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 B2T_DEVICE void umma_commit_pair(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
