@@ -354,6 +354,39 @@ extern "C" size_t b2t_acoustic_workspace_bytes(const b2t_acoustic_batch* b, int 
 }
 
 bool g_rvq_tensor = true;   // b2t_set_option("rvq_tensor", 0/1)
+bool b2t_profile_on();      // pipeline.cu
+
+// ---- optional CUDA-event phase timing of b2t_acoustic_encode (b2t_profile_enable) -------------------
+namespace {
+struct AcProf {
+  std::vector<cudaEvent_t> pool; size_t used = 0;
+  struct Span { int cls; size_t e0, e1; };
+  std::vector<Span> spans;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+};
+thread_local AcProf g_acprof;
+}  // namespace
+void b2t_acoustic_mark(int cls, int begin, cudaStream_t st) {
+  static thread_local size_t open_e0[4];
+  if (!b2t_profile_on() || cls < 0 || cls >= 4) return;
+  if (begin) { open_e0[cls] = g_acprof.used; cudaEventRecord(g_acprof.get(), st); }
+  else { const size_t e1 = g_acprof.used; cudaEventRecord(g_acprof.get(), st); g_acprof.spans.push_back({cls, open_e0[cls], e1}); }
+}
+extern "C" int b2t_acoustic_profile_read(float* ms4) {
+  B2T_REQUIRE(ms4, B2T_ERR_ARG, "b2t_acoustic_profile_read: null argument");
+  for (int i = 0; i < 4; ++i) ms4[i] = 0.f;
+  for (auto& sp : g_acprof.spans) {
+    B2T_CUDA(cudaEventSynchronize(g_acprof.pool[sp.e1]));
+    float ms = 0.f;
+    B2T_CUDA(cudaEventElapsedTime(&ms, g_acprof.pool[sp.e0], g_acprof.pool[sp.e1]));
+    ms4[sp.cls] += ms;
+  }
+  g_acprof.spans.clear(); g_acprof.used = 0;
+  return B2T_OK;
+}
 
 namespace {
 int rvq_launch(const b2t_acoustic_model* m, const float* emb, int rows, int n_q, int16_t* codes, cudaStream_t st,
@@ -407,7 +440,10 @@ int encode_tc(const b2t_acoustic_model* m, const float* wave, const b2t_acoustic
   float* emb = emb_out ? emb_out : b2t_seanet_tc_emb(workspace, b);
   int rc = b2t_seanet_tc_encode(wt, wave, b, workspace, workspace_bytes, emb, active_host, st);
   if (rc != B2T_OK) return rc;
-  return rvq_launch(m, emb, b->total[4], n_q, codes, st);
+  b2t_acoustic_mark(3, 1, st);
+  rc = rvq_launch(m, emb, b->total[4], n_q, codes, st);
+  b2t_acoustic_mark(3, 0, st);
+  return rc;
 }
 }  // namespace
 

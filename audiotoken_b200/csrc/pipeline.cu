@@ -47,6 +47,7 @@ struct Scope {
 }  // namespace
 
 extern "C" int b2t_profile_enable(int on) { g_prof.on = on != 0; return B2T_OK; }
+bool b2t_profile_on() { return g_prof.on; }
 
 // Synchronises, adds up the event spans recorded since the last read into ms_per_class[6]
 // (fbank, layernorm, gemm, attention, dwconv, vq) and returns the GEMM FLOPs issued in *gemm_flops.

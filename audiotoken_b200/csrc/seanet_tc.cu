@@ -26,6 +26,8 @@
 #include "gemm_epilogue.cuh"
 #include "seanet_tc.h"
 
+void b2t_acoustic_mark(int cls, int begin, cudaStream_t st);   // acoustic.cu: 0 front end, 1 LSTM, 2 final conv, 3 RVQ
+
 namespace {
 
 constexpr int kBM = 128;
@@ -33,7 +35,12 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kStages = 4;
 
-B2T_DEVICE float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+// ELU(alpha = 1) with one MUFU: exp(x) = ex2(x * log2 e); every consumer rounds the result to bf16
+B2T_DEVICE float elu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.0f;
+}
 B2T_DEVICE float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 B2T_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
@@ -128,7 +135,7 @@ B2T_DEVICE void conv_epilogue_chunk(const ConvEpi& p, const RowInfo& ri, int col
   if (p.out_elu) {
 #pragma unroll
     for (int i = 0; i < CW / 2; ++i)
-      pk[i] = pack2_bf16(elu_fast(bf16_round(v[2 * i])), elu_fast(bf16_round(v[2 * i + 1])));
+      pk[i] = pack2_bf16(elu_fast(v[2 * i]), elu_fast(v[2 * i + 1]));
     __nv_bfloat16* o = p.out_elu + orow * p.ld_elu + col;
     store_bf16<CW>(o, pk);
     if (p.mirror) {
@@ -205,9 +212,14 @@ struct Smem {
 // out[m, n] = sum_k A[m, k] W[n, k];  A's k-blocks [0, kb0) come from map_a0 (rows row0 + m), the following kb1
 // blocks from map_a1 (rows row1 + m); W k-block index runs over both.
 template <int BN, typename Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1)
 seanet_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_w, int kb0, int kb1, int row0, int row1, int M, int N, Epi p) {
+                 const __grid_constant__ CUtensorMap map_w, int kb0, int kb1, int row0, int row1, int M, int N, Epi p,
+                 int pdl) {
+  // pdl != 0 (LSTM step chain, programmatic dependent launch): this grid may start while the previous step is
+  // still running.  Everything that does not depend on it — barrier/TMEM set-up and the x_t half of the K loop
+  // (operands from map_a0 and the weights) — runs ahead; h_{t-1} (map_a1) and the cell state are touched only
+  // after griddepcontrol.wait.
   using L = Smem<BN>;
   constexpr bool kLstm = std::is_same<Epi, LstmEpi>::value;
   extern __shared__ uint8_t smem_raw[];
@@ -233,6 +245,7 @@ seanet_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     fence_barrier_init();
     fence_proxy_async();
   }
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_w); }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
@@ -243,9 +256,11 @@ seanet_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      bool waited = !pdl;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (!waited && kb >= kb0) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), L::kStageA + L::kStageB);
           if (kb < kb0) tma_load_2d(sA + stage * L::kStageA, &map_a0, full_bar(stage), kb * kBK, row0 + m0);
@@ -280,14 +295,15 @@ seanet_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       }
     }
   } else {
-    // epilogue: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the columns when BN >= 64
+    // epilogue: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the columns when BN >= 32
     const int quad = warp & 3;
     const int part = (warp - 2) >> 2;
-    constexpr int kParts = BN >= 64 ? 2 : 1;
+    constexpr int kParts = BN >= 32 ? 2 : 1;
     constexpr int kColsPerPart = BN / kParts;
-    constexpr int kCW = kColsPerPart >= 32 ? 32 : 16;
+    constexpr int kCW = (kColsPerPart >= 32 && BN > 64) ? 32 : 16;   // narrow chunks keep BN <= 64 within 96 registers
     constexpr int kChunks = kColsPerPart / kCW;
     int acc = 0; uint32_t acc_phase = 0;
+    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
       const int m = m0 + quad * 32 + lane;
@@ -320,19 +336,21 @@ seanet_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // transitivity: no grid of the chain exits early
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-// Conv(1 -> 32, k = 7) on the raw waveform: 4 threads per output row, 8 channels each.
-// xh row = [x (32) | ELU(h) (16)] (ld 48), xe = ELU(x) (ld 32) with the two mirrored halo rows.
-__global__ void __launch_bounds__(256)
+// Conv(1 -> 32, k = 7) on the raw waveform: 4 threads per output row (8 channels each, weights in registers), 512
+// rows per block.  xh row = [x (32) | ELU(h) (16)] (ld 48), xe = ELU(x) (ld 32) with the two mirrored halo rows.
+constexpr int kConv0Rows = 512;
+__global__ void __launch_bounds__(256, 3)
 seanet_conv0_kernel(const float* __restrict__ wave, const int64_t* __restrict__ wave_off,
                     const int32_t* __restrict__ true_len, const int32_t* __restrict__ off4, int c0, int nsub, int M,
                     const float* __restrict__ w /*[32][16]*/, const float* __restrict__ bias,
                     __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xe) {
-  const int m = blockIdx.x * 64 + (threadIdx.x >> 2);
+  __shared__ int s_first;
   const int cg = (threadIdx.x & 3) * 8;
   float wr[8][7], br[8];
 #pragma unroll
@@ -341,37 +359,51 @@ seanet_conv0_kernel(const float* __restrict__ wave, const int64_t* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 7; ++j) wr[c][j] = __ldg(w + (cg + c) * 16 + j);
   }
-  if (m >= M) return;
-  ConvEpi q{};
-  q.off4 = off4; q.c0 = c0; q.nsub = nsub; q.r = 320; q.h_in = 2;
-  const RowInfo ri = map_row(q, m, M);
-  if (!ri.valid) return;
-  const float* x = wave + wave_off[ri.clip];
-  const int tl = true_len[ri.clip];
-  float s[7];
-#pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    int i = ri.t + j - 6;
-    i = i < 0 ? -i : i;
-    s[j] = i < tl ? __ldg(x + i) : 0.f;
+  const int m_block = blockIdx.x * kConv0Rows;
+  const int f0 = __ldg(off4 + c0);
+  auto start = [&](int c) { return 320 * (__ldg(off4 + c0 + c) - f0) + 2 * c; };   // first (halo) row of clip c0 + c
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = nsub;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (start(mid) <= m_block) lo = mid; else hi = mid; }
+    s_first = lo;
   }
-  uint32_t raw[4], el[4];
-  float v[8];
+  __syncthreads();
+  int c = s_first;
+#pragma unroll 1
+  for (int it = 0; it < kConv0Rows / 64; ++it) {
+    const int m = m_block + it * 64 + (threadIdx.x >> 2);
+    if (m >= M) break;
+    while (c + 1 < nsub && start(c + 1) <= m) ++c;
+    const int t = m - start(c) - 2;
+    if (t < 0) continue;                                   // halo row: written by the mirror below
+    const int clip = c0 + c;
+    const float* x = wave + wave_off[clip];
+    const int tl = true_len[clip];
+    float s[7];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float a = br[c];
+    for (int j = 0; j < 7; ++j) {
+      int i = t + j - 6;
+      i = i < 0 ? -i : i;                                  // reflect padding of the 6 left samples
+      s[j] = i < tl ? __ldg(x + i) : 0.f;
+    }
+    uint32_t raw[4], el[4];
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) a = fmaf(wr[c][j], s[j], a);
-    v[c] = a;
+    for (int ch = 0; ch < 8; ++ch) {
+      float a = br[ch];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) a = fmaf(wr[ch][j], s[j], a);
+      v[ch] = a;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      raw[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
+      el[i] = pack2_bf16(elu_fast(bf16_round(v[2 * i])), elu_fast(bf16_round(v[2 * i + 1])));
+    }
+    store_bf16<8>(xh + (size_t)m * 48 + cg, raw);
+    store_bf16<8>(xe + (size_t)m * 32 + cg, el);
+    if (t >= 1 && t <= 2) store_bf16<8>(xe + ((size_t)m - 2 * t) * 32 + cg, el);
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    raw[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
-    el[i] = pack2_bf16(elu_fast(bf16_round(v[2 * i])), elu_fast(bf16_round(v[2 * i + 1])));
-  }
-  store_bf16<8>(xh + (size_t)m * 48 + cg, raw);
-  store_bf16<8>(xe + (size_t)m * 32 + cg, el);
-  if (ri.t >= 1 && ri.t <= 2) store_bf16<8>(xe + ((size_t)m - 2 * ri.t) * 32 + cg, el);
 }
 
 // ---- host ----------------------------------------------------------------------------------------
@@ -391,7 +423,7 @@ int make_map_k(CUtensorMap* map, const void* ptr, long long rows, int K, long lo
 
 template <int BN, typename Epi>
 int launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, int kb0, int kb1, int row0, int row1,
-              int M, int N, const Epi& p, cudaStream_t st) {
+              int M, int N, const Epi& p, cudaStream_t st, int pdl = 0) {
   using L = Smem<BN>;
   static bool configured = false;
   if (!configured) {
@@ -403,11 +435,22 @@ int launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w
   int occ = (227 * 1024) / (L::kTotal + 1024);
   const int tmem_occ = 512 / ((2 * BN < 32) ? 32 : 2 * BN);
   if (occ > tmem_occ) occ = tmem_occ;
-  if (occ > 3) occ = 3;
+  if (occ > (BN <= 64 ? 2 : 1)) occ = (BN <= 64 ? 2 : 1);   // register budget (__launch_bounds__)
   if (occ < 1) occ = 1;
   int grid = b2t_num_sms() * occ;
   if (tiles < grid) grid = tiles;
-  seanet_tc_kernel<BN, Epi><<<grid, kThreads, L::kTotal, st>>>(a0, a1, w, kb0, kb1, row0, row1, M, N, p);
+  if (pdl) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = L::kTotal; lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+    B2T_CUDA(cudaLaunchKernelEx(&lc, seanet_tc_kernel<BN, Epi>, a0, a1, w, kb0, kb1, row0, row1, M, N, p, pdl));
+    b2t_count_launch();
+    return B2T_OK;
+  }
+  seanet_tc_kernel<BN, Epi><<<grid, kThreads, L::kTotal, st>>>(a0, a1, w, kb0, kb1, row0, row1, M, N, p, 0);
   B2T_LAUNCH_CHECK();
   return B2T_OK;
 }
@@ -466,7 +509,8 @@ TcWs tc_carve(void* base, long long sub_frames, int sub_clips, long long total4,
 }
 
 // greedy split of the clip list into front-end sub-batches of at most kSubFrames frames
-constexpr long long kSubFrames = 24576;
+int g_lstm_pdl = 1;               // b2t_set_option("lstm_pdl", 0/1)
+long long g_sub_frames = 24576;   // b2t_set_option("seanet_sub_frames", n)
 struct SubBatch { int c0, c1; long long frames; };
 std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* max_frames, int* max_clips) {
   std::vector<SubBatch> v;
@@ -474,7 +518,7 @@ std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* 
   int c = 0;
   while (c < n) {
     SubBatch s{c, c, 0};
-    while (s.c1 < n && (s.c1 == s.c0 || s.frames + frames_host[s.c1] <= kSubFrames)) { s.frames += frames_host[s.c1]; ++s.c1; }
+    while (s.c1 < n && (s.c1 == s.c0 || s.frames + frames_host[s.c1] <= g_sub_frames)) { s.frames += frames_host[s.c1]; ++s.c1; }
     if (s.frames > mf) mf = s.frames;
     if (s.c1 - s.c0 > mc) mc = s.c1 - s.c0;
     v.push_back(s);
@@ -485,6 +529,9 @@ std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* 
 }
 
 }  // namespace
+
+void b2t_seanet_set_sub_frames(int n) { if (n > 0) g_sub_frames = n; }
+void b2t_seanet_set_lstm_pdl(int on) { g_lstm_pdl = on != 0; }
 
 size_t b2t_seanet_tc_workspace_bytes(const b2t_acoustic_batch* b) {
   if (!b->frames_host) return 0;
@@ -507,13 +554,14 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
 #define RUN(call) do { int rc__ = (call); if (rc__ != B2T_OK) return rc__; } while (0)
 
   // ---- strided-conv front end, one sub-batch of clips at a time (levels 0-3 reuse the same buffers) ----
+  b2t_acoustic_mark(0, 1, st);
   for (const SubBatch& sb : subs) {
     const int ns = sb.c1 - sb.c0;
     long long Ml[5];
     for (int l = 0; l < 5; ++l) Ml[l] = (long long)kR[l] * sb.frames + (long long)kH[l] * ns;
     {
       const int M0 = (int)Ml[0];
-      seanet_conv0_kernel<<<(M0 + 63) / 64, 256, 0, st>>>(wave, b->wave_off, b->true_len, b->off[4], sb.c0, ns, M0,
+      seanet_conv0_kernel<<<(M0 + kConv0Rows - 1) / kConv0Rows, 256, 0, st>>>(wave, b->wave_off, b->true_len, b->off[4], sb.c0, ns, M0,
                                                             wt.conv0_w, wt.conv0_b, w.xh[0], w.xe[0]);
       B2T_LAUNCH_CHECK();
     }
@@ -547,6 +595,8 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
     }
   }
 
+  b2t_acoustic_mark(0, 0, st);
+  b2t_acoustic_mark(1, 1, st);
   // ---- LSTM: per step one GEMM [x_t | h_{t-1}] . [W_ih | W_hh]^T with the cell update in the epilogue ----
   std::vector<int> toff(b->t_max + 1, 0);
   for (int t = 0; t < b->t_max; ++t) toff[t + 1] = toff[t] + active_host[t];
@@ -564,10 +614,13 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
       const int na = active_host[t];
       if (na <= 0) break;
       e.t = t; e.toff_t = toff[t]; e.n_active = na;
-      RUN((launch_bn<256, LstmEpi>(mx, mh, mw, 8, t > 0 ? 8 : 0, toff[t], t > 0 ? toff[t - 1] : 0, na, 2048, e, st)));
+      RUN((launch_bn<256, LstmEpi>(mx, mh, mw, 8, t > 0 ? 8 : 0, toff[t], t > 0 ? toff[t - 1] : 0, na, 2048, e, st,
+                                   t > 0 ? g_lstm_pdl : 0)));
     }
   }
 
+  b2t_acoustic_mark(1, 0, st);
+  b2t_acoustic_mark(2, 1, st);
   // ---- ELU -> Conv(512 -> 128, k7) over the clip-major padded rows (halo 6) -> dense fp32 embeddings ----
   {
     CUtensorMap ma, mw;
@@ -579,6 +632,7 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
     e.bias = wt.final_b; e.out_f32 = emb ? emb : w.emb; e.ld_f32 = 128; e.r = 1; e.h_in = 6; e.h_out = 0;
     RUN(launch_conv(ma, mw, 7 * 512, (int)M, 128, e, st));
   }
+  b2t_acoustic_mark(2, 0, st);
 #undef RUN
   return B2T_OK;
 }

@@ -259,7 +259,7 @@ def main():
         batches = packing.bucket_by_rows(rows.tolist(), enc.max_rows_per_batch)
 
         def make_plan(ln, offs, rws):
-            return plan_acoustic(ln, offs, np.maximum(rws * 320, ln))
+            return plan_acoustic(ln, offs, np.maximum(rws * 320, ln), tiles=False)
     else:
         rows = np.array([packing.length_tokens(int(n), sr, TOKEN_RATE) for n in lengths])
         batches = packing.bucket_by_rows(rows.tolist(), ROW_BUDGET)
@@ -366,9 +366,15 @@ def main():
     # instrumented steps: CUDA-event time per kernel class
     import ctypes as C
     lib = L.load()
-    lib.b2t_profile_enable(0 if acoustic else 1)
+    lib.b2t_profile_enable(1)
     cls_ms = np.zeros(6)
     gemm_flops = 0.0
+    ac_ms = np.zeros(4)
+    for w, plan in (zip(dev_waves, plans) if acoustic else []):
+        enc.encode_plan(w, plan)
+        arr4 = (C.c_float * 4)()
+        L.check(lib.b2t_acoustic_profile_read(arr4), 'acoustic_profile_read')
+        ac_ms += np.array(list(arr4))
     for w, plan in ([] if acoustic else zip(dev_waves, plans)):
         enc.encode_plan(w, plan)
         arr = (C.c_float * 6)()
@@ -380,8 +386,9 @@ def main():
     peak_tf, peak_hbm, peak_src = measured_peaks()
     ach = gemm_flops / (cls_ms[2] / 1e3) / 1e12 if cls_ms[2] > 0 else 0.0
     if acoustic:
-        # 39.73 MFLOP per frame (encoder) + n_q * 2*1024*128 (RVQ); fp32 CUDA-core kernels this round
-        flops = float(rows.sum()) * (39.73e6 + enc.num_codebooks * 2 * 1024 * 128)
+        # 39.73 MFLOP per frame (encoder) + n_q * 2*1024*128 (RVQ)
+        frames = float(rows.sum())
+        flops = frames * (39.73e6 + enc.num_codebooks * 2 * 1024 * 128)
         ach = flops / (ms_res / 1e3) / 1e12
 
     total_audio_s = sum_over_ranks(audio_s)           # units all ranks processed per step
@@ -391,7 +398,7 @@ def main():
         line = {
             'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_res, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if acoustic else 'bf16', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': workload_config(args.workload, lengths), 'clocks': clocks,
             'e2e': {'value': e2e, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(d2h_bytes)},
@@ -404,8 +411,21 @@ def main():
                                               [float(v) for v in cls_ms])),
         }
         if acoustic:
-            line['roofline'].update({'kernel': 'whole acoustic step (fp32 SIMT conv / LSTM / RVQ kernels; tensor-core port pending)',
-                                     'bound': 'tensor', 'gemm_share_of_step': None})
+            # per phase (CUDA events inside the library, one instrumented step): algorithmic FLOPs of SURVEY 8d
+            # front end = 15 208 448 MAC/frame (18 convs minus the final one), LSTM 4 194 304, final conv 458 752
+            ph_flops = [2 * 15208448.0 - 2 * 458752.0, 2 * 4194304.0, 2 * 458752.0, enc.num_codebooks * 2.0 * 1024 * 128]
+            phases = {}
+            for nm, ms_p, fl in zip(['seanet_front_end', 'lstm', 'final_conv', 'rvq'], ac_ms, ph_flops):
+                phases[nm] = {'ms': float(ms_p), 'tflops_algorithmic': (frames * fl / (ms_p / 1e3) / 1e12) if ms_p > 0 else None}
+            # the strided-conv front end moves its intermediates through HBM: bytes the 13 kernels of a sub-batch read
+            # and write per frame (bf16, channels-last) = 389 376 B
+            if ac_ms[0] > 0:
+                phases['seanet_front_end']['hbm_gbps_moved'] = frames * 389376.0 / (ac_ms[0] / 1e3) / 1e9
+                phases['seanet_front_end']['hbm_peak_gbps'] = peak_hbm
+            line['roofline'].update({'kernel': 'whole acoustic step: seanet_conv0 + seanet_tc_kernel (tcgen05 conv/LSTM GEMMs) + '
+                                               'rvq_tc_kernel (tcgen05 bf16x3), SURVEY 8d FLOPs / step time',
+                                     'bound': 'tensor', 'gemm_share_of_step': None, 'phases': phases})
+            line['breakdown_ms_per_step'] = dict(zip(['seanet_front_end', 'lstm', 'final_conv', 'rvq'], [float(v) for v in ac_ms]))
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference_run_acoustic(3, 1) if acoustic else cpu_reference_run(lengths, steps=2, warmup=1)
             line['cpu_baseline'] = base

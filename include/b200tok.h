@@ -265,6 +265,10 @@ int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2
                         int n_q, int precision, void* workspace, size_t workspace_bytes, int16_t* codes,
                         float* emb_out, const int32_t* active_host, void* stream);
 
+/* With b2t_profile_enable(1): milliseconds b2t_acoustic_encode (B2T_PREC_BF16) spent since the last read in
+ * {strided-conv front end, LSTM, final conv, residual VQ}; synchronises.                                  */
+int b2t_acoustic_profile_read(float* ms4_host);
+
 #ifdef __cplusplus
 }
 #endif
