@@ -170,7 +170,184 @@ dwconv_ln_swish_kernel(const T* __restrict__ x, const float* __restrict__ w_dw,
   }
 }
 
+// ---- bf16 production kernel: rows staged once through a shared-memory ring by bulk async copies ----------------
+// One persistent CTA per SM owns a CONTIGUOUS range of 64-row work items (clip order), so consecutive items of a
+// clip continue in the ring and every input row is fetched from HBM once (30 extra rows only where a chain starts).
+// Thread 0 issues cp.async.bulk (global -> shared, mbarrier complete_tx) for the 16 rows the NEXT sub-tile needs
+// while all 512 threads run the 31-tap packed-FMA loop of the current one out of shared memory; the load latency the
+// register-only kernel exposed is gone and the kernel runs at the fp32 FMA rate (31 FMA per output element).
+constexpr int kRing = 64;
+constexpr int kRowBytes = kC * 2;
+constexpr int kRingSmem = kRing * kRowBytes + 64;
+
+B2T_DEVICE void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+B2T_DEVICE void mbar_init_(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+B2T_DEVICE void mbar_expect_(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+B2T_DEVICE void mbar_wait_(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+dwconv_ring_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w_dw,
+                   const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                   const int32_t* __restrict__ row_off, const int32_t* __restrict__ ctile_clip,
+                   const int32_t* __restrict__ ctile_t0, int n_items, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ float s_red[16][kTT];
+  __shared__ float s_stat[kTT];
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t bar_pro = ring_s + kRing * kRowBytes, bar_in0 = bar_pro + 8, bar_in1 = bar_pro + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = tid * 2;
+  if (tid == 0) {
+    mbar_init_(bar_pro, 1); mbar_init_(bar_in0, 1); mbar_init_(bar_in1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  float2 wv[kK];
+#pragma unroll
+  for (int k = 0; k < kK; ++k) {
+    const float2 wk = __ldg(reinterpret_cast<const float2*>(w_dw + (size_t)k * kC + c));
+    wv[k] = make_float2(bf16_round(wk.x), bf16_round(wk.y));
+  }
+  const float g0 = __ldg(ln_w + c), g1 = __ldg(ln_w + c + 1);
+  const float b0 = __ldg(ln_b + c), b1 = __ldg(ln_b + c + 1);
+  __syncthreads();
+
+  const int per = (n_items + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(n_items, i0 + per);
+  int prev_clip = -1, prev_t0 = -1;
+  uint32_t n_pro = 0, n_issued = 0, n_waited = 0;      // barrier use counts (identical in every thread)
+#pragma unroll 1
+  for (int item = i0; item < i1; ++item) {
+    const int clip = ctile_clip[item], tile0 = ctile_t0[item];
+    const int r0 = row_off[clip], rows = row_off[clip + 1] - r0;
+    const bool chained = (clip == prev_clip && tile0 == prev_t0 + kSub * kTT);
+    const bool next_chained = (item + 1 < i1) && ctile_clip[item + 1] == clip;
+    prev_clip = clip; prev_t0 = tile0;
+    if (!chained) {
+      __syncthreads();                                   // nobody still reads the ring
+      if (tid == 0) {
+        const int first = max(0, tile0 - (kK - 1)), last = min(rows, tile0 + kTT);
+        const uint32_t bytes = (uint32_t)(last - first) * kRowBytes;
+        mbar_expect_(bar_pro, bytes);
+        // ring slot of clip row t: (t - tile0 + 32) & 63; rows first..last-1 are contiguous in memory and in the ring
+        bulk_g2s(ring_s + (uint32_t)((first - tile0 + 32) & (kRing - 1)) * kRowBytes, x + (size_t)(r0 + first) * kC, bytes, bar_pro);
+      }
+      if (tile0 == 0) {
+        // rows -30..-1 of the clip are the causal zero padding: slots 2..31 of the ring
+        uint4* z = reinterpret_cast<uint4*>(ring + 2 * kRowBytes);
+        for (int i = tid; i < 30 * kRowBytes / 16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+      }
+      mbar_wait_(bar_pro, n_pro & 1u);
+      ++n_pro;
+    }
+#pragma unroll 1
+    for (int sub = 0; sub < kSub; ++sub) {
+      const int T = tile0 + sub * kTT;
+      if (T >= rows) break;
+      // prefetch the 16 rows the next sub-tile adds (also across a chained item boundary)
+      const bool want_next = (T + kTT < rows) && (sub + 1 < kSub || next_chained);
+      if (want_next) {
+        if (tid == 0) {
+          const int n = min(kTT, rows - (T + kTT));
+          const uint32_t bar = (n_issued & 1u) ? bar_in1 : bar_in0;
+          mbar_expect_(bar, (uint32_t)n * kRowBytes);
+          bulk_g2s(ring_s + (uint32_t)((sub * kTT + kTT + 32) & (kRing - 1)) * kRowBytes, x + (size_t)(r0 + T + kTT) * kC,
+                   (uint32_t)n * kRowBytes, bar);
+        }
+      }
+      if (sub > 0 || chained) {                          // rows T..T+15 arrived with the chunk issued one step ago
+        mbar_wait_((n_waited & 1u) ? bar_in1 : bar_in0, (n_waited >> 1) & 1u);
+        ++n_waited;
+      }
+      if (want_next) ++n_issued;
+
+      float2 av[kTT];
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) av[t] = make_float2(0.f, 0.f);
+      // input row (T - 30 + j), j = 0..45, contributes to output t with tap k = j - t  (0 <= k <= 30)
+#pragma unroll
+      for (int j = 0; j < kTT + kK - 1; ++j) {
+        const uint32_t slot = (uint32_t)((sub * kTT + 2 + j) & (kRing - 1));
+        const uint32_t raw = *reinterpret_cast<const uint32_t*>(ring + slot * kRowBytes + tid * 4);
+        const float2 v = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xFFFF0000u));   // bf16x2 -> fp32
+#pragma unroll
+        for (int t = 0; t < kTT; ++t) {
+          const int k = j - t;
+          if (k >= 0 && k < kK) av[t] = ffma2(wv[k], v, av[t]);
+        }
+      }
+      // LayerNorm over channels, all 16 rows at once (two-pass), then swish
+      float a0[kTT], a1[kTT], part[kTT];
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) {
+        a0[t] = bf16_round(av[t].x);
+        a1[t] = bf16_round(av[t].y);
+        part[t] = a0[t] + a1[t];
+      }
+      const int ridx = warp_sum16_index(lane);
+      float tot = warp_sum16(part, lane);
+      if ((lane & 1) == 0) s_red[warp][ridx] = tot;
+      __syncthreads();
+      if (tid < kTT) {
+        float sm = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < 16; ++wi) sm += s_red[wi][tid];
+        s_stat[tid] = sm * (1.0f / kC);
+      }
+      __syncthreads();
+      float mu[kTT];
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) {
+        mu[t] = s_stat[t];
+        const float d0 = a0[t] - mu[t], d1 = a1[t] - mu[t];
+        part[t] = d0 * d0 + d1 * d1;
+      }
+      tot = warp_sum16(part, lane);
+      __syncthreads();
+      if ((lane & 1) == 0) s_red[warp][ridx] = tot;
+      __syncthreads();
+      if (tid < kTT) {
+        float sm = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < 16; ++wi) sm += s_red[wi][tid];
+        s_stat[tid] = rsqrtf(sm * (1.0f / kC) + 1e-5f);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) {
+        if (T + t < rows) {
+          const float rs = s_stat[t];
+          const float y0 = fmaf(a0[t] - mu[t], rs * g0, b0), y1 = fmaf(a1[t] - mu[t], rs * g1, b1);
+          // swish(y) = y * sigmoid(y) = 0.5 y (1 + tanh(0.5 y)): one MUFU per element; the result is rounded to bf16
+          float t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * y0));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * y1));
+          const float h0 = 0.5f * y0, h1 = 0.5f * y1;
+          st2<__nv_bfloat16>(out + (size_t)(r0 + T + t) * kC + c, fmaf(h0, t0, h0), fmaf(h1, t1, h1));
+        }
+      }
+      __syncthreads();   // s_stat / s_red and the ring rows this sub-tile read may be reused from here on
+    }
+  }
+}
+
 }  // namespace
+
+bool g_dwconv_ring = true;   // b2t_set_option("dwconv_ring", 0/1)
 
 extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float* ln_weight,
                                    const float* ln_bias, const b2t_batch* b, void* out,
@@ -180,7 +357,14 @@ extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float
   if (rc != B2T_OK) return rc;
   if (b->n_ctiles <= 0) return B2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == B2T_PREC_BF16)
+  if (precision == B2T_PREC_BF16 && g_dwconv_ring) {
+    static bool cfg = false;
+    if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(dwconv_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem)); cfg = true; }
+    int grid = b2t_num_sms();
+    if (b->n_ctiles < grid) grid = b->n_ctiles;
+    dwconv_ring_kernel<<<grid, kThreads, kRingSmem, st>>>((const __nv_bfloat16*)x, w_dw, ln_weight, ln_bias, b->row_off,
+                                                         b->ctile_clip, b->ctile_t0, b->n_ctiles, (__nv_bfloat16*)out);
+  } else if (precision == B2T_PREC_BF16)
     dwconv_ln_swish_kernel<__nv_bfloat16, true><<<b->n_ctiles, kThreads, 0, st>>>(
         (const __nv_bfloat16*)x, w_dw, ln_weight, ln_bias, b->row_off, b->ctile_clip, b->ctile_t0, (__nv_bfloat16*)out);
   else
