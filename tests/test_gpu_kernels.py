@@ -315,6 +315,29 @@ def test_vq_argmin_near_ties_and_layernorm(cuda_device, impl):
     assert (o.cpu().long()[~tie3] == idx3[~tie3]).float().mean() > 0.995
 
 
+def test_vq_argmin_baseline_c5_full_size(cuda_device):
+    """BASELINE configs[4] at full size (1M frames x 1024-d, K = 2048, SURVEY 8d seeds): the tensor fast pass +
+    exact finalize against the fp64 oracle on a random sample of rows and against the CUDA-core exact kernel on a
+    contiguous block; the size-independent property 'a centroid quantises to itself' on rows overwritten with centroids."""
+    M, D, K = 1_000_000, 1024, 2048
+    x = torch.randn(M, D, generator=torch.Generator().manual_seed(3))
+    cb = torch.randn(K, D, generator=torch.Generator().manual_seed(4))
+    x[-K:] = cb                                             # every centroid appears once as a frame
+    xd, cbd = x.to(cuda_device), cb.to(cuda_device)
+    stats = {}
+    o16, o32 = ops.vq_argmin(xd, cbd, impl=L.IMPL_TENSOR, stats=stats)
+    torch.cuda.synchronize()
+    got = o32.cpu().long()
+    assert torch.equal(got[-K:], torch.arange(K))
+    sample = torch.randperm(M - K, generator=torch.Generator().manual_seed(5))[:1024]
+    idx, tie = quantize.nearest_centroid(x[sample], cb)
+    assert torch.equal(got[sample][~tie], idx[~tie])
+    _, s32 = ops.vq_argmin(xd[:32768].contiguous(), cbd, impl=L.IMPL_SIMT)
+    assert torch.equal(s32.cpu().long(), got[:32768])
+    assert torch.equal(o16.cpu().long(), got)
+    assert stats['max_rel_err'] < 6.103515625e-5 / 4, stats
+
+
 def test_gemm_multicast_clusters_bit_identical(cuda_device):
     """2-CTA clusters with TMA multicast change data movement only: results equal the 1-CTA kernel bitwise."""
     lib = L.load()
