@@ -406,6 +406,252 @@ seanet_conv0_kernel(const float* __restrict__ wave, const int64_t* __restrict__ 
   }
 }
 
+// ---- level 0 fused: waveform -> conv0 -> ELU -> k3 -> ELU -> [shortcut | k1] -> ELU, one kernel --------------------
+// The 24 kHz level moves 45 % of the front end's bytes when run as separate kernels (x, ELU x, ELU h, y round-trip
+// HBM at 64-96 B per row each).  Here the only HBM traffic is 4 B of waveform in and 64 B of ELU(y) out per row:
+//   builder warps (8)  conv0 on CUDA cores straight from the waveform for the three tap times of every row (reflect
+//                      padding by index), written as the two swizzled UMMA operand tiles  A1 = [ELU x(t-2) | ELU x(t-1) |
+//                      ELU x(t)] (K = 96) and A2 = [x(t) | . ] (K = 48) of a double-buffered pair;
+//   MMA warp           D1 = A1 . W3^T (N = 16), later D2 = A2 . [Wsc | Wk1]^T (N = 32), accumulators in TMEM;
+//   epilogue warps (4) E1: h = ELU(D1 + b3) -> bf16 into columns 32..47 of A2 (shared memory, never HBM);
+//                      E2: ELU(D2 + b) -> global (+ halo mirror).  E1 of tile n+1 runs before E2 of tile n so the
+//                      MMA round trip is hidden.
+constexpr int kL0Builders = 8;
+constexpr int kL0Threads = 32 * (kL0Builders + 4 + 1);
+constexpr int kL0A1 = 2 * kBM * 128;          // two 64-wide k-blocks, 32 KB
+constexpr int kL0A2 = kBM * 128;              // one k-block, 16 KB
+constexpr int kL0Smem = 2 * (kL0A1 + kL0A2) + 4096 + 4096 + 1024 + 512 + 1024;
+
+struct L0Params {
+  const float* wave; const int64_t* wave_off; const int32_t* true_len; const int32_t* off4;
+  const float* w0; const float* b0;           // conv0 fp32 [32][16], [32]
+  const float* b3; const float* bres;         // biases of k3 (16) and of shortcut + k1 (32)
+  __nv_bfloat16* ye;                          // [P_0 rows, 32] ELU(y) with mirrored halo (H = 2)
+  int c0, nsub, M;
+};
+
+__global__ void __launch_bounds__(kL0Threads, 2)
+seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_constant__ CUtensorMap map_wres, L0Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+  // layout: A1[0] A1[1] A2[0] A2[1] W3(4 KB) Wres(4 KB) w0(1 KB) barriers
+  const uint32_t oA1 = 0, oA2 = 2 * kL0A1, oW3 = oA2 + 2 * kL0A2, oWr = oW3 + 4096, oW0 = oWr + 4096, oBar = oW0 + 1024;
+  const uint32_t bars = base + oBar;
+  auto a1_full = [&](int b) { return bars + 8u * b; };
+  auto a2_full = [&](int b) { return bars + 8u * (2 + b); };
+  auto a_empty = [&](int b) { return bars + 8u * (4 + b); };
+  auto d1_full = [&](int b) { return bars + 8u * (6 + b); };
+  auto d1_empty = [&](int b) { return bars + 8u * (8 + b); };
+  auto d2_full = [&](int b) { return bars + 8u * (10 + b); };
+  auto d2_empty = [&](int b) { return bars + 8u * (12 + b); };
+  const uint32_t w_bar = bars + 8u * 14, tmem_slot = bars + 8u * 15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_total = (p.M + kBM - 1) / kBM;
+  const int my_tiles = blockIdx.x < n_tiles_total ? (n_tiles_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(a1_full(b), kL0Builders); mbar_init(a2_full(b), 4); mbar_init(a_empty(b), 1);
+      mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 4); mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 4);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  // zero the operand buffers once (K padding columns are never written again) and stage the conv0 weights
+  for (int i = threadIdx.x; i < (2 * (kL0A1 + kL0A2)) / 16; i += kL0Threads) reinterpret_cast<uint4*>(bp)[i] = make_uint4(0u, 0u, 0u, 0u);
+  float* sw0 = reinterpret_cast<float*>(bp + oW0);
+  for (int i = threadIdx.x; i < 256; i += kL0Threads) {
+    const int c = i >> 3, j = i & 7;
+    sw0[i] = j < 7 ? __ldg(p.w0 + c * 16 + j) : __ldg(p.b0 + c);
+  }
+  float* sb3 = reinterpret_cast<float*>(bp + oBar + 128);      // 16 + 32 biases behind the barriers
+  if (threadIdx.x < 16) sb3[threadIdx.x] = __ldg(p.b3 + threadIdx.x);
+  else if (threadIdx.x < 48) sb3[threadIdx.x] = __ldg(p.bres + threadIdx.x - 16);
+  if (warp == kL0Builders + 4) tmem_alloc(tmem_slot, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(bp + oBar + 8 * 15);
+
+  ConvEpi q{};
+  q.off4 = p.off4; q.c0 = p.c0; q.nsub = p.nsub; q.r = 320; q.h_in = 2;
+
+  if (warp < kL0Builders) {
+    // ===== builders: thread pair per row; half = channels [16*half, 16*half + 16) =====
+    const int i = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const uint32_t row_off = (uint32_t)((i >> 3) * 1024 + (i & 7) * 128);
+    for (int n = 0; n < my_tiles; ++n) {
+      const int buf = n & 1;
+      const int m = ((int)blockIdx.x + n * (int)gridDim.x) * kBM + i;
+      const RowInfo ri = map_row(q, m, p.M);
+      mbar_wait(a_empty(buf), (uint32_t)(((n >> 1) & 1) ^ 1));
+      if (ri.valid) {
+        const float* x = p.wave + __ldg(p.wave_off + ri.clip);
+        const int tl = __ldg(p.true_len + ri.clip);
+        uint8_t* a1 = bp + oA1 + buf * kL0A1;
+        uint8_t* a2 = bp + oA2 + buf * kL0A2;
+        // conv0 at time u for this thread's 16 channels: raw bf16 and ELU bf16 (2 x 16-byte chunks each)
+        auto conv0_at = [&](int u, uint32_t (&raw)[8], uint32_t (&el)[8]) {
+          float sj[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            int idx = u + j - 6;
+            idx = idx < 0 ? -idx : idx;                       // reflect padding of conv0 (on the waveform)
+            sj[j] = idx < tl ? __ldg(x + idx) : 0.f;
+          }
+#pragma unroll
+          for (int cc = 0; cc < 16; cc += 2) {
+            float v2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float4 wa = *reinterpret_cast<const float4*>(sw0 + (half * 16 + cc + e) * 8);
+              const float4 wb = *reinterpret_cast<const float4*>(sw0 + (half * 16 + cc + e) * 8 + 4);
+              float a = wb.w;
+              a = fmaf(wa.x, sj[0], a); a = fmaf(wa.y, sj[1], a); a = fmaf(wa.z, sj[2], a); a = fmaf(wa.w, sj[3], a);
+              a = fmaf(wb.x, sj[4], a); a = fmaf(wb.y, sj[5], a); a = fmaf(wb.z, sj[6], a);
+              v2[e] = a;
+            }
+            raw[cc >> 1] = pack2_bf16(v2[0], v2[1]);
+            el[cc >> 1] = pack2_bf16(elu_fast(v2[0]), elu_fast(v2[1]));
+          }
+        };
+        // ELU x(time) lands in tile row `row`, tap `tap`: chunks 4*tap + 2*half (+1) of that row
+        auto put_tap = [&](int row, int tap, const uint32_t (&el)[8]) {
+          const uint32_t ro = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int chunk = 4 * tap + 2 * half + h2;
+            const uint32_t off = (uint32_t)(chunk >> 3) * (kBM * 128) + ro + (uint32_t)(((chunk & 7) ^ (row & 7)) * 16);
+            *reinterpret_cast<uint4*>(a1 + off) = make_uint4(el[4 * h2], el[4 * h2 + 1], el[4 * h2 + 2], el[4 * h2 + 3]);
+          }
+        };
+        uint32_t raw[8], el[8];
+        conv0_at(ri.t, raw, el);
+        // x(t) is tap 2 of row t, tap 1 of row t+1 and tap 0 of row t+2: computed once, written three times
+        put_tap(i, 2, el);
+        if (i + 1 < kBM && ri.t + 1 < ri.len) put_tap(i + 1, 1, el);
+        if (i + 2 < kBM && ri.t + 2 < ri.len) put_tap(i + 2, 0, el);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int chunk = 2 * half + h2;
+          *reinterpret_cast<uint4*>(a2 + row_off + (uint32_t)((chunk ^ (i & 7)) * 16)) =
+              make_uint4(raw[4 * h2], raw[4 * h2 + 1], raw[4 * h2 + 2], raw[4 * h2 + 3]);
+        }
+        // taps whose producer row lies in the previous tile or before the clip start (reflect: x(-d) = x(d))
+#pragma unroll
+        for (int d = 1; d <= 2; ++d) {
+          if (i < d || ri.t < d) {
+            const int u = ri.t - d;
+            conv0_at(u < 0 ? -u : u, raw, el);
+            put_tap(i, 2 - d, el);
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_full(buf));
+    }
+  } else if (warp < kL0Builders + 4) {
+    // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int i = quad * 32 + lane;
+    const uint32_t row_off = (uint32_t)((i >> 3) * 1024 + (i & 7) * 128);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    auto e1 = [&](int n) {
+      const int buf = n & 1;
+      mbar_wait(d1_full(buf), (uint32_t)((n >> 1) & 1));
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32_x16_nowait(lane_addr + (uint32_t)(buf * 16), r);
+      tmem_ld_wait();
+      tc_fence_before();
+      uint32_t pk[8];
+#pragma unroll
+      for (int c = 0; c < 16; c += 2)
+        pk[c >> 1] = pack2_bf16(elu_fast(__uint_as_float(r[c]) + sb3[c]), elu_fast(__uint_as_float(r[c + 1]) + sb3[c + 1]));
+      uint8_t* a2 = bp + oA2 + buf * kL0A2;
+      *reinterpret_cast<uint4*>(a2 + row_off + (uint32_t)((4 ^ (i & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(a2 + row_off + (uint32_t)((5 ^ (i & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(a2_full(buf)); mbar_arrive(d1_empty(buf)); }
+    };
+    auto e2 = [&](int n) {
+      const int buf = n & 1;
+      const int m = ((int)blockIdx.x + n * (int)gridDim.x) * kBM + i;
+      const RowInfo ri = map_row(q, m, p.M);
+      mbar_wait(d2_full(buf), (uint32_t)((n >> 1) & 1));
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32_nowait(lane_addr + (uint32_t)(32 + buf * 32), r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty(buf));
+      if (ri.valid) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2)
+          pk[c >> 1] = pack2_bf16(elu_fast(__uint_as_float(r[c]) + sb3[16 + c]), elu_fast(__uint_as_float(r[c + 1]) + sb3[16 + c + 1]));
+        __nv_bfloat16* o = p.ye + (size_t)m * 32;            // same row space in and out (level 0, H = 2)
+        store_bf16<32>(o, pk);
+        if (ri.t >= 1 && ri.t <= 2) store_bf16<32>(o - 2 * ri.t * 32, pk);
+      }
+    };
+    if (my_tiles > 0) e1(0);
+    for (int n = 0; n < my_tiles; ++n) {
+      if (n + 1 < my_tiles) e1(n + 1);
+      e2(n);
+    }
+  } else {
+    // ===== MMA warp =====
+    if (lane == 0) {
+      const uint32_t sW3 = base + oW3, sWr = base + oWr;
+      mbar_expect_tx(w_bar, 4096 + 4096);
+      tma_load_2d(sW3, &map_w3, w_bar, 0, 0);
+      tma_load_2d(sW3 + 2048, &map_w3, w_bar, 64, 0);
+      tma_load_2d(sWr, &map_wres, w_bar, 0, 0);
+      mbar_wait(w_bar, 0);
+      constexpr uint32_t idesc1 = make_idesc(kBM, 16), idesc2 = make_idesc(kBM, 32);
+      auto mma2 = [&](int k) {
+        const int buf = k & 1;
+        mbar_wait(a2_full(buf), (uint32_t)((k >> 1) & 1));
+        mbar_wait(d2_empty(buf), (uint32_t)(((k >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(base + oA2 + buf * kL0A2), db = make_smem_desc(sWr);
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+          umma_bf16(tmem_base + (uint32_t)(32 + buf * 32), da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc2, kk ? 1u : 0u);
+        umma_commit(d2_full(buf));
+        umma_commit(a_empty(buf));
+      };
+      for (int n = 0; n < my_tiles; ++n) {
+        const int buf = n & 1;
+        mbar_wait(a1_full(buf), (uint32_t)((n >> 1) & 1));
+        mbar_wait(d1_empty(buf), (uint32_t)(((n >> 1) & 1) ^ 1));
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t da = make_smem_desc(base + oA1 + buf * kL0A1 + kb * (kBM * 128));
+          const uint64_t db = make_smem_desc(sW3 + kb * 2048);
+#pragma unroll
+          for (int kk = 0; kk < (kb ? 2 : 4); ++kk)            // K = 96: the second k-block holds 32 real columns
+            umma_bf16(tmem_base + (uint32_t)(buf * 16), da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc1, (kb | kk) ? 1u : 0u);
+        }
+        umma_commit(d1_full(buf));
+        if (n > 0) mma2(n - 1);
+      }
+      if (my_tiles > 0) mma2(my_tiles - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kL0Builders + 4) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
 // ---- host ----------------------------------------------------------------------------------------
 int make_map_k(CUtensorMap* map, const void* ptr, long long rows, int K, long long ld_elems, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -509,6 +755,7 @@ TcWs tc_carve(void* base, long long sub_frames, int sub_clips, long long total4,
 }
 
 // greedy split of the clip list into front-end sub-batches of at most kSubFrames frames
+int g_l0_fused = 1;               // b2t_set_option("seanet_l0_fused", 0/1)
 int g_lstm_pdl = 1;               // b2t_set_option("lstm_pdl", 0/1)
 long long g_sub_frames = 24576;   // b2t_set_option("seanet_sub_frames", n)
 struct SubBatch { int c0, c1; long long frames; };
@@ -532,6 +779,7 @@ std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* 
 
 void b2t_seanet_set_sub_frames(int n) { if (n > 0) g_sub_frames = n; }
 void b2t_seanet_set_lstm_pdl(int on) { g_lstm_pdl = on != 0; }
+void b2t_seanet_set_l0_fused(int on) { g_l0_fused = on != 0; }
 
 size_t b2t_seanet_tc_workspace_bytes(const b2t_acoustic_batch* b) {
   if (!b->frames_host) return 0;
@@ -559,7 +807,20 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
     const int ns = sb.c1 - sb.c0;
     long long Ml[5];
     for (int l = 0; l < 5; ++l) Ml[l] = (long long)kR[l] * sb.frames + (long long)kH[l] * ns;
-    {
+    if (g_l0_fused) {
+      const int M0 = (int)Ml[0];
+      CUtensorMap m3, mr;
+      RUN(make_map_k(&m3, wt.k3_w[0], 16, 128, 128, 16));
+      RUN(make_map_k(&mr, wt.res_w[0], 32, 64, 64, 32));
+      L0Params lp{wave, b->wave_off, b->true_len, b->off[4], wt.conv0_w, wt.conv0_b, wt.k3_b[0], wt.res_b[0], w.ye[0], sb.c0, ns, M0};
+      static bool cfg = false;
+      if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(seanet_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem)); cfg = true; }
+      int grid = 2 * b2t_num_sms();
+      const int tiles0 = (M0 + kBM - 1) / kBM;
+      if (tiles0 < grid) grid = tiles0;
+      seanet_l0_kernel<<<grid, kL0Threads, kL0Smem, st>>>(m3, mr, lp);
+      B2T_LAUNCH_CHECK();
+    } else {
       const int M0 = (int)Ml[0];
       seanet_conv0_kernel<<<(M0 + kConv0Rows - 1) / kConv0Rows, 256, 0, st>>>(wave, b->wave_off, b->true_len, b->off[4], sb.c0, ns, M0,
                                                             wt.conv0_w, wt.conv0_b, w.xh[0], w.xe[0]);
@@ -570,7 +831,9 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
       CUtensorMap ma, mw;
       ConvEpi e{};
       e.off4 = b->off[4]; e.rank = b->rank; e.toff = b->toff; e.c0 = sb.c0; e.nsub = ns; e.c0_out = sb.c0;
+      const bool fused0 = (l == 0 && g_l0_fused);        // level 0: conv0 + residual block ran as one kernel
       // (1) ELU -> Conv(C -> C/2, k3): window of row m = rows m-2 .. m of xe (3C contiguous elements)
+      if (!fused0) {
       RUN(make_map_k(&ma, w.xe[l] - 2 * C, M, 3 * C, C, kBM));
       RUN(make_map_k(&mw, wt.k3_w[l], C / 2, wt.k3_kpad[l], wt.k3_kpad[l], C / 2));
       e.bias = wt.k3_b[l]; e.out_raw = nullptr; e.out_f32 = nullptr;
@@ -581,6 +844,8 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
       RUN(make_map_k(&mw, wt.res_w[l], C, wt.res_kpad[l], wt.res_kpad[l], C > 256 ? 256 : C));
       e.bias = wt.res_b[l]; e.out_elu = w.ye[l]; e.ld_elu = C; e.mirror = 1;
       RUN(launch_conv(ma, mw, C * 3 / 2, M, C, e, st));
+      }
+      e.out_raw = nullptr; e.out_f32 = nullptr; e.tm_out = 0;
       // (3) Conv(C -> 2C, k = 2s, stride s): super-rows of s input rows; window of output row m' = super-rows m'-1, m'
       const int Mo = (int)(Ml[l] / s);        // = R[l+1]*frames + 1*ns  (one halo super-row per clip)
       RUN(make_map_k(&ma, w.ye[l] - s * C, Mo, 2 * s * C, (long long)s * C, kBM));

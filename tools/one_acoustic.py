@@ -6,6 +6,8 @@ from audiotoken_b200.acoustic import AcousticEncoder, plan_acoustic
 B = int(os.environ.get('B', 16)); SEC = float(os.environ.get('SEC', 20)); PREC = os.environ.get('PREC', 'fp32')
 kw = {} if PREC == 'fp32' else {'precision': PREC}
 enc = AcousticEncoder(device='cuda:0', **kw)
+if os.environ.get('L0F'):
+    enc.lib.b2t_set_option(b'seanet_l0_fused', int(os.environ['L0F']))
 if os.environ.get('PDL'):
     enc.lib.b2t_set_option(b'lstm_pdl', int(os.environ['PDL']))
 if os.environ.get('SUB'):
