@@ -126,8 +126,13 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
         try:
             if not path.lower().endswith(AUDIO_EXTS):
                 raise NotImplementedError(f'unsupported extension: {path}')
-            wave = aio.read_audio(path, sample_rate)
-            return list(aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size))
+            chunks = aio.read_audio_chunks(path, sample_rate, chunk_size, device=getattr(encoder, 'device', None))
+            segs_ = []
+            for ci, wave in enumerate(chunks):                 # one segment per streamed chunk (datasets.py:88-105)
+                for s in aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size):
+                    s.chunk_index = ci
+                    segs_.append(s)
+            return segs_
         except Exception as e:  # noqa: BLE001  (reference logs and continues, datasets.py:136-137)
             return e
 

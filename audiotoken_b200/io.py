@@ -66,12 +66,18 @@ def convert_audio(audio: torch.Tensor, sample_rate: int, target_sample_rate: int
     return audio
 
 
-def read_audio(path, model_sample_rate: int) -> torch.Tensor:
-    """WAV file -> fp32 [1, L] in [-1, 1] at `model_sample_rate` (reference utils.py:47-68)."""
+def read_audio(path, model_sample_rate: int, device=None) -> torch.Tensor:
+    """WAV file -> fp32 [1, L] in [-1, 1] at `model_sample_rate` (reference utils.py:47-68).
+    With a CUDA `device`, PCM decode + mono mix-down + resampling run on the GPU (audiotoken_b200/ingest.py) and the
+    result stays there; otherwise the host path below (torchaudio, as the reference) is used."""
     if not str(path).lower().endswith('.wav'):
         raise NotImplementedError(f'{path}: only .wav can be decoded offline (no ffmpeg/torchcodec in this image)')
     from scipy.io import wavfile
     sr, data = wavfile.read(str(path))
+    if device is not None and torch.device(device).type == 'cuda' and data.dtype in (np.int16, np.float32):
+        from . import ingest
+        raw = torch.from_numpy(np.ascontiguousarray(data).reshape(data.shape[0], -1)).t()     # [C, L] view of [L, C]
+        return ingest.convert_audio(raw, int(sr), model_sample_rate, device)
     if data.dtype == np.int16:
         x = data.astype(np.float32) / 32768.0
     elif data.dtype == np.int32:
@@ -87,6 +93,41 @@ def read_audio(path, model_sample_rate: int) -> torch.Tensor:
     audio = torch.from_numpy(np.ascontiguousarray(x))
     assert audio.dim() == 2, f"Audio needs to be 2D array, provided {audio.dim()}D for {path}"
     return convert_audio(audio, int(sr), model_sample_rate)
+
+
+def read_audio_chunks(path, model_sample_rate: int, chunk_size: int, device=None) -> List[torch.Tensor]:
+    """The reference's batch reader (utils.py:71-101): the file is streamed in chunks of `chunk_size` seconds AT ITS
+    OWN sample rate, every chunk must be mono and is resampled on its own with torchaudio's Resample — so a file
+    whose rate differs from the model's has filter edges at every chunk boundary.  Returns the resampled chunks
+    (fp32 [1, L_i]); on a CUDA `device` decode + resampling run on the GPU and the chunks stay there."""
+    if not str(path).lower().endswith('.wav'):
+        raise NotImplementedError(f'{path}: only .wav can be decoded offline (no ffmpeg/torchcodec in this image)')
+    from scipy.io import wavfile
+    sr, data = wavfile.read(str(path))
+    sr = int(sr)
+    if data.ndim == 2 and data.shape[1] != 1:
+        raise AssertionError(f'Audio needs to be mono, provided {data.shape[1]} channels for {path}')
+    on_gpu = device is not None and torch.device(device).type == 'cuda' and data.dtype in (np.int16, np.float32)
+    if on_gpu:
+        from . import ingest
+        raw = torch.from_numpy(np.ascontiguousarray(data).reshape(1, -1)).to(device, non_blocking=True)
+    else:
+        if data.dtype == np.int16:
+            x = data.astype(np.float32) / 32768.0
+        elif data.dtype == np.int32:
+            x = data.astype(np.float32) / 2147483648.0
+        elif data.dtype == np.uint8:
+            x = (data.astype(np.float32) - 128.0) / 128.0
+        else:
+            x = data.astype(np.float32)
+        raw = torch.from_numpy(np.ascontiguousarray(x).reshape(1, -1))
+    step = int(chunk_size * sr)
+    out = []
+    for a in range(0, raw.shape[1], step):
+        piece = raw[:, a:a + step]
+        out.append(ingest.convert_audio(piece, sr, model_sample_rate, device) if on_gpu
+                   else convert_audio(piece, sr, model_sample_rate))
+    return out
 
 
 def write_wav(path, wave: torch.Tensor, sample_rate: int) -> None:

@@ -265,6 +265,16 @@ int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2
                         int n_q, int precision, void* workspace, size_t workspace_bytes, int16_t* codes,
                         float* emb_out, const int32_t* active_host, void* stream);
 
+/* ---- ingest (reference audiotoken/utils.py:26-44 convert_audio, :98-99) ---------------------------------
+ * PCM16 (/32768) or fp32 decode, mono mix-down (mean of 2 channels) and torchaudio-style sinc resampling in one
+ * kernel.  Sample (c, t) of the input lives at in[t*t_stride + c*ch_stride].  (orig, new) are the gcd-reduced
+ * rates; output sample n*new + i = sum_m taps[i][m] * x[n*orig - width + start[i] + m] (zero outside [0, in_len)),
+ * m < count[i]; taps fp32 [new, max_taps] are the non-zero support of torchaudio's phase filters
+ * (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99).  out_len = ceil(new*in_len/orig).            */
+int b2t_ingest_resample(const void* in, int in_is_int16, long long in_len, int channels, long long ch_stride,
+                        long long t_stride, const float* taps, const int32_t* start, const int32_t* count,
+                        int max_taps, int orig, int new_, int width, float* out, long long out_len, void* stream);
+
 /* With b2t_profile_enable(1): milliseconds b2t_acoustic_encode (B2T_PREC_BF16) spent since the last read in
  * {strided-conv front end, LSTM, final conv, residual VQ}; synchronises.                                  */
 int b2t_acoustic_profile_read(float* ms4_host);

@@ -126,3 +126,23 @@ def test_seanet_oracle_matches_encodec_standin(golden_dir):
         assert agree >= 0.995, (tag, agree)
         ref32 = seanet.rvq_codes_reference_fp32(emb, sd, 16).transpose(0, 1)
         assert float((ref32 == codes).float().mean()) >= 0.995
+
+
+# ------------------------------------------------------------------------------ ingest (resampling)
+def test_resample_oracle_matches_torchaudio_goldens(golden_dir):
+    """oracle/resample.py against outputs of the reference's convert_audio (torchaudio.transforms.Resample defaults):
+    mono / stereo, down- and up-sampling, equal rates."""
+    from oracle import resample
+    g = np.load(os.path.join(golden_dir, 'resample.npz'))
+    k = 0
+    while f'case{k}_meta' in g.files:
+        sr, tgt, ch, n = (int(v) for v in g[f'case{k}_meta'])
+        y = resample.convert_audio(g[f'case{k}_in'], sr, tgt)
+        ref = g[f'case{k}_out']
+        assert y.shape == ref.shape, (k, y.shape, ref.shape)
+        assert float(np.abs(y - ref).max()) < 2e-5, k          # fp32 summation order of a <= 475-tap filter
+        k += 1
+    assert k >= 7
+    # published structure of the filter bank: gcd-reduced rates, 2*width + orig taps per phase
+    kern, width = resample.sinc_kernel(44100, 16000)
+    assert kern.shape == (160, 2 * width + 441) and width == 17
