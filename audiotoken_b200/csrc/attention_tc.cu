@@ -231,7 +231,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");   // every R row is complete
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kWG) : "memory");   // only the warps sharing this row   // every R row is complete
       if (lane == 0) mbar_arrive(bar(B_REMPTY));
       const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
       float m = -INFINITY, l = 0.f;
@@ -279,7 +279,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         mx = band ? mx * kScale : fmaf(mx, kScale, cb);          // this slice's maximum in the log2 domain
         // combine the row maximum with the warps that own the other key slices of this row
         smax[((g & 1) * kWG + wg) * kQT + r] = mx;
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kWG) : "memory");   // only the warps sharing this row
 #pragma unroll
         for (int u = 0; u < kWG; ++u) mx = fmaxf(mx, smax[((g & 1) * kWG + u) * kQT + r]);
         const float mn = fmaxf(m, mx);
@@ -312,7 +312,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       absorb_pv(h * nkt + nkt - 1, nkt == 1);
       // row sum = sum over the key slices (same running maximum in all warps of a row)
       ssum[wg * kQT + r] = l;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kWG) : "memory");   // only the warps sharing this row
       l = 0.f;
 #pragma unroll
       for (int u = 0; u < kWG; ++u) l += ssum[u * kQT + r];
