@@ -417,10 +417,10 @@ def main():
             phases = {}
             for nm, ms_p, fl in zip(['seanet_front_end', 'lstm', 'final_conv', 'rvq'], ac_ms, ph_flops):
                 phases[nm] = {'ms': float(ms_p), 'tflops_algorithmic': (frames * fl / (ms_p / 1e3) / 1e12) if ms_p > 0 else None}
-            # the strided-conv front end moves its intermediates through HBM: bytes the 13 kernels of a sub-batch read
-            # and write per frame (bf16, channels-last) = 389 376 B
+            # the strided-conv front end moves its intermediates through HBM: bytes the 11 kernels of a sub-batch read
+            # and write per frame (bf16, channels-last, level 0 fused) = 286 976 B
             if ac_ms[0] > 0:
-                phases['seanet_front_end']['hbm_gbps_moved'] = frames * 389376.0 / (ac_ms[0] / 1e3) / 1e9
+                phases['seanet_front_end']['hbm_gbps_moved'] = frames * 286976.0 / (ac_ms[0] / 1e3) / 1e9
                 phases['seanet_front_end']['hbm_peak_gbps'] = peak_hbm
             line['roofline'].update({'kernel': 'whole acoustic step: seanet_conv0 + seanet_tc_kernel (tcgen05 conv/LSTM GEMMs) + '
                                                'rvq_tc_kernel (tcgen05 bf16x3), SURVEY 8d FLOPs / step time',
