@@ -20,8 +20,23 @@ namespace {
 
 constexpr int kHeads = 16, kHD = 64, kRel = 73, kLeft = 64, kRight = 8;
 constexpr int kQKV = 3 * kHeads * kHD, kH = kHeads * kHD;
+#ifndef B2T_ATTN_WIDE
+#define B2T_ATTN_WIDE 0
+#endif
+#if B2T_ATTN_WIDE
+// wide configuration (kept as an experiment, measured SLOWER: 212 / 294 TFLOP/s on 10 s / 30 s clips against
+// 259 / 340 for the default): 128-key tiles, one CTA per SM, 16 softmax warps (4 per TMEM lane quadrant, 32 keys
+// each); TMEM: S 2 x 128 + PV 2 x 64 columns.  Two co-resident CTAs hide the hand-off latencies better than
+// doubling the work per hand-off.
+constexpr int kQT = 128, kKT = 128, kStages = 2;
+constexpr int kSoftmaxWarps = 16;
+constexpr int kCtasPerSm = 1, kTmemCols = 512;
+#else
 constexpr int kQT = 128, kKT = 64, kStages = 2;
 constexpr int kSoftmaxWarps = 8;                 // two warps per TMEM lane quadrant: each owns a 32-key slice of S
+constexpr int kCtasPerSm = 2, kTmemCols = 256;
+#endif
+constexpr int kPBuf = kQT * kKT * 2;             // one P buffer: kKT / 64 K-major blocks of 128 rows x 128 B
 constexpr int kThreadsAttn = 64 + 32 * kSoftmaxWarps;
 
 // Two CTAs are resident per SM (<= 113 KB shared memory, 256 TMEM columns, 320 threads each): while one CTA
@@ -30,21 +45,32 @@ constexpr int kThreadsAttn = 64 + 32 * kSoftmaxWarps;
 struct AttnSmem {
   static constexpr int kQ = 0;                                  // 16 KB
   static constexpr int kKV = kQ + kQT * 128;                    // kStages x (K 8 KB + V 8 KB)
-  static constexpr int kP = kKV + kStages * 2 * kKT * 128;      // 2 x 16 KB; buffer 1 first stages E (80 x 128 B)
-  static constexpr int kE = kP + kQT * 128;                     // = P buffer 1 (E is dead once R has been computed)
-  static constexpr int kR = kP + 2 * kQT * 128;                 // [128][80] bf16 = 20 KB
+  static constexpr int kP = kKV + kStages * 2 * kKT * 128;      // 2 P buffers; buffer 1 first stages E (80 x 128 B)
+  static constexpr int kE = kP + kPBuf;                         // = P buffer 1 (E is dead once R has been computed)
+  static constexpr int kR = kP + 2 * kPBuf;                     // [128][80] bf16 = 20 KB
   static constexpr int kMax = kR + kQT * 80 * 2;                // row-max exchange [2 slots][kWG][128] fp32
   static constexpr int kSum = kMax + 2 * 4 * kQT * 4;           // final row-sum exchange [kWG][128] fp32
   static constexpr int kBars = kSum + 4 * kQT * 4;
   static constexpr int kTotal = kBars + 256 + 1024;
 };
-static_assert(2 * AttnSmem::kTotal <= 227 * 1024, "two CTAs per SM");
+static_assert(kCtasPerSm * AttnSmem::kTotal <= 227 * 1024, "shared memory per SM");
 // barrier slots (8 bytes each)
 enum { B_EFULL = 0, B_QFULL, B_QEMPTY = B_QFULL + 2, B_RFULL = B_QEMPTY + 2, B_REMPTY, B_KVFULL, B_KVEMPTY = B_KVFULL + kStages,
        B_SFULL = B_KVEMPTY + kStages, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2, B_PEMPTY = B_PFULL + 2,
        B_PVFULL = B_PEMPTY + 2, B_PVEMPTY = B_PVFULL + 2, B_COUNT = B_PVEMPTY + 2 };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area");
 
+// named barrier 1 + quad among the warps that own the same 32 query rows (immediate ids: the kernel then reserves
+// 5 hardware barriers instead of all 16)
+template <int kCount>
+B2T_DEVICE void row_barrier(int quad) {
+  switch (quad) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"n"(kCount) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"n"(kCount) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"n"(kCount) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"n"(kCount) : "memory"); break;
+  }
+}
 B2T_DEVICE float ex2a(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -68,7 +94,7 @@ B2T_DEVICE void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32_
 // The CTA is persistent over the 16 heads of its (clip, query tile): barriers, the TMEM allocation and E are
 // set up once, the producer prefetches the next head's Q and K/V while the softmax warps finish the current
 // head.  g = head * nkt + i is the running key-tile counter that drives every ring / phase.
-__global__ void __launch_bounds__(kThreadsAttn, 2)
+__global__ void __launch_bounds__(kThreadsAttn, kCtasPerSm)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
                     const __grid_constant__ CUtensorMap map_e,
                     const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
@@ -102,13 +128,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_e); }
-  if (warp == 1) tmem_alloc(bars + 8u * B_COUNT, 256);
+  if (warp == 1) tmem_alloc(bars + 8u * B_COUNT, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // S double buffer [0,128), PV double buffer [128,256); R (80 columns) borrows the PV region before the first PV MMA
-  const uint32_t tS = tmem_base, tPV = tmem_base + 128, tR = tmem_base + 128;
+  const uint32_t tS = tmem_base, tPV = tmem_base + 2 * kKT, tR = tmem_base + 2 * kKT;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -144,7 +170,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const uint32_t sv = sKV + st * 2 * kKT * 128 + kKT * 128;
 #pragma unroll
         for (int kk = 0; kk < kKT / 16; ++kk) {
-          const uint64_t dp = make_smem_desc(sP + b * kQT * 128) + (uint64_t)(2 * kk);
+          const uint64_t dp = make_smem_desc(sP + b * kPBuf + (kk >> 2) * (kQT * 128)) + (uint64_t)(2 * (kk & 3));
           const uint64_t dv = make_smem_desc(sv + kk * 16 * 128);
           umma_bf16(tPV + (uint32_t)(b * kHD), dp, dv, idesc_o, kk != 0);
         }
@@ -231,7 +257,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kWG) : "memory");   // only the warps sharing this row   // every R row is complete
+      row_barrier<32 * kWG>(quad);   // only the warps sharing this row   // every R row is complete
       if (lane == 0) mbar_arrive(bar(B_REMPTY));
       const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
       float m = -INFINITY, l = 0.f;
@@ -279,7 +305,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         mx = band ? mx * kScale : fmaf(mx, kScale, cb);          // this slice's maximum in the log2 domain
         // combine the row maximum with the warps that own the other key slices of this row
         smax[((g & 1) * kWG + wg) * kQT + r] = mx;
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kWG) : "memory");   // only the warps sharing this row
+        row_barrier<32 * kWG>(quad);   // only the warps sharing this row
 #pragma unroll
         for (int u = 0; u < kWG; ++u) mx = fmaxf(mx, smax[((g & 1) * kWG + u) * kQT + r]);
         const float mn = fmaxf(m, mx);
@@ -290,7 +316,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         mbar_wait(bar(B_PEMPTY + b), ((g >> 1) & 1) ^ 1u);
         float ls = 0.f;
         const int kcol = wg * kKW;                                   // key column within the tile
-        uint8_t* half = gbase + AttnSmem::kP + b * kQT * 128 + r * 128;
+        uint8_t* half = gbase + AttnSmem::kP + b * kPBuf + (kcol >> 6) * (kQT * 128) + r * 128;
         const int ch0 = (kcol & 63) >> 3;
 #pragma unroll
         for (int ch = 0; ch < kKW / 8; ++ch) {
@@ -312,7 +338,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       absorb_pv(h * nkt + nkt - 1, nkt == 1);
       // row sum = sum over the key slices (same running maximum in all warps of a row)
       ssum[wg * kQT + r] = l;
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kWG) : "memory");   // only the warps sharing this row
+      row_barrier<32 * kWG>(quad);   // only the warps sharing this row
       l = 0.f;
 #pragma unroll
       for (int u = 0; u < kWG; ++u) l += ssum[u * kQT + r];
@@ -335,7 +361,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
