@@ -100,11 +100,22 @@ B2T_DEVICE RowInfo map_row(const ConvEpi& p, int m, int M) {
   return ri;
 }
 
+// CW bf16 values of one row.  Rows are written one per lane, so a 16-byte store would dirty half a 32-byte sector
+// per instruction (ncu: 47 % excessive sectors); sm_100's 256-bit store writes whole sectors.  dst is 32-byte aligned
+// whenever CW is a multiple of 16 (column offsets are multiples of 16 elements, row pitches multiples of 32 bytes).
 template <int CW>
 B2T_DEVICE void store_bf16(__nv_bfloat16* dst, const uint32_t* pk) {
+  if constexpr (CW % 16 == 0) {
 #pragma unroll
-  for (int i = 0; i < CW / 8; ++i)
-    *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    for (int i = 0; i < CW / 16; ++i)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   ::"l"(dst + 16 * i), "r"(pk[8 * i]), "r"(pk[8 * i + 1]), "r"(pk[8 * i + 2]), "r"(pk[8 * i + 3]),
+                     "r"(pk[8 * i + 4]), "r"(pk[8 * i + 5]), "r"(pk[8 * i + 6]), "r"(pk[8 * i + 7]) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i)
+      *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+  }
 }
 
 // one chunk of CW accumulator columns [col, col + CW) of the row described by ri
