@@ -344,13 +344,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       for (int u = 0; u < kWG; ++u) l += ssum[u * kQT + r];
       if (qpos < rows) {
         const float inv = 1.0f / l;
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(r0 + qpos) * kH + (head0 + h) * kHD + wg * kDW);
+        // one row per lane: 256-bit stores write whole 32-byte sectors (kDW is a multiple of 16)
+        __nv_bfloat16* dst = out + (size_t)(r0 + qpos) * kH + (head0 + h) * kHD + wg * kDW;
 #pragma unroll
-        for (int ch = 0; ch < kDW / 8; ++ch) {
-          uint4 v;
-          v.x = pack_bf16x2(o[ch * 8 + 0] * inv, o[ch * 8 + 1] * inv); v.y = pack_bf16x2(o[ch * 8 + 2] * inv, o[ch * 8 + 3] * inv);
-          v.z = pack_bf16x2(o[ch * 8 + 4] * inv, o[ch * 8 + 5] * inv); v.w = pack_bf16x2(o[ch * 8 + 6] * inv, o[ch * 8 + 7] * inv);
-          dst[ch] = v;
+        for (int ch = 0; ch < kDW / 16; ++ch) {
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(o[ch * 16 + 2 * e] * inv, o[ch * 16 + 2 * e + 1] * inv);
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"l"(dst + 16 * ch), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                       : "memory");
         }
       }
       // ssum is rewritten only after the next head's R barrier; sR likewise (bar.sync at the top of the loop)

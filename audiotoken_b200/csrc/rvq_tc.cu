@@ -21,6 +21,12 @@
 
 namespace {
 
+// one row per lane: 256-bit loads fetch whole 32-byte sectors (a 16-byte load per lane uses half of each)
+B2T_DEVICE void ldg8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+
 constexpr int kRows = 128, kD = 128, kCodes = 1024, kBN = 256;
 constexpr int kRingStages = 3;
 constexpr int kCluster = 4;                       // CTAs sharing one codebook stream (TMA multicast)
@@ -212,9 +218,11 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_c2 /* [n_q*1024, 256] bf16
     float r[kD];
     if (live) {
 #pragma unroll
-      for (int d = 0; d < kD; d += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(emb + (size_t)row * kD + d);
-        r[d] = v.x; r[d + 1] = v.y; r[d + 2] = v.z; r[d + 3] = v.w;
+      for (int d = 0; d < kD; d += 8) {
+        float v[8];
+        ldg8(emb + (size_t)row * kD + d, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[d + e] = v[e];
       }
     } else {
 #pragma unroll
@@ -336,9 +344,11 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_c2 /* [n_q*1024, 256] bf16
       if (q + 1 < n_q && !(dbg & 4)) {
         const float* e = E + (size_t)(live ? best : 0) * kD;
 #pragma unroll
-        for (int d = 0; d < kD; d += 4) {
-          const float4 ev = __ldg(reinterpret_cast<const float4*>(e + d));
-          r[d] -= ev.x; r[d + 1] -= ev.y; r[d + 2] -= ev.z; r[d + 3] -= ev.w;
+        for (int d = 0; d < kD; d += 8) {
+          float v[8];
+          ldg8(e + d, v);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) r[d + u] -= v[u];
         }
       }
     }

@@ -134,7 +134,10 @@ B2T_DEVICE void conv_epilogue_chunk(const ConvEpi& p, const RowInfo& ri, int col
   if (p.out_f32) {
     float* o = p.out_f32 + orow * p.ld_f32 + col;
 #pragma unroll
-    for (int i = 0; i < CW; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    for (int i = 0; i < CW; i += 8)
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3]), "f"(v[i + 4]), "f"(v[i + 5]),
+                     "f"(v[i + 6]), "f"(v[i + 7]) : "memory");
   }
   uint32_t pk[CW / 2];
   if (p.out_raw) {
@@ -167,9 +170,10 @@ B2T_DEVICE void lstm_epilogue_chunk(const LstmEpi& p, int b, int col, const uint
   const int u0 = col >> 2;
   float* cp = p.c + (size_t)b * 512 + u0;
   float cs[8];
-  if (p.t > 0) {
-    const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
-    cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+  if (p.t > 0) {     // one clip per lane: 256-bit accesses move whole 32-byte sectors
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(cs[0]), "=f"(cs[1]), "=f"(cs[2]), "=f"(cs[3]), "=f"(cs[4]), "=f"(cs[5]), "=f"(cs[6]), "=f"(cs[7])
+                 : "l"(cp) : "memory");
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) cs[j] = 0.f;
@@ -183,8 +187,8 @@ B2T_DEVICE void lstm_epilogue_chunk(const LstmEpi& p, int b, int col, const uint
     cs[j] = sigmoid_fast(gf) * cs[j] + sigmoid_fast(gi) * tanh_fast(gg);
     h[j] = sigmoid_fast(go) * tanh_fast(cs[j]);
   }
-  *reinterpret_cast<float4*>(cp) = make_float4(cs[0], cs[1], cs[2], cs[3]);
-  *reinterpret_cast<float4*>(cp + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(cp), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
   uint32_t pk[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pk[j] = pack2_bf16(h[2 * j], h[2 * j + 1]);
