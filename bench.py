@@ -214,7 +214,7 @@ def workload_config(workload, lengths):
     if workload == 'c2':
         name = f'semantic_m encode of 64 x 10 s @16 kHz clips (BASELINE configs[1] shape); conformer x{N_LAYERS} + VQ {CODEBOOK}'
     return {'workload': name, 'clips_per_gpu': int(len(lengths)), 'audio_seconds_per_gpu': float(lengths.sum() / (24000 if workload == 'c4' else SR)),
-            'row_budget_per_batch': ROW_BUDGET,
+            'row_budget_per_batch': (75 * 40000 if workload == 'c4' else ROW_BUDGET),
             'l2': 'inputs larger than L2: every batch streams >1 GB of activations through HBM'}
 
 
