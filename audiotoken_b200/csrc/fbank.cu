@@ -11,7 +11,7 @@
 namespace {
 
 constexpr int kFrame = 400, kHop = 160, kMel = 80, kMaxSpan = 32;
-constexpr int kWarps = 8;
+constexpr int kWarps = 6;      // 5 KB of FFT buffers per warp + 14 KB of tables stay below the 48 KB static limit
 
 __device__ float2 g_tw512[256];  // exp(-2*pi*i*k/512), k < 256
 
@@ -32,8 +32,8 @@ fbank_logmel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ 
   __shared__ float s_win[kFrame];
   __shared__ float s_melw[kMel * kMaxSpan];
   __shared__ int s_mstart[kMel], s_mcnt[kMel];
-  __shared__ float s_x[kWarps][512];
-  __shared__ float2 s_z[kWarps][256];
+  __shared__ float2 s_z[kWarps][320];     // 256 points + padding (up to 4 per 16)
+  __shared__ float2 s_zb[kWarps][320];
 
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tw[i] = g_tw512[i];
   for (int i = threadIdx.x; i < kFrame; i += blockDim.x) s_win[i] = window[i];
@@ -48,7 +48,7 @@ fbank_logmel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ 
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* xs = s_x[warp];
+  float* xs = reinterpret_cast<float*>(s_zb[warp]);   // frame / power spectrum; dead while the FFT ping-pongs
   float2* z = s_z[warp];
   float* zf = reinterpret_cast<float*>(z);
 
@@ -90,30 +90,48 @@ fbank_logmel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ 
     }
     __syncwarp();
 
-    // -- 256-point complex FFT, radix-2 decimation in frequency (output bit-reversed)
+    // -- 256-point complex FFT: Stockham radix-4, 4 passes, natural-order output.  Reads of a pass are unit-stride
+    //    across lanes; the scattered writes of the first two passes land in buffers padded by P elements per 16
+    //    (P = 1, 4) so that every shared-memory access of the transform is bank-conflict free.
+    {
+      auto ph = [](int i, int P) { return i + P * (i >> 4); };
+      auto pass = [&](const float2* src, int Ps, float2* dst, int Pd, int Ns) {
 #pragma unroll
-    for (int lg = 7; lg >= 0; --lg) {
-      const int h = 1 << lg;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        int b = lane + 32 * u;
-        int grp = b >> lg, pos = b & (h - 1);
-        int i = (grp << (lg + 1)) + pos, j = i + h;
-        float2 a = z[i], c = z[j];
-        float2 tw = s_tw[pos << (8 - lg)];
-        float dx = a.x - c.x, dy = a.y - c.y;
-        z[i] = make_float2(a.x + c.x, a.y + c.y);
-        z[j] = make_float2(dx * tw.x - dy * tw.y, dx * tw.y + dy * tw.x);
-      }
-      __syncwarp();
+        for (int u = 0; u < 2; ++u) {
+          const int j = lane + 32 * u, k = j & (Ns - 1);
+          float2 v0 = src[ph(j, Ps)], v1 = src[ph(j + 64, Ps)], v2 = src[ph(j + 128, Ps)], v3 = src[ph(j + 192, Ps)];
+          if (Ns > 1) {
+            const int m = k * (128 / Ns);                    // twiddle exp(-2 pi i r k / (4 Ns)) = tw512[r m]
+            const float2 w1 = s_tw[m], w2 = s_tw[2 * m];
+            float2 w3 = s_tw[(3 * m) & 255];
+            if (3 * m >= 256) { w3.x = -w3.x; w3.y = -w3.y; }
+            v1 = make_float2(v1.x * w1.x - v1.y * w1.y, v1.x * w1.y + v1.y * w1.x);
+            v2 = make_float2(v2.x * w2.x - v2.y * w2.y, v2.x * w2.y + v2.y * w2.x);
+            v3 = make_float2(v3.x * w3.x - v3.y * w3.y, v3.x * w3.y + v3.y * w3.x);
+          }
+          const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+          const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+          const int j0 = ((j - k) << 2) + k;
+          dst[ph(j0, Pd)] = make_float2(s02.x + s13.x, s02.y + s13.y);
+          dst[ph(j0 + Ns, Pd)] = make_float2(d02.x + d13.y, d02.y - d13.x);          // d02 - i d13
+          dst[ph(j0 + 2 * Ns, Pd)] = make_float2(s02.x - s13.x, s02.y - s13.y);
+          dst[ph(j0 + 3 * Ns, Pd)] = make_float2(d02.x - d13.y, d02.y + d13.x);      // d02 + i d13
+        }
+        __syncwarp();
+      };
+      float2* zb = s_zb[warp];
+      pass(z, 0, zb, 1, 1);
+      pass(zb, 1, z, 4, 4);
+      pass(z, 4, zb, 0, 16);
+      pass(zb, 0, z, 0, 64);
     }
 
     // -- split into the 512-point real spectrum, power (:177-181); bins 0..255 (Nyquist weight = 0)
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       int k = lane + 32 * u;
-      float2 zk = z[__brev((unsigned)k) >> 24];
-      float2 zm = z[__brev((unsigned)((256 - k) & 255)) >> 24];
+      float2 zk = z[k];
+      float2 zm = z[(256 - k) & 255];
       float ex = 0.5f * (zk.x + zm.x), ey = 0.5f * (zk.y - zm.y);
       float dx = 0.5f * (zk.x - zm.x), dy = 0.5f * (zk.y + zm.y);
       float ox = dy, oy = -dx;
