@@ -118,3 +118,23 @@ dist.destroy_process_group()
     line = [l for l in r.stdout.splitlines() if l.startswith('{')][-1]
     res = json.loads(line)
     assert res['ok'] and res['max'] <= res['total'] / 2 + 30
+
+
+def test_acoustic_plan_tables():
+    """Host planner of the acoustic path: level lengths (ceil division by the strides 2,4,5,8), the length-sorted
+    LSTM order with its inverse, time-major prefix sums and the 320-sample alignment flag the tensor path needs."""
+    from audiotoken_b200.acoustic import plan_acoustic
+    lens = [3200, 320 * 7, 24000, 320]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    p = plan_acoustic(lens, offs, lens, tiles=False)
+    assert p.aligned320 and p.total_frames == 10 + 7 + 75 + 1
+    assert [int(v) for v in p.lens[4]] == [10, 7, 75, 1]
+    assert [int(v) for v in p.lens[1]] == [1600, 1120, 12000, 160]
+    assert list(p.order) == [2, 0, 1, 3] and list(p.rank[p.order]) == [0, 1, 2, 3]
+    assert list(p.active[:2]) == [4, 3] and int(p.active[7]) == 2 and int(p.active[10]) == 1 and p.active.size == 75
+    assert int(p.toff[-1]) == p.total_frames and list(p.toff[:3]) == [0, 4, 7]
+    assert p.tile_clip[0].size == 0                      # tiles=False: no 64-row work lists
+    q = plan_acoustic([333, 24137], [0, 333], [333, 24137])
+    assert not q.aligned320 and [int(v) for v in q.lens[4]] == [2, 76] and q.tile_clip[0].size > 0
+    with pytest.raises(ValueError):
+        plan_acoustic([333], [0], [333], tiles=False)
