@@ -309,3 +309,90 @@ class AcousticEncoder(torch.nn.Module):
         codes, _ = self.encode_plan(wave, plan)
         fo = plan.offs[4]
         return [codes[:, fo[i]:fo[i] + rows[i]] for i in range(len(clips))]
+
+
+class AcousticDecoder(torch.nn.Module):
+    """Mirror of the reference's ``AcousticDecoder`` (audiotoken/decoder.py:50-76): ``decoder(tokens[B, K, T]) ->
+    fp32 [1, B * T * 320]`` = ``model.decoder(model.quantizer.decode(tokens))`` flattened, on the device.
+    fp32 CUDA-core kernels (csrc/acoustic.cu, b2t_acoustic_decode); no CPU fallback."""
+
+    def __init__(self, config=None, device: str = 'cuda:0', state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 seed: int = 0, **_unused):
+        super().__init__()
+        from .weights import SEANET_DEC_CONVS
+        self.device = torch.device(device)
+        L.require_device(self.device)
+        self.lib = L.load()
+        if state_dict is None:
+            state_dict = synthetic_encodec_state_dict(seed)
+        sd = state_dict
+        n_total = sum(1 for k in sd if k.endswith('codebook.embed'))
+        t: Dict[str, torch.Tensor] = {}
+        ci, ti = 0, 0
+        for name, cin, cout, k, s, transposed in SEANET_DEC_CONVS:
+            w = weight_norm_weight(sd, name).float()
+            if transposed:                                        # [C_in, C_out, 2s] -> phase-major [s, C_out, 2*C_in]
+                assert k == 2 * s
+                wt = torch.cat([w[:, :, :s].permute(2, 1, 0), w[:, :, s:].permute(2, 1, 0)], dim=2)
+                t[f'dec.convt{ti}.w'] = wt.contiguous().to(self.device)
+                t[f'dec.convt{ti}.b'] = sd[name + '.bias'].float().to(self.device).contiguous()
+                ti += 1
+            else:                                                 # [C_out, C_in, k] -> tap-major, K padded to 16
+                wm = w.permute(0, 2, 1).reshape(cout, k * cin)
+                kpad = (k * cin + 15) // 16 * 16
+                wp = torch.zeros(cout, kpad)
+                wp[:, :k * cin] = wm
+                t[f'dec.conv{ci}.w'] = wp.to(self.device).contiguous()
+                t[f'dec.conv{ci}.b'] = sd[name + '.bias'].float().to(self.device).contiguous()
+                ci += 1
+        p = 'decoder.layers.1.lstm.'
+        for layer in range(2):
+            t[f'dec.lstm{layer}.w_ih'] = sd[p + f'weight_ih_l{layer}'].float().to(self.device).contiguous()
+            t[f'dec.lstm{layer}.w_hh'] = sd[p + f'weight_hh_l{layer}'].float().to(self.device).contiguous()
+            t[f'dec.lstm{layer}.b'] = (sd[p + f'bias_ih_l{layer}'] + sd[p + f'bias_hh_l{layer}']).float().to(self.device).contiguous()
+        t['rvq.codebooks'] = torch.stack([sd[f'quantizer.layers.{q}.codebook.embed'].float() for q in range(n_total)]).to(self.device).contiguous()
+        self.tensors = t
+        with torch.cuda.device(self.device):
+            self.handle = self.lib.b2t_acoustic_create()
+            for name, ten in t.items():
+                L.check(self.lib.b2t_acoustic_set_tensor(self.handle, name.encode(), ten.data_ptr()), name)
+        self._ws: Optional[torch.Tensor] = None
+        self.last_launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.b2t_acoustic_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def decode_packed(self, codes: torch.Tensor, frames: Sequence[int]) -> torch.Tensor:
+        """codes int16 [n_q, sum(frames)] (packed clips) -> fp32 [sum(frames) * 320] on the device."""
+        assert codes.is_cuda and codes.dtype == torch.int16 and codes.is_contiguous()
+        n_q = codes.shape[0]
+        lens = [int(f) * HOP for f in frames]
+        offs = np.zeros(len(lens), dtype=np.int64)
+        offs[1:] = np.cumsum(lens)[:-1]
+        plan = plan_acoustic(lens, offs, lens)
+        assert plan.total_frames == codes.shape[1]
+        with torch.cuda.device(self.device):
+            db = DeviceAcousticBatch(plan, self.device)
+            need = self.lib.b2t_acoustic_decode_workspace_bytes(db.byref())
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(int(need) + 1024, dtype=torch.uint8, device=self.device)
+            wave = torch.empty(int(plan.offs[0][-1]), dtype=torch.float32, device=self.device)
+            L.check(self.lib.b2t_acoustic_decode(self.handle, codes.data_ptr(), db.byref(), n_q, self._ws.data_ptr(),
+                                                 self._ws.numel(), wave.data_ptr(), db.active.ctypes.data, L.stream_ptr()),
+                    'b2t_acoustic_decode')
+            self.last_launches = self.lib.b2t_last_launch_count()
+            self._keep = db
+        return wave
+
+    def forward(self, input_batch: torch.Tensor) -> torch.Tensor:
+        """tokens [B, K, T] (any integer dtype) -> fp32 [1, B * T * 320]  (reference decoder.py:62-76)."""
+        assert input_batch.dim() == 3
+        B, K, T = input_batch.shape
+        codes = input_batch.to(self.device).to(torch.int16).permute(1, 0, 2).reshape(K, B * T).contiguous()
+        return self.decode_packed(codes, [T] * B).unsqueeze(0)

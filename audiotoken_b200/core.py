@@ -111,8 +111,29 @@ class AudioToken:
         self.last_stats = encode_files(self.encoder, files, outdir, sr, rate, chunk_size, batch_size, num_workers,
                                        rel_dir=None if audio_files else str(audio_dir))
 
-    def decode(self, *a, **k):
-        raise NotImplementedError("token -> audio decoding is outside the scope of this build (SURVEY.md section 8f)")
+    def load_decoder(self, **kwargs):
+        """reference core.py:291-313.  Only the acoustic decoder is built."""
+        if getattr(self, 'decoder', None) is not None:
+            return
+        if self.tokenizer_name != Tokenizers.acoustic:
+            raise NotImplementedError("semantic token -> audio decoding (GPT-2 + Bark, reference decoder.py:79-) is outside "
+                                      "the scope of this build (SURVEY.md section 8f)")
+        from .acoustic import AcousticDecoder
+        kw = {k: v for k, v in {**self.kwargs, **kwargs}.items() if k in ('state_dict', 'seed')}
+        self.decoder = AcousticDecoder(device=self.device, **kw)
+
+    def decode(self, tokens, **kwargs) -> torch.Tensor:
+        """tokens (1, num_codebooks, num_tokens) -> audio fp32 CPU (1, num_samples)  (reference core.py:317-357)."""
+        self.load_decoder(**kwargs)
+        if isinstance(tokens, np.ndarray):
+            tokens = torch.from_numpy(tokens)
+        elif isinstance(tokens, (os.PathLike, str)):
+            tokens = torch.load(tokens, map_location='cpu')
+        elif not isinstance(tokens, torch.Tensor):
+            raise ValueError(f"Unsupported input type {type(tokens)}. Should be one of: np.ndarray, torch.Tensor, os.PathLike")
+        if tokens.dim() == 2:
+            tokens = tokens.unsqueeze(0)
+        return self.decoder(tokens.to(dtype=torch.long)).cpu()
 
 
 def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, token_rate: int, chunk_size: int,

@@ -539,3 +539,226 @@ extern "C" int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wav
   return rvq_launch(m, emb, t4, n_q, codes, st);
 #undef RUN
 }
+
+// =====================================================================================================
+// Decode half (reference audiotoken/decoder.py:62-76: `quantizer.decode` + `model.decoder`,
+// architecture as mirrored by transformers modeling_encodec.py:179-219, 316-353, 440-447).  fp32 CUDA-core kernels
+// (the reference's CPU numerics), same channels-last ragged layout and level tables as the fp32 encoder: level 4 is
+// the 75 Hz frame rate, level 0 the waveform; every level length is R_l * frames.
+// =====================================================================================================
+namespace {
+
+// codes int16 [n_q, rows] -> emb fp32 [rows, 128] = sum over stages of the selected codewords, in stage order
+__global__ void __launch_bounds__(256)
+rvq_decode_kernel(const int16_t* __restrict__ codes, int rows, const float* __restrict__ codebooks, int n_q,
+                  float* __restrict__ emb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (row, 4-float group)
+  const int row = i >> 5, g = i & 31;
+  if (row >= rows) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < n_q; ++q) {
+    const int c = codes[(size_t)q * rows + row];
+    const float4 e = __ldg(reinterpret_cast<const float4*>(codebooks + ((size_t)q * 1024 + c) * 128 + 4 * g));
+    acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+  }
+  reinterpret_cast<float4*>(emb + (size_t)row * 128)[g] = acc;
+}
+
+// Causal transposed conv (k = 2s, stride s) with ELU on its input, as one implicit GEMM per output phase j = u mod s:
+//   out[t*s + j, co] = b[co] + sum_ci ELU(x[t, ci]) W[ci, co, j] + ELU(x[t-1, ci]) W[ci, co, j + s]
+// (the k - s trailing samples of the full transposed convolution are trimmed, so output length = s * input length).
+// w: [s][cout][kdim_pad], k index = half * cin + ci (half 0: x[t], half 1: x[t-1]).  grid = (tiles of 64 input rows,
+// ceil(cout / 64), s).
+struct ConvTArgs {
+  const float* in; int cin; const float* w; int kdim_pad; const float* bias; float* out; int cout; int s;
+  const int32_t* in_off; const int32_t* in_len; const int32_t* out_off;
+  const int32_t* tile_clip; const int32_t* tile_t0;
+};
+
+__global__ void __launch_bounds__(256)
+seanet_convt_kernel(ConvTArgs a) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int clip = a.tile_clip[blockIdx.x], t0 = a.tile_t0[blockIdx.x];
+  const int n0 = blockIdx.y * 64, phase = blockIdx.z;
+  const int in_len = a.in_len[clip];
+  const long long in_base = (long long)a.in_off[clip] * a.cin;
+  const float* W = a.w + (size_t)phase * a.cout * a.kdim_pad;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int t = t0 + lr;
+  float acc[4][4] = {};
+  const int kdim = 2 * a.cin;
+  for (int k0 = 0; k0 < a.kdim_pad; k0 += 16) {
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t < in_len) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kidx = k0 + lk + i;
+        if (kidx < kdim) {
+          const int half = kidx >= a.cin, ci = kidx - half * a.cin;
+          const int src = t - half;
+          if (src >= 0) av[i] = eluf(a.in[in_base + (long long)src * a.cin + ci]);
+        }
+      }
+    }
+    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + lr < a.cout) wv = *reinterpret_cast<const float4*>(W + (size_t)(n0 + lr) * a.kdim_pad + k0 + lk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[lk + i][lr] = av[i];
+    Ws[lk][lr] = wv.x; Ws[lk + 1][lr] = wv.y; Ws[lk + 2][lr] = wv.z; Ws[lk + 3][lr] = wv.w;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 x4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float ar[4] = {x4.x, x4.y, x4.z, x4.w}, wr[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const long long out_base = a.out_off[clip];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tt = t0 + ty * 4 + i;
+    if (tt >= in_len) continue;
+    const size_t row = (size_t)(out_base + (long long)tt * a.s + phase) * a.cout;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < a.cout) a.out[row + n] = acc[i][j] + a.bias[n];
+    }
+  }
+}
+
+// decoder convs in forward order (transposed ones are handled by seanet_convt_kernel): index into "dec.conv<i>"
+const ConvSpec kDecConvs[14] = {
+    {128, 512, 7, 1},                                             // 0: layers.0
+    {256, 128, 3, 1}, {128, 256, 1, 1}, {256, 256, 1, 1},         // 1-3: block 4 (k3, k1, shortcut)
+    {128, 64, 3, 1},  {64, 128, 1, 1},  {128, 128, 1, 1},         // 4-6: block 7
+    {64, 32, 3, 1},   {32, 64, 1, 1},   {64, 64, 1, 1},           // 7-9: block 10
+    {32, 16, 3, 1},   {16, 32, 1, 1},   {32, 32, 1, 1},           // 10-12: block 13
+    {32, 1, 7, 1}};                                               // 13: layers.15
+const int kDecUpC[4] = {512, 256, 128, 64};                       // input channels of the 4 transposed convs
+const int kDecUpS[4] = {8, 5, 4, 2};
+
+struct DecWs {
+  float* emb; float* a4; float* xg; float* s1; float* s2; float* hA; float* hB; float* c;
+  float* u[4]; float* h[4]; float* y[4];      // per finer level (3, 2, 1, 0): upsampled, block hidden, block output
+  size_t total;
+};
+DecWs dec_carve(void* base, const b2t_acoustic_batch* b) {
+  DecWs w;
+  uint8_t* p = (uint8_t*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p ? (void*)(p + off) : nullptr; off += align_up_a(bytes, 256); return (float*)r; };
+  const size_t t4 = b->total[4];
+  w.emb = take(t4 * 128 * 4); w.a4 = take(t4 * 512 * 4); w.xg = take(t4 * 2048 * 4); w.s1 = take(t4 * 512 * 4); w.s2 = take(t4 * 512 * 4);
+  w.hA = take((size_t)b->n_clips * 512 * 4); w.hB = take((size_t)b->n_clips * 512 * 4); w.c = take((size_t)b->n_clips * 512 * 4);
+  for (int i = 0; i < 4; ++i) {
+    const int lvl = 3 - i, C = kDecUpC[i] / 2;
+    w.u[i] = take((size_t)b->total[lvl] * C * 4); w.h[i] = take((size_t)b->total[lvl] * (C / 2) * 4); w.y[i] = take((size_t)b->total[lvl] * C * 4);
+  }
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t b2t_acoustic_decode_workspace_bytes(const b2t_acoustic_batch* b) {
+  if (!b) return 0;
+  return dec_carve(nullptr, b).total;
+}
+
+extern "C" int b2t_acoustic_decode(const b2t_acoustic_model* m, const int16_t* codes, const b2t_acoustic_batch* b, int n_q,
+                                   void* workspace, size_t workspace_bytes, float* wave_out, const int32_t* active_host,
+                                   void* stream) {
+  B2T_REQUIRE(m && codes && b && workspace && wave_out && active_host, B2T_ERR_ARG, "b2t_acoustic_decode: null argument");
+  B2T_REQUIRE(n_q >= 1 && n_q <= 32, B2T_ERR_ARG, "b2t_acoustic_decode: n_q must be in [1, 32]");
+  B2T_REQUIRE(b->aligned320, B2T_ERR_ARG, "b2t_acoustic_decode: every clip must be frames * 320 samples long");
+  int rc = b2t_arch_ok();
+  if (rc != B2T_OK) return rc;
+  b2t_reset_launch_count();
+  if (b->n_clips <= 0 || b->total[4] <= 0) return B2T_OK;
+  DecWs w = dec_carve(workspace, b);
+  B2T_REQUIRE(workspace_bytes >= w.total, B2T_ERR_WORKSPACE, "b2t_acoustic_decode: workspace %zu < %zu", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool missing = false;
+  std::string miss;
+  auto T = [&](const std::string& n) -> const float* {
+    auto it = m->t.find(n);
+    if (it == m->t.end()) { if (!missing) miss = n; missing = true; return nullptr; }
+    return (const float*)it->second;
+  };
+  auto conv = [&](int ci, int lvl, const float* in, float* out, const float* resid, int elu) -> int {
+    const ConvSpec& cs = kDecConvs[ci];
+    ConvArgs a{};
+    a.in = in; a.cin = cs.cin; a.w = T("dec.conv" + std::to_string(ci) + ".w"); a.bias = T("dec.conv" + std::to_string(ci) + ".b");
+    B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_decode: tensor '%s' not set", miss.c_str());
+    a.kdim_pad = (cs.k * cs.cin + 15) / 16 * 16;
+    a.out = out; a.cout = cs.cout; a.resid = resid; a.k = cs.k; a.s = 1; a.elu_in = elu;
+    a.in_off = b->off[lvl]; a.in_len = b->len[lvl]; a.out_off = b->off[lvl]; a.out_len = b->len[lvl];
+    a.tile_clip = b->tile_clip[lvl]; a.tile_t0 = b->tile_t0[lvl];
+    if (b->n_tiles[lvl] <= 0) return B2T_OK;
+    dim3 grid(b->n_tiles[lvl], (cs.cout + 63) / 64);
+    seanet_conv_kernel<<<grid, 256, 0, st>>>(a);
+    B2T_LAUNCH_CHECK();
+    return B2T_OK;
+  };
+#define RUN(call) do { int rc__ = (call); if (rc__ != B2T_OK) return rc__; } while (0)
+  const int t4 = b->total[4];
+  const float* cbs = T("rvq.codebooks");
+  B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_decode: tensor '%s' not set", miss.c_str());
+  rvq_decode_kernel<<<(t4 * 32 + 255) / 256, 256, 0, st>>>(codes, t4, cbs, n_q, w.emb);
+  B2T_LAUNCH_CHECK();
+  RUN(conv(0, 4, w.emb, w.a4, nullptr, 0));                       // Conv(128 -> 512, k7)
+  for (int layer = 0; layer < 2; ++layer) {                       // LSTM x2 + skip
+    const std::string L = "dec.lstm" + std::to_string(layer) + ".";
+    const float* wih = T(L + "w_ih"); const float* whh = T(L + "w_hh"); const float* bias = T(L + "b");
+    B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_decode: tensor '%s' not set", miss.c_str());
+    {
+      ConvArgs a{};
+      a.in = layer == 0 ? w.a4 : w.s1; a.cin = 512; a.w = wih; a.kdim_pad = 512; a.bias = bias; a.out = w.xg; a.cout = 2048;
+      a.k = 1; a.s = 1; a.elu_in = 0;
+      a.in_off = b->off[4]; a.in_len = b->len[4]; a.out_off = b->off[4]; a.out_len = b->len[4];
+      a.tile_clip = b->tile_clip[4]; a.tile_t0 = b->tile_t0[4];
+      dim3 grid(b->n_tiles[4], 2048 / 64);
+      seanet_conv_kernel<<<grid, 256, 0, st>>>(a);
+      B2T_LAUNCH_CHECK();
+    }
+    float* hp = w.hA; float* hn = w.hB;
+    for (int t = 0; t < b->t_max; ++t) {
+      const int na = active_host[t];
+      if (na <= 0) break;
+      dim3 grid(512 / 32, (na + 31) / 32);
+      lstm_step_kernel<<<grid, 256, 0, st>>>(w.xg, whh, hp, hn, w.c, layer == 0 ? w.s1 : w.s2,
+                                             layer == 1 ? w.a4 : nullptr, b->order, b->off[4], t, na);
+      B2T_LAUNCH_CHECK();
+      float* tmp = hp; hp = hn; hn = tmp;
+    }
+  }
+  const float* x = w.s2;
+  for (int i = 0; i < 4; ++i) {                                   // ELU, transposed conv, residual block
+    const int lin = 4 - i, lout = 3 - i, cin = kDecUpC[i], cout = cin / 2, s = kDecUpS[i];
+    ConvTArgs a{};
+    a.in = x; a.cin = cin; a.w = T("dec.convt" + std::to_string(i) + ".w"); a.bias = T("dec.convt" + std::to_string(i) + ".b");
+    B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_acoustic_decode: tensor '%s' not set", miss.c_str());
+    a.kdim_pad = (2 * cin + 15) / 16 * 16; a.out = w.u[i]; a.cout = cout; a.s = s;
+    a.in_off = b->off[lin]; a.in_len = b->len[lin]; a.out_off = b->off[lout];
+    a.tile_clip = b->tile_clip[lin]; a.tile_t0 = b->tile_t0[lin];
+    dim3 grid(b->n_tiles[lin], (cout + 63) / 64, s);
+    seanet_convt_kernel<<<grid, 256, 0, st>>>(a);
+    B2T_LAUNCH_CHECK();
+    const int c0 = 1 + 3 * i;
+    RUN(conv(c0, lout, w.u[i], w.h[i], nullptr, 1));              // ELU, k3, C -> C/2
+    RUN(conv(c0 + 2, lout, w.u[i], w.y[i], nullptr, 0));          // 1x1 shortcut on the block input
+    RUN(conv(c0 + 1, lout, w.h[i], w.y[i], w.y[i], 1));           // ELU, k1, C/2 -> C, + shortcut
+    x = w.y[i];
+  }
+  RUN(conv(13, 0, x, wave_out, nullptr, 1));                      // ELU, Conv(32 -> 1, k7)
+  return B2T_OK;
+#undef RUN
+}

@@ -27,6 +27,7 @@ EXPORTS = [
     'b2t_last_launch_count', 'b2t_profile_enable', 'b2t_profile_read',
     'b2t_acoustic_create', 'b2t_acoustic_destroy', 'b2t_acoustic_set_tensor', 'b2t_acoustic_workspace_bytes',
     'b2t_acoustic_encode', 'b2t_rvq_encode', 'b2t_acoustic_profile_read', 'b2t_ingest_resample',
+    'b2t_acoustic_decode_workspace_bytes', 'b2t_acoustic_decode',
 ]
 
 
@@ -113,6 +114,9 @@ def load() -> C.CDLL:
     lib.b2t_acoustic_workspace_bytes.argtypes = [C.POINTER(AcousticBatch), i32]
     lib.b2t_acoustic_workspace_bytes.restype = sz
     lib.b2t_acoustic_encode.argtypes = [vp, vp, C.POINTER(AcousticBatch), i32, i32, vp, sz, vp, vp, vp, vp]
+    lib.b2t_acoustic_decode_workspace_bytes.argtypes = [C.POINTER(AcousticBatch)]
+    lib.b2t_acoustic_decode_workspace_bytes.restype = sz
+    lib.b2t_acoustic_decode.argtypes = [vp, vp, C.POINTER(AcousticBatch), i32, vp, sz, vp, vp, vp]
     ll = C.c_longlong
     lib.b2t_ingest_resample.argtypes = [vp, i32, ll, i32, ll, ll, vp, vp, vp, i32, i32, i32, i32, vp, ll, vp]
     lib.b2t_acoustic_profile_read.argtypes = [C.POINTER(C.c_float)]

@@ -114,6 +114,25 @@ SEANET_CONVS = [
 ]
 
 
+# EnCodec 24 kHz decoder (HF EncodecDecoder layer indices): (name, C_in, C_out, k, stride, transposed)
+SEANET_DEC_CONVS = [
+    ('decoder.layers.0.conv', 128, 512, 7, 1, False),
+    ('decoder.layers.3.conv', 512, 256, 16, 8, True),
+    ('decoder.layers.4.block.1.conv', 256, 128, 3, 1, False), ('decoder.layers.4.block.3.conv', 128, 256, 1, 1, False),
+    ('decoder.layers.4.shortcut.conv', 256, 256, 1, 1, False),
+    ('decoder.layers.6.conv', 256, 128, 10, 5, True),
+    ('decoder.layers.7.block.1.conv', 128, 64, 3, 1, False), ('decoder.layers.7.block.3.conv', 64, 128, 1, 1, False),
+    ('decoder.layers.7.shortcut.conv', 128, 128, 1, 1, False),
+    ('decoder.layers.9.conv', 128, 64, 8, 4, True),
+    ('decoder.layers.10.block.1.conv', 64, 32, 3, 1, False), ('decoder.layers.10.block.3.conv', 32, 64, 1, 1, False),
+    ('decoder.layers.10.shortcut.conv', 64, 64, 1, 1, False),
+    ('decoder.layers.12.conv', 64, 32, 4, 2, True),
+    ('decoder.layers.13.block.1.conv', 32, 16, 3, 1, False), ('decoder.layers.13.block.3.conv', 16, 32, 1, 1, False),
+    ('decoder.layers.13.shortcut.conv', 32, 32, 1, 1, False),
+    ('decoder.layers.15.conv', 32, 1, 7, 1, False),
+]
+
+
 def synthetic_encodec_state_dict(seed: int = 0, n_codebooks: int = 32) -> Dict[str, torch.Tensor]:
     """HF-named fp32 tensors of the EnCodec 24 kHz encoder, its 2-layer LSTM and the RVQ codebooks."""
     g = torch.Generator().manual_seed(seed)
@@ -132,6 +151,18 @@ def synthetic_encodec_state_dict(seed: int = 0, n_codebooks: int = 32) -> Dict[s
     for q in range(n_codebooks):
         # later stages quantise smaller residuals: shrink the codebooks geometrically so every stage stays informative
         sd[f'quantizer.layers.{q}.codebook.embed'] = torch.randn(1024, 128, generator=gq) * (0.12 * 0.85 ** q)
+    # decoder (own generator: the encoder / codebook tensors above do not depend on it)
+    gd = torch.Generator().manual_seed(seed + 2)
+    for name, cin, cout, k, _s, transposed in SEANET_DEC_CONVS:
+        shape = (cin, cout, k) if transposed else (cout, cin, k)
+        v = _randn(gd, *shape, std=1.0 / (cin * k) ** 0.5 * (2.0 ** 0.5 if transposed else 1.0))
+        norm = v.flatten(1).norm(dim=1).view(shape[0], 1, 1)
+        sd[name + '.parametrizations.weight.original0'] = norm * (1.0 + 0.1 * _randn(gd, shape[0], 1, 1))
+        sd[name + '.parametrizations.weight.original1'] = v
+        sd[name + '.bias'] = _randn(gd, cout, std=0.05)
+    for layer in range(2):
+        for nm, shape in (('weight_ih', (2048, 512)), ('weight_hh', (2048, 512)), ('bias_ih', (2048,)), ('bias_hh', (2048,))):
+            sd[f'decoder.layers.1.lstm.{nm}_l{layer}'] = (torch.rand(*shape, generator=gd) * 2 - 1) * bound
     return sd
 
 

@@ -265,6 +265,19 @@ int b2t_acoustic_encode(const b2t_acoustic_model* m, const float* wave, const b2
                         int n_q, int precision, void* workspace, size_t workspace_bytes, int16_t* codes,
                         float* emb_out, const int32_t* active_host, void* stream);
 
+/* ---- acoustic decode (reference audiotoken/decoder.py:62-76) --------------------------
+ * wave = model.decoder(model.quantizer.decode(codes)): sum of the selected codewords per frame, Conv k7, 2-layer
+ * LSTM + skip, 4 x (ELU, causal transposed conv k = 2s stride s = 8,5,4,2, residual block), ELU, Conv k7 -> 1 channel.
+ * fp32 CUDA-core kernels.  codes int16 [n_q, total[4]] (stage-major over the packed frames, as b2t_acoustic_encode
+ * writes them); wave_out fp32 [total[0]] with clip i at off[0][i] (len[0][i] = 320 * frames, batch->aligned320).
+ * Extra tensors: dec.conv<i>.w/.b (i = 0..13, forward order without the transposed convs, same format as conv<i>),
+ * dec.convt<j>.w fp32 [s, C_out, pad16(2*C_in)] (phase-major: k index = half*C_in + ci, half 0 -> W[ci,co,phase],
+ * half 1 -> W[ci,co,phase+s]) + dec.convt<j>.b, dec.lstm<l>.w_ih / .w_hh / .b.                               */
+size_t b2t_acoustic_decode_workspace_bytes(const b2t_acoustic_batch* batch);
+int b2t_acoustic_decode(const b2t_acoustic_model* m, const int16_t* codes, const b2t_acoustic_batch* batch, int n_q,
+                        void* workspace, size_t workspace_bytes, float* wave_out, const int32_t* active_host,
+                        void* stream);
+
 /* ---- ingest (reference audiotoken/utils.py:26-44 convert_audio, :98-99) ---------------------------------
  * PCM16 (/32768) or fp32 decode, mono mix-down (mean of 2 channels) and torchaudio-style sinc resampling in one
  * kernel.  Sample (c, t) of the input lives at in[t*t_stride + c*ch_stride].  (orig, new) are the gcd-reduced

@@ -19,9 +19,10 @@ from typing import Dict, List
 import torch
 import torch.nn.functional as F
 
-from audiotoken_b200.weights import SEANET_CONVS, weight_norm_weight
+from audiotoken_b200.weights import SEANET_CONVS, SEANET_DEC_CONVS, weight_norm_weight
 
 _CONV = {name: (cin, cout, k, s) for name, cin, cout, k, s in SEANET_CONVS}
+_CONV.update({name: (cin, cout, k, s) for name, cin, cout, k, s, _t in SEANET_DEC_CONVS})
 
 
 def _pad1d_reflect(x: torch.Tensor, left: int, right: int) -> torch.Tensor:
@@ -47,12 +48,12 @@ def conv(x: torch.Tensor, sd: Dict[str, torch.Tensor], name: str) -> torch.Tenso
     return F.conv1d(x, weight_norm_weight(sd, name), sd[name + '.bias'], stride=s)
 
 
-def lstm(x: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+def lstm(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str = 'encoder.layers.13.lstm.') -> torch.Tensor:
     """x [B, 512, T] -> LSTM(2 layers)(x) + x   (modeling_encodec.py:222-233; gate order i, f, g, o)."""
     h_in = x.permute(2, 0, 1)                                    # [T, B, 512]
     inp = h_in
     for layer in range(2):
-        p = f'encoder.layers.13.lstm.'
+        p = prefix
         w_ih, w_hh = sd[p + f'weight_ih_l{layer}'], sd[p + f'weight_hh_l{layer}']
         b = sd[p + f'bias_ih_l{layer}'] + sd[p + f'bias_hh_l{layer}']
         T, B, _ = inp.shape
@@ -112,3 +113,36 @@ def rvq_codes_reference_fp32(emb: torch.Tensor, sd: Dict[str, torch.Tensor], n_q
         out.append(idx.view(B, T))
         r = r - F.embedding(idx, E)
     return torch.stack(out, 0)
+
+
+# ---- decode half (reference audiotoken/decoder.py:62-76: quantizer.decode + decoder) ---------------
+def conv_transpose(x: torch.Tensor, sd: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
+    """x [B, C_in, T] -> [B, C_out, T*s]: causal EncodecConvTranspose1d (modeling_encodec.py:179-219): the k - s
+    trailing samples of the full transposed convolution are trimmed (trim_right_ratio = 1)."""
+    _cin, _cout, k, s = _CONV[name]
+    y = F.conv_transpose1d(x, weight_norm_weight(sd, name), sd[name + '.bias'], stride=s)
+    return y[..., :y.shape[-1] - (k - s)]
+
+
+def rvq_decode(codes: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """codes int [n_q, B, T] -> embeddings [B, 128, T]: sum of the selected codewords in stage order
+    (modeling_encodec.py:440-447 `quantized_out = quantized_out + quantized`)."""
+    n_q, B, T = codes.shape
+    out = torch.zeros(B, T, 128)
+    for q in range(n_q):
+        out = out + sd[f'quantizer.layers.{q}.codebook.embed'].float()[codes[q].long()]
+    return out.permute(0, 2, 1)
+
+
+def decoder(emb: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """emb [B, 128, T] -> waveform [B, 1, 320*T]  (modeling_encodec.py:316-353: conv k7, LSTM + skip, 4 x (ELU,
+    transposed conv, residual block), ELU, conv k7)."""
+    x = conv(emb.float(), sd, 'decoder.layers.0.conv')
+    x = lstm(x, sd, 'decoder.layers.1.lstm.')
+    for up, blk in ((3, 4), (6, 7), (9, 10), (12, 13)):
+        x = conv_transpose(F.elu(x), sd, f'decoder.layers.{up}.conv')
+        p = f'decoder.layers.{blk}.'
+        h = conv(F.elu(x), sd, p + 'block.1.conv')
+        h = conv(F.elu(h), sd, p + 'block.3.conv')
+        x = conv(x, sd, p + 'shortcut.conv') + h
+    return conv(F.elu(x), sd, 'decoder.layers.15.conv')

@@ -133,7 +133,7 @@ def main_acoustic():
     sd = synthetic_encodec_state_dict(0)
     model = EncodecModel(EncodecConfig())
     missing, unexpected = model.load_state_dict(sd, strict=False)
-    assert not unexpected and not [k for k in missing if k.startswith('encoder') or k.endswith('codebook.embed')]
+    assert not unexpected and not [k for k in missing if k.startswith(('encoder', 'decoder')) or k.endswith('codebook.embed')]
     model.eval()
     save = {}
     # BASELINE config 1 shape scaled down (1 s), an odd length (right reflect extra padding), a very short clip
@@ -145,6 +145,13 @@ def main_acoustic():
         save[f'lengths_{tag}'] = np.array(lengths)
         save[f'emb_{tag}'] = emb.numpy()
         save[f'codes_{tag}'] = codes.transpose(0, 1).numpy().astype(np.int16)   # [B, K, T] as encoder.py:54
+        if tag in ('a', 'c'):
+            with torch.no_grad():                                          # reference decoder.py:67-68
+                deq = model.quantizer.decode(codes)
+                wav = model.decoder(deq)
+            save[f'deq_{tag}'] = deq.numpy()
+            save[f'dec_{tag}'] = wav.numpy()
+            print('acoustic decode', tag, tuple(deq.shape), tuple(wav.shape))
         print('acoustic', tag, tuple(emb.shape), tuple(codes.shape))
     np.savez_compressed(os.path.join(HERE, 'acoustic.npz'), **save)
 

@@ -154,3 +154,43 @@ def test_acoustic_audiotoken_api(cuda_device, tmp_path):
     assert b.shape == (8, math.ceil(9000 / 24000 * 75))
     # a trailing 100-sample chunk is below the 3200-sample minimum and is skipped (reference datasets.py:95-97)
     assert np.load(tmp_path / 'o' / 'f2.npy').shape == (8, 75)
+
+
+# ---------------------------------------------------------------------------------------- decode half
+@pytest.mark.parametrize('tag', ['a', 'c'])
+def test_acoustic_decode_matches_golden(cuda_device, golden_dir, tag):
+    """reference decoder.py:62-76 (quantizer.decode + SEANet decoder) through b2t_acoustic_decode against the
+    EnCodec stand-in goldens: waveform within 1e-4 relative (fp32)."""
+    from audiotoken_b200.acoustic import AcousticDecoder
+    g = np.load(os.path.join(golden_dir, 'acoustic.npz'))
+    dec = AcousticDecoder(device='cuda:0', state_dict=synthetic_encodec_state_dict(0))
+    codes = torch.from_numpy(g[f'codes_{tag}'])                            # [B, 16, T]
+    wav = dec(codes.to(cuda_device))
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g[f'dec_{tag}']).reshape(1, -1)
+    assert wav.shape == ref.shape and wav.dtype == torch.float32
+    err = float((wav.cpu() - ref).norm() / ref.norm())
+    assert err < 1e-4, err
+    # ragged: the same clips decoded as one packed batch of different lengths == each clip alone (causal decoder)
+    B, K, T = codes.shape
+    if B == 2:
+        c0, c1 = codes[0, :, :40], codes[1]
+        packed = torch.cat([c0, c1], dim=1).to(torch.int16).contiguous().to(cuda_device)
+        w = dec.decode_packed(packed, [40, T]).cpu()
+        alone0 = dec(c0.unsqueeze(0).to(cuda_device)).cpu().reshape(-1)
+        alone1 = dec(c1.unsqueeze(0).to(cuda_device)).cpu().reshape(-1)
+        assert torch.equal(w[:40 * 320], alone0) and torch.equal(w[40 * 320:], alone1)
+        # causality: the first 40 frames of a clip decode to the first 12800 samples of the full decode
+        assert torch.equal(alone0, ref.reshape(B, -1)[0, :40 * 320]) or float((alone0 - ref.reshape(B, -1)[0, :40 * 320]).abs().max()) < 1e-4
+
+
+def test_acoustic_audiotoken_encode_decode_roundtrip_api(cuda_device):
+    """AudioToken.decode for the acoustic tokenizer (reference core.py:317-357): shapes, dtype, determinism."""
+    tok = AudioToken(tokenizer=Tokenizers.acoustic, device='cuda:0', num_codebooks=8)
+    x = synthetic_waveform(5, 24000, 24000).unsqueeze(0)
+    t = tok.encode(x)                                                     # [1, 8, 75]
+    y = tok.decode(t)
+    assert y.shape == (1, 24000) and y.dtype == torch.float32 and y.device.type == 'cpu'
+    assert torch.equal(y, tok.decode(t.numpy()))
+    with pytest.raises(NotImplementedError):
+        AudioToken(tokenizer=Tokenizers.semantic_m, device='cuda:0', n_layers=1).decode(torch.zeros(1, 1, 10, dtype=torch.long))

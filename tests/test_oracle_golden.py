@@ -146,3 +146,20 @@ def test_resample_oracle_matches_torchaudio_goldens(golden_dir):
     # published structure of the filter bank: gcd-reduced rates, 2*width + orig taps per phase
     kern, width = resample.sinc_kernel(44100, 16000)
     assert kern.shape == (160, 2 * width + 441) and width == 17
+
+
+def test_acoustic_decoder_oracle_matches_encodec_golden(golden_dir):
+    """oracle/seanet.py decode half (codeword sum + SEANet decoder with causal transposed convs) against HF
+    EncodecModel.quantizer.decode / .decoder on the synthetic weights (reference decoder.py:67-68)."""
+    from audiotoken_b200.weights import synthetic_encodec_state_dict
+    from oracle import seanet
+    g = np.load(os.path.join(golden_dir, 'acoustic.npz'))
+    sd = synthetic_encodec_state_dict(0)
+    for tag in ('a', 'c'):
+        codes = torch.from_numpy(g[f'codes_{tag}']).long().transpose(0, 1)      # [16, B, T]
+        deq = seanet.rvq_decode(codes, sd)
+        assert float((deq - torch.from_numpy(g[f'deq_{tag}'])).abs().max()) < 1e-6
+        wav = seanet.decoder(deq, sd)
+        ref = torch.from_numpy(g[f'dec_{tag}'])
+        assert wav.shape == ref.shape
+        assert float((wav - ref).norm() / ref.norm()) < 1e-5
