@@ -431,11 +431,19 @@ seanet_conv0_kernel(const float* __restrict__ wave, const int64_t* __restrict__ 
 //   epilogue warps (4) E1: h = ELU(D1 + b3) -> bf16 into columns 32..47 of A2 (shared memory, never HBM);
 //                      E2: ELU(D2 + b) -> global (+ halo mirror).  E1 of tile n+1 runs before E2 of tile n so the
 //                      MMA round trip is hidden.
+//   edge warp          the taps a row cannot get from its neighbours' registers: the two rows at the start of a tile
+//                      and at the start of a clip (reflect) need x(t-1), x(t-2) evaluated on their own — at most 18
+//                      (row, tap, channel half) tasks per tile, one per lane, next to the builders instead of inside
+//                      builder warp 0 (where they tripled the critical path); it also looks the next tile up.
 constexpr int kL0Builders = 8;
-constexpr int kL0Threads = 32 * (kL0Builders + 4 + 1);
+constexpr int kL0EdgeWarp = kL0Builders, kL0Epi0 = kL0Builders + 1, kL0MmaWarp = kL0Builders + 5;
+constexpr int kL0Threads = 32 * (kL0Builders + 1 + 4 + 1);
 constexpr int kL0A1 = 2 * kBM * 128;          // two 64-wide k-blocks, 32 KB
 constexpr int kL0A2 = kBM * 128;              // one k-block, 16 KB
-constexpr int kL0Smem = 2 * (kL0A1 + kL0A2) + 4096 + 4096 + 1024 + 512 + 1024;
+constexpr int kL0Smem = 2 * (kL0A1 + kL0A2) + 4096 + 4096 + 1024 + 1024 + 1024;   // operands, W3, Wres, w0, barrier block, slack
+
+// what the builder threads need to know about a 128-row tile: the clip of its first row and the next one
+struct L0TileInfo { long long woff0, woff1; int t0, len0, len1, tl0, tl1, has1; };
 
 struct L0Params {
   const float* wave; const int64_t* wave_off; const int32_t* true_len; const int32_t* off4;
@@ -443,6 +451,7 @@ struct L0Params {
   const float* b3; const float* bres;         // biases of k3 (16) and of shortcut + k1 (32)
   __nv_bfloat16* ye;                          // [P_0 rows, 32] ELU(y) with mirrored halo (H = 2)
   int c0, nsub, M;
+  long long* dbg;                             // optional timeline of CTA 0 (developer tool): [tile][8] clock64 stamps
 };
 
 __global__ void __launch_bounds__(kL0Threads, 2)
@@ -461,16 +470,18 @@ seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_consta
   auto d2_full = [&](int b) { return bars + 8u * (10 + b); };
   auto d2_empty = [&](int b) { return bars + 8u * (12 + b); };
   const uint32_t w_bar = bars + 8u * 14, tmem_slot = bars + 8u * 15;
+  auto ti_full = [&](int b) { return bars + 320u + 8u * b; };      // tile look-up n is in tinfo[n & 7]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_total = (p.M + kBM - 1) / kBM;
   const int my_tiles = blockIdx.x < n_tiles_total ? (n_tiles_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(a1_full(b), kL0Builders); mbar_init(a2_full(b), 4); mbar_init(a_empty(b), 1);
+      mbar_init(a1_full(b), kL0Builders + 1); mbar_init(a2_full(b), 4); mbar_init(a_empty(b), 1);
       mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), 4); mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), 4);
     }
     mbar_init(w_bar, 1);
+    mbar_init(ti_full(0), 1); mbar_init(ti_full(1), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -484,92 +495,124 @@ seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_consta
   float* sb3 = reinterpret_cast<float*>(bp + oBar + 128);      // 16 + 32 biases behind the barriers
   if (threadIdx.x < 16) sb3[threadIdx.x] = __ldg(p.b3 + threadIdx.x);
   else if (threadIdx.x < 48) sb3[threadIdx.x] = __ldg(p.bres + threadIdx.x - 16);
-  if (warp == kL0Builders + 4) tmem_alloc(tmem_slot, 128);
+  if (warp == kL0MmaWarp) tmem_alloc(tmem_slot, 128);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(bp + oBar + 8 * 15);
 
-  ConvEpi q{};
-  q.off4 = p.off4; q.c0 = p.c0; q.nsub = p.nsub; q.r = 320; q.h_in = 2;
+  // Tile look-ups (first row of the tile -> clip, time, the clip after it) are produced two tiles ahead by the MMA
+  // thread in its idle time (slot n & 7, mbarrier ti_full[n & 1]); builders, the edge warp and the E2 epilogue derive
+  // every row of the tile from them (a tile spans at most two clips: >= 320 rows each), so no thread runs a binary
+  // search or a chain of dependent global loads per row.
+  L0TileInfo* tinfo = reinterpret_cast<L0TileInfo*>(bp + oBar + 512);
+  auto derive = [&](const L0TileInfo& ti, int i) {
+    RowInfo ri;
+    const int t = ti.t0 + i;
+    const bool second = t >= ti.len0;
+    ri.t = second ? t - ti.len0 - 2 : t;                    // the next clip starts with its 2 halo rows
+    ri.len = second ? ti.len1 : ti.len0;
+    ri.clip = second ? 1 : 0;
+    ri.valid = i >= 0 && i < kBM && ri.t >= 0 && ri.t < ri.len && (!second || ti.has1);
+    return ri;
+  };
 
-  if (warp < kL0Builders) {
-    // ===== builders: thread pair per row; half = channels [16*half, 16*half + 16) =====
-    const int i = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const uint32_t row_off = (uint32_t)((i >> 3) * 1024 + (i & 7) * 128);
+  if (warp <= kL0EdgeWarp) {
+    // ===== builders (warps 0-7): thread pair per row; half = channels [16*half, 16*half + 16) =====
+    // ===== edge warp (warp 8): one (row, tap, half) task per lane =====
+    const bool edge = warp == kL0EdgeWarp;
+    // conv0 at time u for 16 channels [16*half, 16*half + 16): raw bf16 and ELU bf16 (2 x 16-byte chunks each)
+    auto conv0_at = [&](const float* x, int tl, int half, int u, uint32_t (&raw)[8], uint32_t (&el)[8]) {
+      float sj[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        int idx = u + j - 6;
+        idx = idx < 0 ? -idx : idx;                         // reflect padding of conv0 (on the waveform)
+        sj[j] = idx < tl ? __ldg(x + idx) : 0.f;
+      }
+#pragma unroll
+      for (int cc = 0; cc < 16; cc += 2) {
+        float v2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float4 wa = *reinterpret_cast<const float4*>(sw0 + (half * 16 + cc + e) * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sw0 + (half * 16 + cc + e) * 8 + 4);
+          float a = wb.w;
+          a = fmaf(wa.x, sj[0], a); a = fmaf(wa.y, sj[1], a); a = fmaf(wa.z, sj[2], a); a = fmaf(wa.w, sj[3], a);
+          a = fmaf(wb.x, sj[4], a); a = fmaf(wb.y, sj[5], a); a = fmaf(wb.z, sj[6], a);
+          v2[e] = a;
+        }
+        raw[cc >> 1] = pack2_bf16(v2[0], v2[1]);
+        el[cc >> 1] = pack2_bf16(elu_fast(v2[0]), elu_fast(v2[1]));
+      }
+    };
+    // ELU x(time) lands in tile row `row`, tap `tap`: chunks 4*tap + 2*half (+1) of that row
+    auto put_tap = [&](uint8_t* a1, int half, int row, int tap, const uint32_t (&el)[8]) {
+      const uint32_t ro = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int chunk = 4 * tap + 2 * half + h2;
+        const uint32_t off = (uint32_t)(chunk >> 3) * (kBM * 128) + ro + (uint32_t)(((chunk & 7) ^ (row & 7)) * 16);
+        *reinterpret_cast<uint4*>(a1 + off) = make_uint4(el[4 * h2], el[4 * h2 + 1], el[4 * h2 + 2], el[4 * h2 + 3]);
+      }
+    };
     for (int n = 0; n < my_tiles; ++n) {
       const int buf = n & 1;
-      const int m = ((int)blockIdx.x + n * (int)gridDim.x) * kBM + i;
-      const RowInfo ri = map_row(q, m, p.M);
-      mbar_wait(a_empty(buf), (uint32_t)(((n >> 1) & 1) ^ 1));
-      if (ri.valid) {
-        const float* x = p.wave + __ldg(p.wave_off + ri.clip);
-        const int tl = __ldg(p.true_len + ri.clip);
-        uint8_t* a1 = bp + oA1 + buf * kL0A1;
-        uint8_t* a2 = bp + oA2 + buf * kL0A2;
-        // conv0 at time u for this thread's 16 channels: raw bf16 and ELU bf16 (2 x 16-byte chunks each)
-        auto conv0_at = [&](int u, uint32_t (&raw)[8], uint32_t (&el)[8]) {
-          float sj[7];
-#pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            int idx = u + j - 6;
-            idx = idx < 0 ? -idx : idx;                       // reflect padding of conv0 (on the waveform)
-            sj[j] = idx < tl ? __ldg(x + idx) : 0.f;
-          }
-#pragma unroll
-          for (int cc = 0; cc < 16; cc += 2) {
-            float v2[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float4 wa = *reinterpret_cast<const float4*>(sw0 + (half * 16 + cc + e) * 8);
-              const float4 wb = *reinterpret_cast<const float4*>(sw0 + (half * 16 + cc + e) * 8 + 4);
-              float a = wb.w;
-              a = fmaf(wa.x, sj[0], a); a = fmaf(wa.y, sj[1], a); a = fmaf(wa.z, sj[2], a); a = fmaf(wa.w, sj[3], a);
-              a = fmaf(wb.x, sj[4], a); a = fmaf(wb.y, sj[5], a); a = fmaf(wb.z, sj[6], a);
-              v2[e] = a;
-            }
-            raw[cc >> 1] = pack2_bf16(v2[0], v2[1]);
-            el[cc >> 1] = pack2_bf16(elu_fast(v2[0]), elu_fast(v2[1]));
-          }
-        };
-        // ELU x(time) lands in tile row `row`, tap `tap`: chunks 4*tap + 2*half (+1) of that row
-        auto put_tap = [&](int row, int tap, const uint32_t (&el)[8]) {
-          const uint32_t ro = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && n < 64) p.dbg[n * 8 + 0] = clock64();
+      mbar_wait(ti_full(buf), (uint32_t)((n >> 1) & 1));
+      const L0TileInfo ti = tinfo[n & 7];
+      uint8_t* a1 = bp + oA1 + buf * kL0A1;
+      uint8_t* a2 = bp + oA2 + buf * kL0A2;
+      if (!edge) {
+        const int i = threadIdx.x & 127, half = threadIdx.x >> 7;
+        const uint32_t row_off = (uint32_t)((i >> 3) * 1024 + (i & 7) * 128);
+        const RowInfo ri = derive(ti, i);
+        mbar_wait(a_empty(buf), (uint32_t)(((n >> 1) & 1) ^ 1));
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && n < 64) p.dbg[n * 8 + 1] = clock64();
+        if (ri.valid) {
+          const float* x = p.wave + (ri.clip ? ti.woff1 : ti.woff0);
+          const int tl = ri.clip ? ti.tl1 : ti.tl0;
+          uint32_t raw[8], el[8];
+          conv0_at(x, tl, half, ri.t, raw, el);
+          // x(t) is tap 2 of row t, tap 1 of row t+1 and tap 0 of row t+2: computed once, written three times
+          put_tap(a1, half, i, 2, el);
+          if (i + 1 < kBM && ri.t + 1 < ri.len) put_tap(a1, half, i + 1, 1, el);
+          if (i + 2 < kBM && ri.t + 2 < ri.len) put_tap(a1, half, i + 2, 0, el);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const int chunk = 4 * tap + 2 * half + h2;
-            const uint32_t off = (uint32_t)(chunk >> 3) * (kBM * 128) + ro + (uint32_t)(((chunk & 7) ^ (row & 7)) * 16);
-            *reinterpret_cast<uint4*>(a1 + off) = make_uint4(el[4 * h2], el[4 * h2 + 1], el[4 * h2 + 2], el[4 * h2 + 3]);
+            const int chunk = 2 * half + h2;
+            *reinterpret_cast<uint4*>(a2 + row_off + (uint32_t)((chunk ^ (i & 7)) * 16)) =
+                make_uint4(raw[4 * h2], raw[4 * h2 + 1], raw[4 * h2 + 2], raw[4 * h2 + 3]);
           }
-        };
-        uint32_t raw[8], el[8];
-        conv0_at(ri.t, raw, el);
-        // x(t) is tap 2 of row t, tap 1 of row t+1 and tap 0 of row t+2: computed once, written three times
-        put_tap(i, 2, el);
-        if (i + 1 < kBM && ri.t + 1 < ri.len) put_tap(i + 1, 1, el);
-        if (i + 2 < kBM && ri.t + 2 < ri.len) put_tap(i + 2, 0, el);
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int chunk = 2 * half + h2;
-          *reinterpret_cast<uint4*>(a2 + row_off + (uint32_t)((chunk ^ (i & 7)) * 16)) =
-              make_uint4(raw[4 * h2], raw[4 * h2 + 1], raw[4 * h2 + 2], raw[4 * h2 + 3]);
         }
-        // taps whose producer row lies in the previous tile or before the clip start (reflect: x(-d) = x(d))
-#pragma unroll
-        for (int d = 1; d <= 2; ++d) {
-          if (i < d || ri.t < d) {
-            const int u = ri.t - d;
-            conv0_at(u < 0 ? -u : u, raw, el);
-            put_tap(i, 2 - d, el);
-          }
+      } else {
+        // taps whose producer row lies in the previous tile or before the clip start (reflect: x(-d) = x(d)):
+        // row i needs tap 2-d evaluated on its own iff i < d or t(i) < d.  Candidates: the first two rows of the
+        // tile, of the first clip (when the tile starts inside its halo) and of the second clip; lane = (group,
+        // (row, d) in {(0,1), (0,2), (1,2)}, half).  Coinciding candidates write identical values.
+        const int grp = lane / 6, sub = (lane % 6) >> 1, half = lane & 1;
+        const int rel = sub == 2 ? 1 : 0, d = sub == 0 ? 1 : 2;
+        const int first = grp == 0 ? 0 : grp == 1 ? -ti.t0 : ti.len0 + 2 - ti.t0;   // row with i == 0 / t == 0
+        const int i = first + rel;
+        const bool cand = lane < 18 && (grp != 1 || ti.t0 < 0);
+        const RowInfo ri = derive(ti, cand ? i : -1);
+        mbar_wait(a_empty(buf), (uint32_t)(((n >> 1) & 1) ^ 1));
+        if (ri.valid && (i < d || ri.t < d)) {
+          const float* x = p.wave + (ri.clip ? ti.woff1 : ti.woff0);
+          const int tl = ri.clip ? ti.tl1 : ti.tl0;
+          const int u = ri.t - d;
+          uint32_t raw[8], el[8];
+          conv0_at(x, tl, half, u < 0 ? -u : u, raw, el);
+          put_tap(a1, half, i, 2 - d, el);
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a1_full(buf));
+      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && n < 64) p.dbg[n * 8 + 2] = clock64();
     }
-  } else if (warp < kL0Builders + 4) {
+  } else if (warp < kL0MmaWarp) {
     // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
     const int i = quad * 32 + lane;
@@ -578,6 +621,7 @@ seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_consta
     auto e1 = [&](int n) {
       const int buf = n & 1;
       mbar_wait(d1_full(buf), (uint32_t)((n >> 1) & 1));
+      if (p.dbg && blockIdx.x == 0 && warp == kL0Epi0 && lane == 0 && n < 64) p.dbg[n * 8 + 3] = clock64();
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32_x16_nowait(lane_addr + (uint32_t)(buf * 16), r);
@@ -593,12 +637,14 @@ seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_consta
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive(a2_full(buf)); mbar_arrive(d1_empty(buf)); }
+      if (p.dbg && blockIdx.x == 0 && warp == kL0Epi0 && lane == 0 && n < 64) p.dbg[n * 8 + 4] = clock64();
     };
     auto e2 = [&](int n) {
       const int buf = n & 1;
       const int m = ((int)blockIdx.x + n * (int)gridDim.x) * kBM + i;
-      const RowInfo ri = map_row(q, m, p.M);
+      const RowInfo ri = derive(tinfo[n & 7], m < p.M ? i : -1);   // slot n & 7 is rewritten for tile n + 8, after E1(n + 5)
       mbar_wait(d2_full(buf), (uint32_t)((n >> 1) & 1));
+      if (p.dbg && blockIdx.x == 0 && warp == kL0Epi0 && lane == 0 && n < 64) p.dbg[n * 8 + 5] = clock64();
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32_nowait(lane_addr + (uint32_t)(32 + buf * 32), r);
@@ -615,6 +661,7 @@ seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_consta
         store_bf16<32>(o, pk);
         if (ri.t >= 1 && ri.t <= 2) store_bf16<32>(o - 2 * ri.t * 32, pk);
       }
+      if (p.dbg && blockIdx.x == 0 && warp == kL0Epi0 && lane == 0 && n < 64) p.dbg[n * 8 + 6] = clock64();
     };
     if (my_tiles > 0) e1(0);
     for (int n = 0; n < my_tiles; ++n) {
@@ -631,6 +678,36 @@ seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_consta
       tma_load_2d(sWr, &map_wres, w_bar, 0, 0);
       mbar_wait(w_bar, 0);
       constexpr uint32_t idesc1 = make_idesc(kBM, 16), idesc2 = make_idesc(kBM, 32);
+      // incremental look-up: tiles of a CTA only move forward through the clip table
+      const int f0 = __ldg(p.off4 + p.c0);
+      int lk = 0;                                            // clip (relative to c0) of the previous look-up
+      auto clip_row0 = [&](int c) { return 320 * (__ldg(p.off4 + p.c0 + c) - f0) + 2 * c; };   // first (halo) row of clip c
+      auto lookup = [&](int n) {
+        const int m0 = ((int)blockIdx.x + n * (int)gridDim.x) * kBM;
+        int steps = 0;
+        while (lk + 1 < p.nsub && clip_row0(lk + 1) <= m0) {
+          ++lk;
+          if (++steps == 8) {                                // many tiny clips: finish with a binary search
+            int lo = lk, hi = p.nsub;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (clip_row0(mid) <= m0) lo = mid; else hi = mid; }
+            lk = lo;
+            break;
+          }
+        }
+        const int clip = p.c0 + lk;
+        const int fa = __ldg(p.off4 + clip), fb = __ldg(p.off4 + clip + 1);
+        L0TileInfo ti;
+        ti.t0 = m0 - (320 * (fa - f0) + 2 * lk) - 2; ti.len0 = 320 * (fb - fa);
+        ti.woff0 = __ldg(p.wave_off + clip); ti.tl0 = __ldg(p.true_len + clip);
+        ti.has1 = lk + 1 < p.nsub;
+        ti.woff1 = ti.has1 ? __ldg(p.wave_off + clip + 1) : 0;
+        ti.tl1 = ti.has1 ? __ldg(p.true_len + clip + 1) : 0;
+        ti.len1 = ti.has1 ? 320 * (__ldg(p.off4 + clip + 2) - fb) : 0;
+        tinfo[n & 7] = ti;
+        mbar_arrive(ti_full(n & 1));                         // release: the slot is written before the arrival
+      };
+      if (my_tiles > 0) lookup(0);
+      if (my_tiles > 1) lookup(1);
       auto mma2 = [&](int k) {
         const int buf = k & 1;
         mbar_wait(a2_full(buf), (uint32_t)((k >> 1) & 1));
@@ -657,14 +734,17 @@ seanet_l0_kernel(const __grid_constant__ CUtensorMap map_w3, const __grid_consta
             umma_bf16(tmem_base + (uint32_t)(buf * 16), da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc1, (kb | kk) ? 1u : 0u);
         }
         umma_commit(d1_full(buf));
-        if (n > 0) mma2(n - 1);
+        if (p.dbg && blockIdx.x == 0 && n < 64) p.dbg[n * 8 + 7] = clock64();
+        // D2 of the same tile as soon as E1 has produced ELU h: the operand buffers go back to the builders one
+        // MMA round trip after D1 instead of one whole tile later (the builders are the long pole, not this warp)
+        mma2(n);
+        if (n + 2 < my_tiles) lookup(n + 2);
       }
-      if (my_tiles > 0) mma2(my_tiles - 1);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kL0Builders + 4) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+  if (warp == kL0MmaWarp) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
 // ---- host ----------------------------------------------------------------------------------------
@@ -770,6 +850,7 @@ TcWs tc_carve(void* base, long long sub_frames, int sub_clips, long long total4,
 }
 
 // greedy split of the clip list into front-end sub-batches of at most kSubFrames frames
+long long* g_l0_dbg = nullptr;    // b2t_seanet_set_l0_dbg(device buffer of 64 x 8 int64) — developer timeline
 int g_l0_fused = 1;               // b2t_set_option("seanet_l0_fused", 0/1)
 int g_lstm_pdl = 1;               // b2t_set_option("lstm_pdl", 0/1)
 long long g_sub_frames = 24576;   // b2t_set_option("seanet_sub_frames", n)
@@ -795,6 +876,7 @@ std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* 
 void b2t_seanet_set_sub_frames(int n) { if (n > 0) g_sub_frames = n; }
 void b2t_seanet_set_lstm_pdl(int on) { g_lstm_pdl = on != 0; }
 void b2t_seanet_set_l0_fused(int on) { g_l0_fused = on != 0; }
+extern "C" void b2t_seanet_set_l0_dbg(long long* p) { g_l0_dbg = p; }
 
 size_t b2t_seanet_tc_workspace_bytes(const b2t_acoustic_batch* b) {
   if (!b->frames_host) return 0;
@@ -827,7 +909,8 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
       CUtensorMap m3, mr;
       RUN(make_map_k(&m3, wt.k3_w[0], 16, 128, 128, 16));
       RUN(make_map_k(&mr, wt.res_w[0], 32, 64, 64, 32));
-      L0Params lp{wave, b->wave_off, b->true_len, b->off[4], wt.conv0_w, wt.conv0_b, wt.k3_b[0], wt.res_b[0], w.ye[0], sb.c0, ns, M0};
+      L0Params lp{wave, b->wave_off, b->true_len, b->off[4], wt.conv0_w, wt.conv0_b, wt.k3_b[0], wt.res_b[0], w.ye[0], sb.c0, ns, M0,
+                  g_l0_dbg};
       static bool cfg = false;
       if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(seanet_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem)); cfg = true; }
       int grid = 2 * b2t_num_sms();

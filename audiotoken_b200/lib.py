@@ -27,7 +27,7 @@ EXPORTS = [
     'b2t_last_launch_count', 'b2t_profile_enable', 'b2t_profile_read',
     'b2t_acoustic_create', 'b2t_acoustic_destroy', 'b2t_acoustic_set_tensor', 'b2t_acoustic_workspace_bytes',
     'b2t_acoustic_encode', 'b2t_rvq_encode', 'b2t_acoustic_profile_read', 'b2t_ingest_resample',
-    'b2t_acoustic_decode_workspace_bytes', 'b2t_acoustic_decode',
+    'b2t_acoustic_decode_workspace_bytes', 'b2t_acoustic_decode', 'b2t_vq_ema_workspace_bytes', 'b2t_vq_ema_update',
 ]
 
 
@@ -97,6 +97,10 @@ def load() -> C.CDLL:
     lib.b2t_vq_workspace_bytes.restype = sz
     lib.b2t_vq_argmin.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
     lib.b2t_vq_debug_stats.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_uint), C.POINTER(C.c_float)]
+    lib.b2t_vq_ema_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.b2t_vq_ema_workspace_bytes.restype = sz
+    f32 = C.c_float
+    lib.b2t_vq_ema_update.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, f32, f32, f32, vp, vp, vp, sz, vp]
     lib.b2t_semantic_create.argtypes = [i32, i32, i32]
     lib.b2t_semantic_create.restype = vp
     lib.b2t_semantic_destroy.argtypes = [vp]

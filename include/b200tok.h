@@ -183,6 +183,24 @@ int b2t_vq_argmin(const float* x, int ldx, int rows, int dim, const float* codeb
 int b2t_vq_debug_stats(const void* workspace, int rows, int dim, int codebook_size,
                        unsigned int* n_fallback_host, float* max_rel_err_host);
 
+/* Codebook training step (reference scripts/clustering/cluster_tokens.py:293-311 calls
+ * VectorQuantize(dim, codebook_size, decay=0.8, commitment_weight=1) (:142-147) in training mode on each batch of
+ * embeddings; the class is third-party `vector_quantize_pytorch`, unpinned, requirements.txt:10).  Given the
+ * assignment idx[r] of every row against the CURRENT codebook (b2t_vq_argmin, out_i32), applies the published EMA
+ * k-means update of a Euclidean codebook in place:
+ *     cluster_size <- cluster_size*decay + n*(1-decay);   embed_avg <- embed_avg*decay + s*(1-decay)
+ *     codebook_k    = embed_avg_k / ((cluster_size_k + eps) / (sum(cluster_size) + K*eps) * sum(cluster_size))
+ * with n_k / s_k the count / sum of the rows assigned to k, and writes commit_loss = commitment_weight *
+ * mean((codebook_old[idx] - x)^2) (device scalar, optional) and quantized = codebook_old[idx] (optional).
+ * Deterministic: rows are counting-sorted by centroid and summed in row order, no floating-point atomics.
+ * State tensors are the reference checkpoint's `_codebook.embed[0]`, `_codebook.embed_avg[0]`,
+ * `_codebook.cluster_size[0]` (cluster_tokens.py:316-320).                                              */
+size_t b2t_vq_ema_workspace_bytes(int rows, int dim, int codebook_size);
+int b2t_vq_ema_update(const float* x, int ldx, int rows, int dim, const int32_t* idx, float* codebook,
+                      float* embed_avg, float* cluster_size, int codebook_size, float decay, float eps,
+                      float commitment_weight, float* commit_loss, float* quantized, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* ---- whole semantic encoder (reference Wav2VecBertEncoder.forward, encoder.py:163-186) ------- */
 typedef struct b2t_semantic_model b2t_semantic_model;
 

@@ -71,3 +71,32 @@ def rvq_encode(emb: torch.Tensor, codebooks: torch.Tensor, n_q: int,
         out.append(i)
         r = r - E[i]
     return torch.stack(out, 0)
+
+
+def vq_ema_train_step(x: torch.Tensor, embed: torch.Tensor, embed_avg: torch.Tensor, cluster_size: torch.Tensor,
+                      decay: float = 0.8, eps: float = 1e-5, commitment_weight: float = 1.0, dtype=torch.float64):
+    """One training-mode forward of the reference's quantiser (scripts/clustering/cluster_tokens.py:142-147, 293-311:
+    `VectorQuantize(dim, codebook_size, decay=0.8, commitment_weight=1)` called on a batch).  The class is third-party
+    (`vector_quantize_pytorch`, unpinned, requirements.txt:10); this restates the published training forward of its
+    Euclidean codebook (one head, ema_update, threshold_ema_dead_code = 0, codebook already initialised):
+
+        idx = argmin cdist(x, embed);  quantize = embed[idx];  loss = mse(quantize, x) * commitment_weight
+        cluster_size <- cluster_size*decay + onehot.sum(0)*(1-decay)
+        embed_avg    <- embed_avg*decay + (onehot^T x)*(1-decay)
+        embed        <- embed_avg / (laplace_smoothing(cluster_size, K, eps) * cluster_size.sum())[:, None]
+
+    x [M, D]; returns (idx int64 [M], loss float, embed', embed_avg', cluster_size') in `dtype`.
+    PARITY UNPINNED against the third-party package itself (absent offline); anchored on the call site only."""
+    x = x.detach().cpu().to(dtype)
+    e = embed.detach().cpu().to(dtype)
+    K = e.shape[0]
+    idx, _ = nearest_centroid(x, e)
+    q = e[idx]
+    loss = float(((q - x) ** 2).mean() * commitment_weight)
+    n = torch.bincount(idx, minlength=K).to(dtype)
+    s = torch.zeros_like(e).index_add_(0, idx, x)
+    cs = cluster_size.detach().cpu().to(dtype) * decay + n * (1.0 - decay)
+    avg = embed_avg.detach().cpu().to(dtype) * decay + s * (1.0 - decay)
+    tot = cs.sum()
+    smoothed = (cs + eps) / (tot + K * eps) * tot
+    return idx, loss, avg / smoothed.unsqueeze(1), avg, cs

@@ -163,3 +163,33 @@ def test_acoustic_decoder_oracle_matches_encodec_golden(golden_dir):
         ref = torch.from_numpy(g[f'dec_{tag}'])
         assert wav.shape == ref.shape
         assert float((wav - ref).norm() / ref.norm()) < 1e-5
+
+
+def test_vq_ema_oracle_equals_onehot_formulation():
+    """oracle/quantize.py::vq_ema_train_step against the one-hot / matmul formulation the third-party class
+    publishes (one_hot -> sum, x^T onehot, mul_(decay).add_(new*(1-decay)), laplace smoothing), written out
+    independently here; plus two properties: decay = 0 gives the (smoothed) cluster means, empty clusters shrink."""
+    import torch
+    from oracle import quantize
+    g = torch.Generator().manual_seed(11)
+    M, D, K = 600, 32, 50
+    x = torch.randn(M, D, generator=g, dtype=torch.float64)
+    embed = torch.randn(K, D, generator=g, dtype=torch.float64)
+    embed[7] = 100.0                                   # never selected
+    avg0, cs0 = embed.clone(), torch.full((K,), 3.0, dtype=torch.float64)
+    idx, loss, e, avg, cs = quantize.vq_ema_train_step(x, embed, avg0, cs0, decay=0.8, eps=1e-5)
+    dist = -torch.cdist(x, embed)
+    ind = dist.argmax(-1)
+    onehot = torch.nn.functional.one_hot(ind, K).to(torch.float64)
+    cs_ref = cs0.clone().mul_(0.8).add_(onehot.sum(0) * 0.2)
+    avg_ref = avg0.clone().mul_(0.8).add_((x.t() @ onehot).t() * 0.2)
+    sm = (cs_ref + 1e-5) / (cs_ref.sum() + K * 1e-5) * cs_ref.sum()
+    assert torch.equal(idx, ind)
+    assert torch.allclose(cs, cs_ref, rtol=1e-13) and torch.allclose(avg, avg_ref, rtol=1e-12, atol=1e-13)
+    assert torch.allclose(e, avg_ref / sm.unsqueeze(1), rtol=1e-12, atol=1e-13)
+    assert abs(loss - float(((embed[ind] - x) ** 2).mean())) < 1e-12
+    assert cs[7] == 3.0 * 0.8
+    _, _, e0, _, cs00 = quantize.vq_ema_train_step(x, embed, avg0, cs0, decay=0.0, eps=1e-5)
+    used = torch.unique(ind)
+    means = torch.stack([x[ind == k].mean(0) for k in used])
+    assert torch.allclose(e0[used], means, rtol=1e-4)
