@@ -368,9 +368,324 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   }
 }
 
+
+#if !B2T_ATTN_WIDE
+// ---- two-pass variant ------------------------------------------------------------------------------------
+// Online softmax costs this kernel a cross-warp max exchange, a correction factor and a TMEM read + rescale of the
+// output accumulator per key tile — more instructions and hand-offs than the exponentials themselves, while the
+// tensor pipe idles (13 % busy).  Here the row maximum is fixed BEFORE any exponential is taken:
+//   pass 1  S = Q.K^T for every key tile (tensor core), softmax warps keep only the running maximum of their slice;
+//           row bound m = (max raw score + max relative-key bias of the row) / 8 >= every biased score of the row
+//           (a bound instead of the exact maximum is enough: P stays <= 1 and bf16 keeps fp32's exponent range);
+//   pass 2  S again (QK^T is recomputed: +50 % tensor work on an idle pipe), P = 2^(score - m) -> bf16 -> shared
+//           memory, O += P.V accumulated in TMEM across all key tiles; O is read once per head, the row sums are
+//           combined once per head.
+// Per key tile a softmax thread runs LDTM + max (pass 1) and LDTM + FMA/EX2/ADD + pack + store (pass 2): no
+// exchange, no correction, no accumulator traffic.  K/V tiles move through a ring of four 8 KB slots (pass 1 uses
+// one per tile, pass 2 two), the S and P double buffers are shared by both passes.
+namespace tp {
+enum { EFULL = 0, QFULL, RFULL, OFULL, KVFULL, KVEMPTY = KVFULL + 4, SFULL = KVEMPTY + 4, SEMPTY = SFULL + 2,
+       PFULL = SEMPTY + 2, PEMPTY = PFULL + 2, COUNT = PEMPTY + 2 };
+constexpr int kSlots = 4, kSlotBytes = kKT * 128;
+static_assert(COUNT * 8 + 8 <= 256, "barrier area");
+static_assert(kSlots * kSlotBytes == kStages * 2 * kKT * 128, "the slot ring reuses the K/V stage area");
+}  // namespace tp
+
+__global__ void __launch_bounds__(kThreadsAttn, kCtasPerSm)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ CUtensorMap map_e,
+                     const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
+                     const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
+                     __nv_bfloat16* __restrict__ out, long long* __restrict__ dbg /* developer timeline of one CTA, or null */) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base + AttnSmem::kQ, sKV = base + AttnSmem::kKV, sP = base + AttnSmem::kP, sE = base + AttnSmem::kE;
+  __nv_bfloat16* sR = reinterpret_cast<__nv_bfloat16*>(gbase + AttnSmem::kR);
+  const uint32_t bars = base + AttnSmem::kBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + AttnSmem::kBars + 8 * tp::COUNT);
+  // timeline: CTA (300, 5) — a mid-grid CTA so that both CTAs of the SM are in steady state; stamps of warp 2 lane 0
+  const bool tl = dbg != nullptr && blockIdx.x == 300 && blockIdx.y == 5 && threadIdx.x == 64;
+  int tln = 0;
+  auto stamp = [&]() { if (tl && tln < 128) dbg[tln++] = clock64(); };
+  stamp();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int clip = qtile_clip[blockIdx.x], q0 = qtile_q0[blockIdx.x];
+  const int r0 = row_off[clip], rows = row_off[clip + 1] - r0, nkeys = valid_rows[clip];
+  const int nkt = (nkeys + kKT - 1) / kKT;
+  const int head = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(tp::EFULL), 1); mbar_init(bar(tp::QFULL), 1); mbar_init(bar(tp::RFULL), 1); mbar_init(bar(tp::OFULL), 1);
+    for (int s = 0; s < tp::kSlots; ++s) { mbar_init(bar(tp::KVFULL + s), 1); mbar_init(bar(tp::KVEMPTY + s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(tp::SFULL + b), 1); mbar_init(bar(tp::SEMPTY + b), kSoftmaxWarps);
+      mbar_init(bar(tp::PFULL + b), kSoftmaxWarps); mbar_init(bar(tp::PEMPTY + b), 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_e); }
+  if (warp == 1) tmem_alloc(bars + 8u * tp::COUNT, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // S double buffer [0,128); O accumulator [128,192); R (80 columns) borrows the O region until the first PV MMA
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT, tR = tmem_base + 2 * kKT;
+
+  if (warp == 0) {
+    // ===== TMA producer: slot counter c runs over pass-1 K tiles, then (K, V) pairs of pass 2 =====
+    if (lane == 0) {
+      mbar_expect_tx(bar(tp::EFULL), 80 * 128);
+      tma_load_2d(sE, &map_e, bar(tp::EFULL), 0, 0);
+      mbar_expect_tx(bar(tp::QFULL), kQT * 128);
+      tma_load_2d(sQ, &map_qkv, bar(tp::QFULL), head * kHD, r0 + q0);
+      int c = 0;
+      auto load_slot = [&](int col, int i) {
+        const int st = c % tp::kSlots;
+        mbar_wait(bar(tp::KVEMPTY + st), ((c / tp::kSlots) & 1) ^ 1u);
+        mbar_expect_tx(bar(tp::KVFULL + st), tp::kSlotBytes);
+        tma_load_2d(sKV + st * tp::kSlotBytes, &map_kv, bar(tp::KVFULL + st), col + head * kHD, r0 + i * kKT);
+        ++c;
+      };
+      for (int i = 0; i < nkt; ++i) load_slot(kH, i);
+      for (int i = 0; i < nkt; ++i) { load_slot(kH, i); load_slot(2 * kH, i); }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T   (both K-major)
+      constexpr uint32_t idesc_r = make_idesc(128, 80);           // R = Q E^T
+      constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
+      const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ);
+      mbar_wait(bar(tp::EFULL), 0);
+      mbar_wait(bar(tp::QFULL), 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tR, dq + (uint64_t)(2 * k), de + (uint64_t)(2 * k), idesc_r, k != 0);
+      umma_commit(bar(tp::RFULL));
+      // S tile j (j < nkt: pass 1, else pass 2) out of ring slot c
+      auto issue_s = [&](int j, int c) {
+        const int st = c % tp::kSlots, b = j & 1;
+        mbar_wait(bar(tp::KVFULL + st), (c / tp::kSlots) & 1);
+        mbar_wait(bar(tp::SEMPTY + b), ((j >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc(sKV + st * tp::kSlotBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS + (uint32_t)(b * kKT), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
+        umma_commit(bar(tp::SFULL + b));
+        umma_commit(bar(tp::KVEMPTY + st));
+      };
+      // O += P(i) V(i), V in ring slot c
+      auto issue_pv = [&](int i, int c) {
+        const int st = c % tp::kSlots, pb = i & 1;
+        mbar_wait(bar(tp::PFULL + pb), (i >> 1) & 1);
+        mbar_wait(bar(tp::KVFULL + st), (c / tp::kSlots) & 1);
+        tc_fence_after();
+        const uint32_t sv = sKV + st * tp::kSlotBytes;
+#pragma unroll
+        for (int kk = 0; kk < kKT / 16; ++kk) {
+          const uint64_t dp = make_smem_desc(sP + pb * kPBuf) + (uint64_t)(2 * kk);
+          const uint64_t dv = make_smem_desc(sv + kk * 16 * 128);
+          umma_bf16(tO, dp, dv, idesc_o, (i | kk) != 0);
+        }
+        umma_commit(bar(tp::PEMPTY + pb));
+        umma_commit(bar(tp::KVEMPTY + st));
+        if (i == nkt - 1) umma_commit(bar(tp::OFULL));
+      };
+      for (int j = 0; j < nkt; ++j) issue_s(j, j);
+      for (int i = 0; i < nkt; ++i) {
+        issue_s(nkt + i, nkt + 2 * i);
+        if (i > 0) issue_pv(i - 1, nkt + 2 * i - 1);
+      }
+      issue_pv(nkt - 1, 3 * nkt - 1);
+    }
+  } else {
+    // ===== softmax / output warps: thread = (query row = TMEM lane, key slice wg of kKW keys) =====
+    constexpr int kWG = kSoftmaxWarps / 4;          // warps per TMEM lane quadrant
+    constexpr int kKW = kKT / kWG;                  // keys of each S tile handled by one thread
+    constexpr int kDW = kHD / kWG;                  // head dims of the output handled by one thread
+    static_assert(kWG == 2 && kKW == 32 && kDW == 32, "two-pass kernel: 8 softmax warps, 64-key tiles");
+    const int quad = warp & 3;
+    const int wg = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const int qpos = q0 + r;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
+    float* smax = reinterpret_cast<float*>(gbase + AttnSmem::kMax);   // [slot][wg][row]
+    float* ssum = reinterpret_cast<float*>(gbase + AttnSmem::kSum);
+    const __nv_bfloat16* myR = sR + r * 80;
+
+    // R row -> bf16 (the reference's einsum output dtype) -> shared memory; the two warps of a row split the
+    // columns and keep the largest bias of their part
+    stamp();                                        // [1] set-up done
+    mbar_wait(bar(tp::RFULL), 0);
+    stamp();                                        // [2] R ready
+    tc_fence_after();
+    float bmax = -INFINITY;
+    {
+      __nv_bfloat16* rr = sR + r * 80;
+      uint32_t a[32];
+      tmem_ld_32x32_nowait(tR + lane_base + wg * 32, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const __nv_bfloat16 v = __float2bfloat16_rn(__uint_as_float(a[i]));
+        rr[wg * 32 + i] = v;
+        bmax = fmaxf(bmax, __bfloat162float(v));
+      }
+      if (wg == kWG - 1) {
+        uint32_t c[16];
+        tmem_ld_32x32_x16_nowait(tR + lane_base + 64, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const __nv_bfloat16 v = __float2bfloat16_rn(__uint_as_float(c[i]));
+          rr[64 + i] = v;
+          if (64 + i < kRel) bmax = fmaxf(bmax, __bfloat162float(v));
+        }
+      }
+    }
+    tc_fence_before();
+    smax[(0 * kWG + wg) * kQT + r] = bmax;
+    row_barrier<32 * kWG>(quad);                    // every R row is complete, both bias maxima are visible
+    bmax = fmaxf(smax[(0 * kWG + 0) * kQT + r], smax[(0 * kWG + 1) * kQT + r]);
+    const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
+    stamp();                                        // [3] R in shared memory
+
+    // S slice of tile j (running tile counter over both passes) into registers, buffer handed back at once
+    auto load_s = [&](int j, float (&t)[kKW]) {
+      const int b = j & 1;
+      mbar_wait(bar(tp::SFULL + b), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t x[32];
+      tmem_ld_32x32_nowait(tS + lane_base + (uint32_t)(b * kKT + wg * kKW), x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(x[e]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(tp::SEMPTY + b));
+    };
+
+    // ---- pass 1: largest raw score of the row ----
+    float mx = -INFINITY;
+    for (int i = 0; i < nkt; ++i) {
+      const int k0 = i * kKT + wg * kKW;
+      float t[kKW];
+      load_s(i, t);
+      if (k0 + kKW > nkeys) {
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
+      }
+      float m0 = fmaxf(t[0], t[1]), m1 = fmaxf(t[2], t[3]);
+#pragma unroll
+      for (int e = 4; e < kKW; e += 4) { m0 = fmaxf(m0, fmaxf(t[e], t[e + 1])); m1 = fmaxf(m1, fmaxf(t[e + 2], t[e + 3])); }
+      mx = fmaxf(mx, fmaxf(m0, m1));
+      stamp();                                      // [4 + i] pass-1 tile done
+    }
+    smax[(1 * kWG + wg) * kQT + r] = mx;
+    row_barrier<32 * kWG>(quad);
+    mx = fmaxf(smax[(1 * kWG + 0) * kQT + r], smax[(1 * kWG + 1) * kQT + r]);
+    const float m = (mx + bmax) * kScale;           // >= every biased score of this row, log2 domain
+
+    // ---- pass 2: P = 2^(score - m), O += P.V on the tensor core ----
+    float l = 0.f;
+    for (int i = 0; i < nkt; ++i) {
+      const int pb = i & 1, k0 = i * kKT + wg * kKW;
+      float t[kKW];
+      load_s(nkt + i, t);
+      stamp();                                      // [4 + nkt + 3 i] S slice in registers
+      // scores in the log2 domain: (q.k + bias) * log2e/8.  Outside the diagonal band the bias is one constant per
+      // row, so scale, bias and -m fold into a single FMA in front of the exp2.
+      const int dlo = k0 - qpos, dhi = k0 + kKW - 1 - qpos;
+      const bool band = !(dhi <= -kLeft || dlo >= kRight);
+      const float cb = dhi <= -kLeft ? rl : rrt;
+      if (band) {
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) {
+          const int idx = max(-kLeft, min(kRight, dlo + e)) + kLeft;
+          t[e] = t[e] + __bfloat162float(myR[idx]);
+        }
+      }
+      if (k0 + kKW > nkeys) {
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
+      }
+      const float off = (band ? 0.f : cb) - m;                   // p = 2^(raw * kScale + off)
+      mbar_wait(bar(tp::PEMPTY + pb), ((i >> 1) & 1) ^ 1u);
+      stamp();                                      // [.. + 1] P buffer free
+      float ls0 = 0.f, ls1 = 0.f;
+      const int kcol = wg * kKW;                                   // key column within the tile
+      uint8_t* half = gbase + AttnSmem::kP + pb * kPBuf + r * 128;
+      const int ch0 = kcol >> 3;
+#pragma unroll
+      for (int ch = 0; ch < kKW / 8; ++ch) {
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pv[e] = ex2a(fmaf(t[ch * 8 + e], kScale, off));
+        ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+        ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+        uint4 v;
+        v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]);
+        v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);
+        *reinterpret_cast<uint4*>(half + (((ch0 + ch) ^ (r & 7)) << 4)) = v;
+      }
+      l += ls0 + ls1;
+      fence_proxy_async();          // P visible to the tensor core (generic -> async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(tp::PFULL + pb));
+      stamp();                                      // [.. + 2] P handed over
+    }
+
+    // ---- output: O / l ----
+    ssum[wg * kQT + r] = l;
+    row_barrier<32 * kWG>(quad);
+    l = ssum[0 * kQT + r] + ssum[1 * kQT + r];
+    mbar_wait(bar(tp::OFULL), 0);
+    stamp();                                        // O complete
+    tc_fence_after();
+    uint32_t x[kDW];
+    tmem_ld_32x32_nowait(tO + lane_base + (uint32_t)(wg * kDW), x);
+    tmem_ld_wait();
+    tc_fence_before();
+    if (qpos < rows) {
+      const float inv = 1.0f / l;
+      // one row per lane: 256-bit stores write whole 32-byte sectors
+      __nv_bfloat16* dst = out + (size_t)(r0 + qpos) * kH + head * kHD + wg * kDW;
+#pragma unroll
+      for (int ch = 0; ch < kDW / 16; ++ch) {
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          w[e] = pack_bf16x2(__uint_as_float(x[ch * 16 + 2 * e]) * inv, __uint_as_float(x[ch * 16 + 2 * e + 1]) * inv);
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"l"(dst + 16 * ch), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+      }
+    }
+    stamp();                                        // output stored
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+  stamp();                                          // CTA done
+}
+#endif  // !B2T_ATTN_WIDE
+
 }  // namespace
 
 int g_attn_heads_per_cta = 1;   // kept for the option plumbing; the kernel needs 1 (E and R borrow per-head buffers)
+long long* g_attn_dbg = nullptr;   // b2t_attention_set_dbg(device buffer of 128 int64): developer timeline
+extern "C" void b2t_attention_set_dbg(long long* p) { g_attn_dbg = p; }
+int g_attn_two_pass = 1;        // b2t_set_option("attn_two_pass", 0/1): fixed-maximum two-pass kernel vs online softmax
 
 // host entry used by b2t_relkey_attention (attention.cu)
 int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, cudaStream_t st) {
@@ -390,6 +705,19 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
   }
   const int hpc = 1;
   dim3 grid(b->n_qtiles128, kHeads / hpc);
+#if !B2T_ATTN_WIDE
+  if (g_attn_two_pass) {
+    static bool cfg2 = false;
+    if (!cfg2) {
+      B2T_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal));
+      cfg2 = true;
+    }
+    attention_tc2_kernel<<<grid, kThreadsAttn, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
+                                                                      b->qtile128_q0, (__nv_bfloat16*)out, g_attn_dbg);
+    B2T_LAUNCH_CHECK();
+    return B2T_OK;
+  }
+#endif
   attention_tc_kernel<<<grid, kThreadsAttn, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
                                                                    b->qtile128_q0, (__nv_bfloat16*)out, hpc);
   B2T_LAUNCH_CHECK();
