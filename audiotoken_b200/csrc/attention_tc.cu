@@ -408,7 +408,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   // timeline: CTA (300, 5) — a mid-grid CTA so that both CTAs of the SM are in steady state; stamps of warp 2 lane 0
   const bool tl = dbg != nullptr && blockIdx.x == 300 && blockIdx.y == 5 && threadIdx.x == 64;
   int tln = 0;
+#ifdef B2T_ATTN_TIMELINE
   auto stamp = [&]() { if (tl && tln < 128) dbg[tln++] = clock64(); };
+#else
+  auto stamp = [&]() { (void)tl; (void)tln; };
+#endif
   stamp();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -436,73 +440,99 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   // S double buffer [0,128); O accumulator [128,192); R (80 columns) borrows the O region until the first PV MMA
   const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT, tR = tmem_base + 2 * kKT;
 
+  // Ring position p (0 .. 3 nkt - 1): K tiles of pass 1, then K(0) V(0) K(1) V(1) ...; slot p & 3, use count p >> 2.
+  // The two single-thread instruction streams that feed the tensor core run in DIFFERENT warps: warp 1 issues the
+  // S MMAs, warp 0 the TMA loads and the PV MMAs.  One warp doing all of it was the critical path of the kernel
+  // (clock64 timeline: ~1500 clocks of issue latency per key tile against ~900 clocks of softmax work).
   if (warp == 0) {
-    // ===== TMA producer: slot counter c runs over pass-1 K tiles, then (K, V) pairs of pass 2 =====
-    if (lane == 0) {
+    // ===== TMA producer + PV issuer: whole warp polls (uniform control flow), one elected lane issues =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
+    const uint64_t dkv = make_smem_desc(sKV), dp0 = make_smem_desc(sP);
+    if (leader) {
       mbar_expect_tx(bar(tp::EFULL), 80 * 128);
       tma_load_2d(sE, &map_e, bar(tp::EFULL), 0, 0);
       mbar_expect_tx(bar(tp::QFULL), kQT * 128);
       tma_load_2d(sQ, &map_qkv, bar(tp::QFULL), head * kHD, r0 + q0);
-      int c = 0;
-      auto load_slot = [&](int col, int i) {
-        const int st = c % tp::kSlots;
-        mbar_wait(bar(tp::KVEMPTY + st), ((c / tp::kSlots) & 1) ^ 1u);
-        mbar_expect_tx(bar(tp::KVFULL + st), tp::kSlotBytes);
-        tma_load_2d(sKV + st * tp::kSlotBytes, &map_kv, bar(tp::KVFULL + st), col + head * kHD, r0 + i * kKT);
-        ++c;
-      };
-      for (int i = 0; i < nkt; ++i) load_slot(kH, i);
-      for (int i = 0; i < nkt; ++i) { load_slot(kH, i); load_slot(2 * kH, i); }
     }
+    const int total = 3 * nkt;
+    int c = 0, ip = 0;                              // next ring position to load, next PV
+    uint32_t idle = 0;                              // bounded polling: a protocol bug traps instead of hanging the GPU
+    while (c < total || ip < nkt) {
+      if (++idle > (1u << 26)) __trap();
+      if (c < total) {
+        const uint32_t st = (uint32_t)c & 3u;
+        if (mbar_test_wait(bar(tp::KVEMPTY) + 8u * st, (((uint32_t)c >> 2) & 1u) ^ 1u)) {
+          const int t2 = c - nkt;
+          const int tile = t2 < 0 ? c : (t2 >> 1);
+          const int col = (t2 >= 0 && (t2 & 1)) ? 2 * kH : kH;
+          if (leader) {
+            mbar_expect_tx(bar(tp::KVFULL) + 8u * st, tp::kSlotBytes);
+            tma_load_2d(sKV + st * tp::kSlotBytes, &map_kv, bar(tp::KVFULL) + 8u * st, col + head * kHD, r0 + tile * kKT);
+          }
+          ++c;
+          idle = 0;
+        }
+      }
+      if (ip < nkt) {
+        const uint32_t pb = (uint32_t)ip & 1u, pos = (uint32_t)(nkt + 2 * ip + 1), st = pos & 3u;
+        bool ok = mbar_test_wait(bar(tp::PFULL) + 8u * pb, ((uint32_t)ip >> 1) & 1u);
+        ok &= mbar_test_wait(bar(tp::KVFULL) + 8u * st, (pos >> 2) & 1u);
+        if (ok) {
+          tc_fence_after();
+          if (leader) {
+            const uint64_t dv = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4)), dp = dp0 + (uint64_t)(pb * (kPBuf >> 4));
+#pragma unroll
+            for (int kk = 0; kk < kKT / 16; ++kk)
+              umma_bf16(tO, dp + (uint64_t)(2 * kk), dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o, (ip | kk) != 0);
+            umma_commit(bar(tp::PEMPTY) + 8u * pb);
+            umma_commit(bar(tp::KVEMPTY) + 8u * st);
+            if (ip == nkt - 1) umma_commit(bar(tp::OFULL));
+          }
+          ++ip;
+          idle = 0;
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T   (both K-major)
-      constexpr uint32_t idesc_r = make_idesc(128, 80);           // R = Q E^T
-      constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
-      const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ);
-      mbar_wait(bar(tp::EFULL), 0);
-      mbar_wait(bar(tp::QFULL), 0);
-      tc_fence_after();
+    // ===== S issuer (whole warp waits, one elected lane issues) =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T   (both K-major)
+    constexpr uint32_t idesc_r = make_idesc(128, 80);           // R = Q E^T
+    const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ), dkv = make_smem_desc(sKV);
+    mbar_wait(bar(tp::EFULL), 0);
+    mbar_wait(bar(tp::QFULL), 0);
+    tc_fence_after();
+    if (leader) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16(tR, dq + (uint64_t)(2 * k), de + (uint64_t)(2 * k), idesc_r, k != 0);
       umma_commit(bar(tp::RFULL));
-      // S tile j (j < nkt: pass 1, else pass 2) out of ring slot c
-      auto issue_s = [&](int j, int c) {
-        const int st = c % tp::kSlots, b = j & 1;
-        mbar_wait(bar(tp::KVFULL + st), (c / tp::kSlots) & 1);
-        mbar_wait(bar(tp::SEMPTY + b), ((j >> 1) & 1) ^ 1u);
-        tc_fence_after();
-        const uint64_t dk = make_smem_desc(sKV + st * tp::kSlotBytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tS + (uint32_t)(b * kKT), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
-        umma_commit(bar(tp::SFULL + b));
-        umma_commit(bar(tp::KVEMPTY + st));
-      };
-      // O += P(i) V(i), V in ring slot c
-      auto issue_pv = [&](int i, int c) {
-        const int st = c % tp::kSlots, pb = i & 1;
-        mbar_wait(bar(tp::PFULL + pb), (i >> 1) & 1);
-        mbar_wait(bar(tp::KVFULL + st), (c / tp::kSlots) & 1);
-        tc_fence_after();
-        const uint32_t sv = sKV + st * tp::kSlotBytes;
-#pragma unroll
-        for (int kk = 0; kk < kKT / 16; ++kk) {
-          const uint64_t dp = make_smem_desc(sP + pb * kPBuf) + (uint64_t)(2 * kk);
-          const uint64_t dv = make_smem_desc(sv + kk * 16 * 128);
-          umma_bf16(tO, dp, dv, idesc_o, (i | kk) != 0);
-        }
-        umma_commit(bar(tp::PEMPTY + pb));
-        umma_commit(bar(tp::KVEMPTY + st));
-        if (i == nkt - 1) umma_commit(bar(tp::OFULL));
-      };
-      for (int j = 0; j < nkt; ++j) issue_s(j, j);
-      for (int i = 0; i < nkt; ++i) {
-        issue_s(nkt + i, nkt + 2 * i);
-        if (i > 0) issue_pv(i - 1, nkt + 2 * i - 1);
-      }
-      issue_pv(nkt - 1, 3 * nkt - 1);
     }
+    // S tile j (j < nkt: pass 1, else pass 2) from ring position pos
+    auto issue_s = [&](uint32_t j, uint32_t pos) {
+      const uint32_t b = j & 1u, st = pos & 3u;
+      const uint32_t bk = bar(tp::KVFULL) + 8u * st, bs = bar(tp::SEMPTY) + 8u * b;
+      const uint32_t pk = (pos >> 2) & 1u, ps = ((j >> 1) & 1u) ^ 1u;
+      uint32_t spins = 0;
+      for (;;) {                                    // both probes in flight together
+        bool ok = mbar_try_wait(bk, pk);
+        ok &= mbar_try_wait(bs, ps);
+        if (ok) break;
+        if (++spins > (1u << 26)) __trap();
+      }
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dk = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS + b * kKT, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
+        umma_commit(bar(tp::SFULL) + 8u * b);
+        umma_commit(bar(tp::KVEMPTY) + 8u * st);
+      }
+    };
+    for (int j = 0; j < nkt; ++j) issue_s((uint32_t)j, (uint32_t)j);
+    for (int i = 0; i < nkt; ++i) issue_s((uint32_t)(nkt + i), (uint32_t)(nkt + 2 * i));
+    __syncwarp();
   } else {
     // ===== softmax / output warps: thread = (query row = TMEM lane, key slice wg of kKW keys) =====
     constexpr int kWG = kSoftmaxWarps / 4;          // warps per TMEM lane quadrant

@@ -30,6 +30,16 @@ B2T_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time before it reports failure)
+B2T_DEVICE bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (-> launch failure reported by the host) instead of hanging
 // the GPU box.  2^26 probes of a hardware-sleeping try_wait is seconds, far beyond any real wait.
 B2T_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -37,6 +47,18 @@ B2T_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
   }
+}
+// One lane of a CONVERGED warp.  Code guarded by this predicate inside warp-uniform control flow lets ptxas issue
+// tcgen05.mma / tcgen05.commit / TMA loads straight from the uniform datapath; `if (lane == 0)` around a whole loop
+// makes the region divergent and every such instruction is wrapped in an elect-and-retry loop with R2UR copies.
+B2T_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 B2T_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 B2T_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_pipeline.py -m gpu -q -p no:cacheprovider -k "not fp32" -s > gpurun_out/p_rest2.log 2>&1; echo "p_rest exit=$?"; grep -i "rel\|agree\|passed\|failed\|error" gpurun_out/p_rest2.log | cut -c1-300 | tail -30
+timeout 120 python tools/attn_sweep.py > gpurun_out/attn_sweep4.log 2>&1; echo "sweep exit=$?"; tail -16 gpurun_out/attn_sweep4.log
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider -k "attention" > gpurun_out/k_attn4.log 2>&1; echo "k_attn exit=$?"; tail -3 gpurun_out/k_attn4.log
