@@ -268,47 +268,55 @@ seanet_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Producer and MMA warps run their loops warp-wide (uniform control flow) and let one elected lane issue: inside an
+  // `if (lane == 0)` region ptxas wraps every TMA / tcgen05 instruction in an elect-and-retry loop with R2UR copies,
+  // and for the narrow convolutions (a handful of MMAs per tile) that issue latency was a large part of a tile.
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      bool waited = !pdl;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (!waited && kb >= kb0) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    bool waited = !pdl;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (!waited && kb >= kb0) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (leader) {
           mbar_expect_tx(full_bar(stage), L::kStageA + L::kStageB);
           if (kb < kb0) tma_load_2d(sA + stage * L::kStageA, &map_a0, full_bar(stage), kb * kBK, row0 + m0);
           else tma_load_2d(sA + stage * L::kStageA, &map_a1, full_bar(stage), (kb - kb0) * kBK, row1 + m0);
           tma_load_2d(sB + stage * L::kStageB, &map_w, full_bar(stage), kb * kBK, n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(kBM, BN);
+    const uint64_t da0 = make_smem_desc(sA), db0 = make_smem_desc(sB);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint64_t da = make_smem_desc(sA + stage * L::kStageA);
-          const uint64_t db = make_smem_desc(sB + stage * L::kStageB);
+        if (leader) {
+          const uint64_t da = da0 + (uint64_t)(stage * (L::kStageA >> 4));
+          const uint64_t db = db0 + (uint64_t)(stage * (L::kStageB >> 4));
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    __syncwarp();
   } else {
     // epilogue: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the columns when BN >= 32
     const int quad = warp & 3;
