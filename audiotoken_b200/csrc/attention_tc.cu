@@ -391,7 +391,14 @@ static_assert(COUNT * 8 + 8 <= 256, "barrier area");
 static_assert(kSlots * kSlotBytes == kStages * 2 * kKT * 128, "the slot ring reuses the K/V stage area");
 }  // namespace tp
 
-__global__ void __launch_bounds__(kThreadsAttn, kCtasPerSm)
+// kOnesSum: the row sums come from the tensor core as well — a second accumulator L += P . 1 (N = 16 MMAs against a
+//           constant [16 keys x 16] block whose first column is one), i.e. the sum of exactly the bf16 values that
+//           enter P.V; removes 32 FADD per thread and tile and the cross-warp sum exchange.
+//           Measured SLOWER (404 vs 437 TFLOP/s on 30 s clips): the four extra MMAs lengthen the PV issue stream,
+//           which is worth more than the 32 FADD they save in the (parallel) softmax warps.  Kept as an option.
+constexpr int kThreadsAttn2 = 96 + 32 * kSoftmaxWarps;          // TMA, S-issue and PV-issue warps + softmax warps
+template <bool kOnesSum>
+__global__ void __launch_bounds__(kThreadsAttn2, kCtasPerSm)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ CUtensorMap map_e,
                      const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
@@ -406,7 +413,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + AttnSmem::kBars + 8 * tp::COUNT);
   // timeline: CTA (300, 5) — a mid-grid CTA so that both CTAs of the SM are in steady state; stamps of warp 2 lane 0
-  const bool tl = dbg != nullptr && blockIdx.x == 300 && blockIdx.y == 5 && threadIdx.x == 64;
+  const bool tl = dbg != nullptr && blockIdx.x == 300 && blockIdx.y == 5 && threadIdx.x == 96;
   int tln = 0;
 #ifdef B2T_ATTN_TIMELINE
   auto stamp = [&]() { if (tl && tln < 128) dbg[tln++] = clock64(); };
@@ -439,16 +446,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   const uint32_t tmem_base = *tmem_slot_ptr;
   // S double buffer [0,128); O accumulator [128,192); R (80 columns) borrows the O region until the first PV MMA
   const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT, tR = tmem_base + 2 * kKT;
+  const uint32_t tL = tmem_base + 2 * kKT + kHD;   // [192,208): row sums (column 0), kOnesSum only
+  const uint32_t sOnes = base + AttnSmem::kMax + 2048;          // 2 KB, 1024-aligned, behind the max exchange slots
 
   // Ring position p (0 .. 3 nkt - 1): K tiles of pass 1, then K(0) V(0) K(1) V(1) ...; slot p & 3, use count p >> 2.
-  // The two single-thread instruction streams that feed the tensor core run in DIFFERENT warps: warp 1 issues the
-  // S MMAs, warp 0 the TMA loads and the PV MMAs.  One warp doing all of it was the critical path of the kernel
-  // (clock64 timeline: ~1500 clocks of issue latency per key tile against ~900 clocks of softmax work).
+  // The three single-thread instruction streams that feed the tensor core run in DIFFERENT warps: warp 0 issues the
+  // TMA loads, warp 1 the S MMAs, warp 2 the PV MMAs.  One warp doing all of it was the critical path of the kernel
+  // (clock64 timeline: ~1500 clocks of issue latency per key tile against ~900 clocks of softmax work); every
+  // instruction added to one of these streams still shows up in the kernel time.
   if (warp == 0) {
-    // ===== TMA producer + PV issuer: whole warp polls (uniform control flow), one elected lane issues =====
+    // ===== TMA producer: whole warp waits (uniform control flow), one elected lane issues =====
     const bool leader = elect_one();
-    constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
-    const uint64_t dkv = make_smem_desc(sKV), dp0 = make_smem_desc(sP);
     if (leader) {
       mbar_expect_tx(bar(tp::EFULL), 80 * 128);
       tma_load_2d(sE, &map_e, bar(tp::EFULL), 0, 0);
@@ -456,42 +464,48 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       tma_load_2d(sQ, &map_qkv, bar(tp::QFULL), head * kHD, r0 + q0);
     }
     const int total = 3 * nkt;
-    int c = 0, ip = 0;                              // next ring position to load, next PV
-    uint32_t idle = 0;                              // bounded polling: a protocol bug traps instead of hanging the GPU
-    while (c < total || ip < nkt) {
-      if (++idle > (1u << 26)) __trap();
-      if (c < total) {
-        const uint32_t st = (uint32_t)c & 3u;
-        if (mbar_test_wait(bar(tp::KVEMPTY) + 8u * st, (((uint32_t)c >> 2) & 1u) ^ 1u)) {
-          const int t2 = c - nkt;
-          const int tile = t2 < 0 ? c : (t2 >> 1);
-          const int col = (t2 >= 0 && (t2 & 1)) ? 2 * kH : kH;
-          if (leader) {
-            mbar_expect_tx(bar(tp::KVFULL) + 8u * st, tp::kSlotBytes);
-            tma_load_2d(sKV + st * tp::kSlotBytes, &map_kv, bar(tp::KVFULL) + 8u * st, col + head * kHD, r0 + tile * kKT);
-          }
-          ++c;
-          idle = 0;
-        }
+    for (int c = 0; c < total; ++c) {
+      const uint32_t st = (uint32_t)c & 3u;
+      const int t2 = c - nkt;
+      const int tile = t2 < 0 ? c : (t2 >> 1);
+      const int col = (t2 >= 0 && (t2 & 1)) ? 2 * kH : kH;
+      mbar_wait(bar(tp::KVEMPTY) + 8u * st, (((uint32_t)c >> 2) & 1u) ^ 1u);
+      if (leader) {
+        mbar_expect_tx(bar(tp::KVFULL) + 8u * st, tp::kSlotBytes);
+        tma_load_2d(sKV + st * tp::kSlotBytes, &map_kv, bar(tp::KVFULL) + 8u * st, col + head * kHD, r0 + tile * kKT);
       }
-      if (ip < nkt) {
-        const uint32_t pb = (uint32_t)ip & 1u, pos = (uint32_t)(nkt + 2 * ip + 1), st = pos & 3u;
-        bool ok = mbar_test_wait(bar(tp::PFULL) + 8u * pb, ((uint32_t)ip >> 1) & 1u);
-        ok &= mbar_test_wait(bar(tp::KVFULL) + 8u * st, (pos >> 2) & 1u);
-        if (ok) {
-          tc_fence_after();
-          if (leader) {
-            const uint64_t dv = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4)), dp = dp0 + (uint64_t)(pb * (kPBuf >> 4));
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ===== PV issuer =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
+    constexpr uint32_t idesc_l = make_idesc(128, 16, 1);        // L += P 1
+    const uint64_t dkv = make_smem_desc(sKV), dp0 = make_smem_desc(sP), dones = make_smem_desc(sOnes);
+    for (int ip = 0; ip < nkt; ++ip) {
+      const uint32_t pb = (uint32_t)ip & 1u, pos = (uint32_t)(nkt + 2 * ip + 1), st = pos & 3u;
+      const uint32_t bp = bar(tp::PFULL) + 8u * pb, bv = bar(tp::KVFULL) + 8u * st;
+      const uint32_t pp = ((uint32_t)ip >> 1) & 1u, pv = (pos >> 2) & 1u;
+      uint32_t spins = 0;
+      for (;;) {                                      // both probes in flight together
+        bool ok = mbar_try_wait(bp, pp);
+        ok &= mbar_try_wait(bv, pv);
+        if (ok) break;
+        if (++spins > (1u << 26)) __trap();
+      }
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dv = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4)), dp = dp0 + (uint64_t)(pb * (kPBuf >> 4));
 #pragma unroll
-            for (int kk = 0; kk < kKT / 16; ++kk)
-              umma_bf16(tO, dp + (uint64_t)(2 * kk), dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o, (ip | kk) != 0);
-            umma_commit(bar(tp::PEMPTY) + 8u * pb);
-            umma_commit(bar(tp::KVEMPTY) + 8u * st);
-            if (ip == nkt - 1) umma_commit(bar(tp::OFULL));
-          }
-          ++ip;
-          idle = 0;
+        for (int kk = 0; kk < kKT / 16; ++kk)
+          umma_bf16(tO, dp + (uint64_t)(2 * kk), dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o, (ip | kk) != 0);
+        if constexpr (kOnesSum) {
+#pragma unroll
+          for (int kk = 0; kk < kKT / 16; ++kk) umma_bf16(tL, dp + (uint64_t)(2 * kk), dones, idesc_l, (ip | kk) != 0);
         }
+        umma_commit(bar(tp::PEMPTY) + 8u * pb);
+        umma_commit(bar(tp::KVEMPTY) + 8u * st);
+        if (ip == nkt - 1) umma_commit(bar(tp::OFULL));
       }
     }
     __syncwarp();
@@ -540,7 +554,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     constexpr int kDW = kHD / kWG;                  // head dims of the output handled by one thread
     static_assert(kWG == 2 && kKW == 32 && kDW == 32, "two-pass kernel: 8 softmax warps, 64-key tiles");
     const int quad = warp & 3;
-    const int wg = (warp - 2) >> 2;
+    const int wg = (warp - 3) >> 2;
     const int r = quad * 32 + lane;
     const int qpos = q0 + r;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -581,6 +595,18 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     }
     tc_fence_before();
     smax[(0 * kWG + wg) * kQT + r] = bmax;
+    if constexpr (kOnesSum) {
+      // [16 keys x 64] bf16 block in the MN-major SWIZZLE_128B layout of a V tile: element (key k, n = 0) = 1.
+      // Written long before the first PV MMA; every writer's fence.proxy.async in front of its first PFULL arrival
+      // publishes it to the tensor core.
+      uint32_t* ob = reinterpret_cast<uint32_t*>(gbase + AttnSmem::kMax + 2048);
+      const int tid = threadIdx.x - 96;             // 0 .. 255: 2 of the 512 words each
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int w = 2 * tid + j;                  // key row w >> 5; (k, n = 0) sits in chunk (0 ^ (k & 7)) of its row
+        ob[w] = ((w & 31) == (((w >> 5) & 7) << 2)) ? 0x00003F80u : 0u;
+      }
+    }
     row_barrier<32 * kWG>(quad);                    // every R row is complete, both bias maxima are visible
     bmax = fmaxf(smax[(0 * kWG + 0) * kQT + r], smax[(0 * kWG + 1) * kQT + r]);
     const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
@@ -646,24 +672,27 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
       }
       const float off = (band ? 0.f : cb) - m;                   // p = 2^(raw * kScale + off)
-      mbar_wait(bar(tp::PEMPTY + pb), ((i >> 1) & 1) ^ 1u);
-      stamp();                                      // [.. + 1] P buffer free
       float ls0 = 0.f, ls1 = 0.f;
       const int kcol = wg * kKW;                                   // key column within the tile
       uint8_t* half = gbase + AttnSmem::kP + pb * kPBuf + r * 128;
       const int ch0 = kcol >> 3;
+      uint4 v[kKW / 8];                                            // the whole slice first, the buffer wait as late as possible
 #pragma unroll
       for (int ch = 0; ch < kKW / 8; ++ch) {
         float pv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) pv[e] = ex2a(fmaf(t[ch * 8 + e], kScale, off));
-        ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-        ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-        uint4 v;
-        v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]);
-        v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);
-        *reinterpret_cast<uint4*>(half + (((ch0 + ch) ^ (r & 7)) << 4)) = v;
+        if constexpr (!kOnesSum) {
+          ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+          ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+        }
+        v[ch].x = pack_bf16x2(pv[0], pv[1]); v[ch].y = pack_bf16x2(pv[2], pv[3]);
+        v[ch].z = pack_bf16x2(pv[4], pv[5]); v[ch].w = pack_bf16x2(pv[6], pv[7]);
       }
+      mbar_wait(bar(tp::PEMPTY + pb), ((i >> 1) & 1) ^ 1u);
+      stamp();                                      // [.. + 1] P buffer free
+#pragma unroll
+      for (int ch = 0; ch < kKW / 8; ++ch) *reinterpret_cast<uint4*>(half + (((ch0 + ch) ^ (r & 7)) << 4)) = v[ch];
       l += ls0 + ls1;
       fence_proxy_async();          // P visible to the tensor core (generic -> async proxy)
       __syncwarp();
@@ -672,14 +701,22 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     }
 
     // ---- output: O / l ----
-    ssum[wg * kQT + r] = l;
-    row_barrier<32 * kWG>(quad);
-    l = ssum[0 * kQT + r] + ssum[1 * kQT + r];
+    if constexpr (!kOnesSum) {
+      ssum[wg * kQT + r] = l;
+      row_barrier<32 * kWG>(quad);
+      l = ssum[0 * kQT + r] + ssum[1 * kQT + r];
+    }
     mbar_wait(bar(tp::OFULL), 0);
     stamp();                                        // O complete
     tc_fence_after();
     uint32_t x[kDW];
     tmem_ld_32x32_nowait(tO + lane_base + (uint32_t)(wg * kDW), x);
+    if constexpr (kOnesSum) {
+      uint32_t ls[16];
+      tmem_ld_32x32_x16_nowait(tL + lane_base, ls);
+      tmem_ld_wait();
+      l = __uint_as_float(ls[0]);
+    }
     tmem_ld_wait();
     tc_fence_before();
     if (qpos < rows) {
@@ -737,13 +774,16 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
   dim3 grid(b->n_qtiles128, kHeads / hpc);
 #if !B2T_ATTN_WIDE
   if (g_attn_two_pass) {
+    // g_attn_two_pass bits: 1 = two-pass, 4 = row sums on the tensor core as well
     static bool cfg2 = false;
     if (!cfg2) {
-      B2T_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal));
+      B2T_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal));
+      B2T_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal));
       cfg2 = true;
     }
-    attention_tc2_kernel<<<grid, kThreadsAttn, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
-                                                                      b->qtile128_q0, (__nv_bfloat16*)out, g_attn_dbg);
+    auto kern = (g_attn_two_pass & 4) ? attention_tc2_kernel<true> : attention_tc2_kernel<false>;
+    kern<<<grid, kThreadsAttn2, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip, b->qtile128_q0,
+                                                       (__nv_bfloat16*)out, g_attn_dbg);
     B2T_LAUNCH_CHECK();
     return B2T_OK;
   }

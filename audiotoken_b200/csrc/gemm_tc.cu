@@ -483,7 +483,7 @@ extern "C" int b2t_set_option(const char* name, int value) {
   if (std::string(name) == "seanet_sub_frames") { b2t_seanet_set_sub_frames(value); return B2T_OK; }
   if (std::string(name) == "rvq_dbg") { g_rvq_dbg = value; return B2T_OK; }
   if (std::string(name) == "rvq_tensor") { g_rvq_tensor = value != 0; return B2T_OK; }
-  if (std::string(name) == "attn_two_pass") { g_attn_two_pass = value != 0; return B2T_OK; }
+  if (std::string(name) == "attn_two_pass") { g_attn_two_pass = value; return B2T_OK; }
   if (std::string(name) == "attn_heads_per_cta") {
     B2T_REQUIRE(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, B2T_ERR_ARG, "attn_heads_per_cta must divide 16");
     g_attn_heads_per_cta = value;
