@@ -42,13 +42,15 @@ constexpr int kThreadsAttn = 64 + 32 * kSoftmaxWarps;
 // Two CTAs are resident per SM (<= 113 KB shared memory, 256 TMEM columns, 320 threads each): while one CTA
 // sits in a TMEM-load / barrier / proxy-fence latency the other one computes — the two softmax pipelines
 // interleave without any explicit ping-pong protocol.
+constexpr int kRS = 82;                          // row stride of the R tile in shared memory (bf16 elements)
 struct AttnSmem {
   static constexpr int kQ = 0;                                  // 16 KB
   static constexpr int kKV = kQ + kQT * 128;                    // kStages x (K 8 KB + V 8 KB)
   static constexpr int kP = kKV + kStages * 2 * kKT * 128;      // 2 P buffers; buffer 1 first stages E (80 x 128 B)
   static constexpr int kE = kP + kPBuf;                         // = P buffer 1 (E is dead once R has been computed)
-  static constexpr int kR = kP + 2 * kPBuf;                     // [128][80] bf16 = 20 KB
-  static constexpr int kMax = kR + kQT * 80 * 2;                // row-max exchange [2 slots][kWG][128] fp32
+  static constexpr int kR = kP + 2 * kPBuf;                     // [128][kRS] bf16: rows 41 words apart, so that a warp's per-row
+                                                                // accesses (lane = row) spread over all 32 banks (80 gave 8-way conflicts)
+  static constexpr int kMax = (kR + kQT * kRS * 2 + 1023) & ~1023;   // row-max exchange [2 slots][kWG][128] fp32 (+ the ones block)
   static constexpr int kSum = kMax + 2 * 4 * kQT * 4;           // final row-sum exchange [kWG][128] fp32
   static constexpr int kBars = kSum + 4 * kQT * 4;
   static constexpr int kTotal = kBars + 256 + 1024;
@@ -216,7 +218,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
     float* smax = reinterpret_cast<float*>(gbase + AttnSmem::kMax);   // [slot][wg][row]
     float* ssum = reinterpret_cast<float*>(gbase + AttnSmem::kSum);
-    const __nv_bfloat16* myR = sR + r * 80;
+    const __nv_bfloat16* myR = sR + r * kRS;
 
     float corr_prev = 1.f;
     float o[kDW];
@@ -240,7 +242,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       mbar_wait(bar(B_RFULL), h & 1);
       tc_fence_after();
       {
-        __nv_bfloat16* rr = sR + r * 80;
+        __nv_bfloat16* rr = sR + r * kRS;
         if (wg < 2) {
           uint32_t a[32];
           tmem_ld_32x32_nowait(tR + lane_base + wg * 32, a);
@@ -561,7 +563,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
     float* smax = reinterpret_cast<float*>(gbase + AttnSmem::kMax);   // [slot][wg][row]
     float* ssum = reinterpret_cast<float*>(gbase + AttnSmem::kSum);
-    const __nv_bfloat16* myR = sR + r * 80;
+    const __nv_bfloat16* myR = sR + r * kRS;
 
     // R row -> bf16 (the reference's einsum output dtype) -> shared memory; the two warps of a row split the
     // columns and keep the largest bias of their part
@@ -571,25 +573,26 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     tc_fence_after();
     float bmax = -INFINITY;
     {
-      __nv_bfloat16* rr = sR + r * 80;
+      uint32_t* rr = reinterpret_cast<uint32_t*>(sR + r * kRS);     // bf16 pairs, 4-byte aligned (kRS is even)
       uint32_t a[32];
       tmem_ld_32x32_nowait(tR + lane_base + wg * 32, a);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const __nv_bfloat16 v = __float2bfloat16_rn(__uint_as_float(a[i]));
-        rr[wg * 32 + i] = v;
-        bmax = fmaxf(bmax, __bfloat162float(v));
+      for (int i = 0; i < 32; i += 2) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+        rr[(wg * 32 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&v);
+        bmax = fmaxf(bmax, fmaxf(__low2float(v), __high2float(v)));
       }
       if (wg == kWG - 1) {
         uint32_t c[16];
         tmem_ld_32x32_x16_nowait(tR + lane_base + 64, c);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const __nv_bfloat16 v = __float2bfloat16_rn(__uint_as_float(c[i]));
-          rr[64 + i] = v;
-          if (64 + i < kRel) bmax = fmaxf(bmax, __bfloat162float(v));
+        for (int i = 0; i < 16; i += 2) {
+          const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(c[i]), __uint_as_float(c[i + 1]));
+          rr[(64 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&v);
+          if (64 + i < kRel) bmax = fmaxf(bmax, __low2float(v));
+          if (64 + i + 1 < kRel) bmax = fmaxf(bmax, __high2float(v));
         }
       }
     }

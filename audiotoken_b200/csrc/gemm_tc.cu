@@ -471,6 +471,7 @@ extern bool g_rvq_tensor;          // acoustic.cu
 extern int g_rvq_dbg;              // rvq_tc.cu
 void b2t_seanet_set_sub_frames(int n);   // seanet_tc.cu
 void b2t_seanet_set_lstm_pdl(int on);
+void b2t_seanet_set_lstm_overlap(int on);
 void b2t_seanet_set_l0_fused(int on);
 extern bool g_dwconv_ring;         // dwconv.cu
 
@@ -480,6 +481,7 @@ extern "C" int b2t_set_option(const char* name, int value) {
   if (std::string(name) == "dwconv_ring") { g_dwconv_ring = value != 0; return B2T_OK; }
   if (std::string(name) == "seanet_l0_fused") { b2t_seanet_set_l0_fused(value); return B2T_OK; }
   if (std::string(name) == "lstm_pdl") { b2t_seanet_set_lstm_pdl(value); return B2T_OK; }
+  if (std::string(name) == "lstm_overlap") { b2t_seanet_set_lstm_overlap(value); return B2T_OK; }
   if (std::string(name) == "seanet_sub_frames") { b2t_seanet_set_sub_frames(value); return B2T_OK; }
   if (std::string(name) == "rvq_dbg") { g_rvq_dbg = value; return B2T_OK; }
   if (std::string(name) == "rvq_tensor") { g_rvq_tensor = value != 0; return B2T_OK; }

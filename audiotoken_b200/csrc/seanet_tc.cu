@@ -828,7 +828,7 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 struct TcWs {
   __nv_bfloat16* xe[4]; __nv_bfloat16* xh[4]; __nv_bfloat16* ye[4];   // sub-batch buffers (point past the guard)
   __nv_bfloat16* x4t; __nv_bfloat16* s1t; __nv_bfloat16* h2t; __nv_bfloat16* s2e;
-  float* emb; float* c;
+  float* emb; float* c; float* c2;              // c / c2: cell state of LSTM layer 1 / 2
   size_t total;
 };
 
@@ -853,6 +853,7 @@ TcWs tc_carve(void* base, long long sub_frames, int sub_clips, long long total4,
   w.s2e = s ? (__nv_bfloat16*)s + (size_t)kGuard * 512 : nullptr;
   w.emb = (float*)take((size_t)total4 * 128 * 4);
   w.c = (float*)take((size_t)n_clips * 512 * 4);
+  w.c2 = (float*)take((size_t)n_clips * 512 * 4);
   w.total = off;
   return w;
 }
@@ -861,6 +862,7 @@ TcWs tc_carve(void* base, long long sub_frames, int sub_clips, long long total4,
 long long* g_l0_dbg = nullptr;    // b2t_seanet_set_l0_dbg(device buffer of 64 x 8 int64) — developer timeline
 int g_l0_fused = 1;               // b2t_set_option("seanet_l0_fused", 0/1)
 int g_lstm_pdl = 1;               // b2t_set_option("lstm_pdl", 0/1)
+int g_lstm_overlap = 1;           // b2t_set_option("lstm_overlap", 0/1): layer 2 follows layer 1 on a second stream
 long long g_sub_frames = 24576;   // b2t_set_option("seanet_sub_frames", n)
 struct SubBatch { int c0, c1; long long frames; };
 std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* max_frames, int* max_clips) {
@@ -883,6 +885,7 @@ std::vector<SubBatch> split_clips(const int32_t* frames_host, int n, long long* 
 
 void b2t_seanet_set_sub_frames(int n) { if (n > 0) g_sub_frames = n; }
 void b2t_seanet_set_lstm_pdl(int on) { g_lstm_pdl = on != 0; }
+void b2t_seanet_set_lstm_overlap(int on) { g_lstm_overlap = on != 0; }
 void b2t_seanet_set_l0_fused(int on) { g_l0_fused = on != 0; }
 extern "C" void b2t_seanet_set_l0_dbg(long long* p) { g_l0_dbg = p; }
 
@@ -971,23 +974,59 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
   // ---- LSTM: per step one GEMM [x_t | h_{t-1}] . [W_ih | W_hh]^T with the cell update in the epilogue ----
   std::vector<int> toff(b->t_max + 1, 0);
   for (int t = 0; t < b->t_max; ++t) toff[t + 1] = toff[t] + active_host[t];
+  // One step kernel has 80 CTAs (10 row tiles x 8 column tiles at 1250 clips) on 148 SMs and the 2 x t_max steps are
+  // two dependent chains — but layer 2 at step t only needs layer 1 up to step t.  With lstm_overlap the second layer
+  // runs on a side stream kChunk steps behind the first (one event per chunk), so two step kernels are resident at a
+  // time; each layer keeps its own cell-state buffer.
+  constexpr int kChunk = 32;
+  static thread_local cudaStream_t side = nullptr;
+  static thread_local std::vector<cudaEvent_t> evs;
+  const bool overlap = g_lstm_overlap != 0 && b->t_max > kChunk;
+  if (overlap && !side) B2T_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  CUtensorMap mx[2], mh[2], mw[2];
+  LstmEpi ep[2];
   for (int layer = 0; layer < 2; ++layer) {
     const __nv_bfloat16* xin = layer == 0 ? w.x4t : w.s1t;
     __nv_bfloat16* hout = layer == 0 ? w.s1t : w.h2t;
-    CUtensorMap mx, mh, mw;
-    RUN(make_map_k(&mx, xin, (long long)total4 + kBM, 512, 512, kBM));
-    RUN(make_map_k(&mh, hout, (long long)total4 + kBM, 512, 512, kBM));
-    RUN(make_map_k(&mw, wt.lstm_w[layer], 2048, 1024, 1024, 256));
+    RUN(make_map_k(&mx[layer], xin, (long long)total4 + kBM, 512, 512, kBM));
+    RUN(make_map_k(&mh[layer], hout, (long long)total4 + kBM, 512, 512, kBM));
+    RUN(make_map_k(&mw[layer], wt.lstm_w[layer], 2048, 1024, 1024, 256));
     LstmEpi e{};
-    e.bias = wt.lstm_b[layer]; e.order = b->order; e.off4 = b->off[4]; e.c = w.c; e.h_out = hout;
+    e.bias = wt.lstm_b[layer]; e.order = b->order; e.off4 = b->off[4]; e.c = layer == 0 ? w.c : w.c2; e.h_out = hout;
     e.skip = layer == 1 ? w.x4t : nullptr; e.s2e = layer == 1 ? w.s2e : nullptr;
-    for (int t = 0; t < b->t_max; ++t) {
-      const int na = active_host[t];
-      if (na <= 0) break;
-      e.t = t; e.toff_t = toff[t]; e.n_active = na;
-      RUN((launch_bn<256, LstmEpi>(mx, mh, mw, 8, t > 0 ? 8 : 0, toff[t], t > 0 ? toff[t - 1] : 0, na, 2048, e, st,
-                                   t > 0 ? g_lstm_pdl : 0)));
+    ep[layer] = e;
+  }
+  int t_end = 0;
+  while (t_end < b->t_max && active_host[t_end] > 0) ++t_end;
+  auto run_steps = [&](int layer, int ta, int tb, cudaStream_t s, bool first_plain) -> int {
+    for (int t = ta; t < tb; ++t) {
+      LstmEpi e = ep[layer];
+      e.t = t; e.toff_t = toff[t]; e.n_active = active_host[t];
+      const int pdl = (t > 0 && !(first_plain && t == ta)) ? g_lstm_pdl : 0;
+      RUN((launch_bn<256, LstmEpi>(mx[layer], mh[layer], mw[layer], 8, t > 0 ? 8 : 0, toff[t], t > 0 ? toff[t - 1] : 0,
+                                   active_host[t], 2048, e, s, pdl)));
     }
+    return B2T_OK;
+  };
+  if (!overlap) {
+    RUN(run_steps(0, 0, t_end, st, false));
+    RUN(run_steps(1, 0, t_end, st, false));
+  } else {
+    const int n_chunks = (t_end + kChunk - 1) / kChunk;
+    while ((int)evs.size() < n_chunks + 1) {
+      cudaEvent_t ev;
+      B2T_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      evs.push_back(ev);
+    }
+    for (int k = 0; k < n_chunks; ++k) {
+      const int ta = k * kChunk, tb = std::min(t_end, ta + kChunk);
+      RUN(run_steps(0, ta, tb, st, false));
+      B2T_CUDA(cudaEventRecord(evs[k], st));
+      B2T_CUDA(cudaStreamWaitEvent(side, evs[k], 0));
+      RUN(run_steps(1, ta, tb, side, true));      // the first step after an event wait is a plain (fully ordered) launch
+    }
+    B2T_CUDA(cudaEventRecord(evs[n_chunks], side));
+    B2T_CUDA(cudaStreamWaitEvent(st, evs[n_chunks], 0));
   }
 
   b2t_acoustic_mark(1, 0, st);
