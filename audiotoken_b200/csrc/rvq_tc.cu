@@ -161,29 +161,22 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_c2 /* [n_q*1024, 256] bf16
   if (warp == 0) {
     // ===== TMA producer: per 256-code tile the k-blocks  Ehi[0:64], Ehi[64:128], Elo[0:64], Elo[64:128];
     //       this CTA fetches codes [rank*64, rank*64+64) of the tile and multicasts them to the whole cluster =====
-    // (whole warp, uniform control flow; one elected lane issues — see seanet_tc.cu)
-    {
-      const bool leader = elect_one();
+    if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int q = 0; q < n_q; ++q)
         for (int j = 0; j < kTilesPerStage; ++j)
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);       // all CTAs of the cluster released this slot
-            if (leader) {
-              mbar_expect_tx(full_bar(stage), kTileB);
-              tma_load_2d_mc(sB + stage * kTileB + cta_rank * (kTileB / kCluster), &map_c2, full_bar(stage), kb * kBK,
-                             q * kCodes + j * kBN + (int)cta_rank * (kBN / kCluster), (uint16_t)((1u << kCluster) - 1));
-            }
+            mbar_expect_tx(full_bar(stage), kTileB);
+            tma_load_2d_mc(sB + stage * kTileB + cta_rank * (kTileB / kCluster), &map_c2, full_bar(stage), kb * kBK,
+                           q * kCodes + j * kBN + (int)cta_rank * (kBN / kCluster), (uint16_t)((1u << kCluster) - 1));
             if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
           }
-      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (whole warp waits, one elected lane issues) =====
-    {
-      const bool leader = elect_one();
+    // ===== MMA issuer =====
+    if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kRows, kBN);
-      const uint64_t db0 = make_smem_desc(sB), da0 = make_smem_desc(sA);
       int stage = 0; uint32_t phase = 0;
       int g = 0;
       for (int q = 0; q < n_q; ++q) {
@@ -197,27 +190,24 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_c2 /* [n_q*1024, 256] bf16
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            if (leader) {
-              const uint64_t db = db0 + (uint64_t)(stage * (kTileB >> 4));
-              const int kk = kb & 1;
-              const uint64_t da_hi = da0 + (uint64_t)(kk * (kTileA >> 4));
-              const uint64_t da_lo = da0 + (uint64_t)((2 + kk) * (kTileA >> 4));
+            const uint64_t db = make_smem_desc(sB + stage * kTileB);
+            const int kk = kb & 1;
+            const uint64_t da_hi = make_smem_desc(sA + kk * kTileA);
+            const uint64_t da_lo = make_smem_desc(sA + (2 + kk) * kTileA);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(tmem_d, da_hi + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kb < 2) {                                  // codebook hi also meets the residual's lo part
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)
-                umma_bf16(tmem_d, da_hi + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-              if (kb < 2) {                                // codebook hi also meets the residual's lo part
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)
-                  umma_bf16(tmem_d, da_lo + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
-              }
-              umma_commit_mc(empty_bar(stage), (uint16_t)((1u << kCluster) - 1));
-              if (kb == 3) umma_commit(tfull_bar(acc));
+                umma_bf16(tmem_d, da_lo + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
             }
+            umma_commit_mc(empty_bar(stage), (uint16_t)((1u << kCluster) - 1));
             if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
           }
+          umma_commit(tfull_bar(acc));
         }
       }
-      __syncwarp();
     }
   } else {
     // ===== row threads: TMEM lane quadrant = warp % 4 =====
