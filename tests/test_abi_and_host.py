@@ -51,6 +51,23 @@ def test_no_cpu_fallback():
         assert b'fallback' in lib.b2t_last_error() or b'CUDA' in lib.b2t_last_error()
 
 
+def test_codebook_trainer_has_no_cpu_path():
+    """The training step refuses a CPU device and, without a GPU, the ABI call itself fails."""
+    from audiotoken_b200.training import CodebookTrainer
+    with pytest.raises(L.B2TError):
+        CodebookTrainer(64, 16, device='cpu')
+    if not torch.cuda.is_available():
+        lib = L.load()
+        x = torch.zeros(8, 64)
+        idx = torch.zeros(8, dtype=torch.int32)
+        cb, avg, cs = torch.zeros(16, 64), torch.zeros(16, 64), torch.zeros(16)
+        ws = torch.zeros(lib.b2t_vq_ema_workspace_bytes(8, 64, 16), dtype=torch.uint8)
+        rc = lib.b2t_vq_ema_update(x.data_ptr(), 64, 8, 64, idx.data_ptr(), cb.data_ptr(), avg.data_ptr(), cs.data_ptr(), 16,
+                                   0.8, 1e-5, 1.0, None, None, ws.data_ptr(), ws.numel(), None)
+        assert rc != 0
+        assert torch.equal(cb, torch.zeros(16, 64))
+
+
 def test_product_tables_match_oracle():
     dense = dense_mel_bank()
     assert np.array_equal(dense.numpy(), fbank.mel_filters().numpy()[:256])
