@@ -61,8 +61,13 @@ int b2t_version(void);
 const char* b2t_last_error(void);
 /* B2T_OK iff `device` is compute capability 10.x. */
 int b2t_device_check(int device);
-/* Library-wide switches (A/B measurements): "gemm_multicast" 0/1 — run the tcgen05 GEMM as 2-CTA
- * clusters issuing tcgen05.mma.cta_group::2 on 256 x 256 tiles (default 1) or one CTA per 128 x 256 tile. */
+/* Library-wide switches (A/B measurements; every default is the measured-fastest, parity-tested path):
+ *   "gemm_multicast" 0/1    tcgen05 GEMM as 2-CTA clusters issuing tcgen05.mma.cta_group::2 on 256 x 256 tiles (1) or
+ *                           one CTA per 128 x 256 tile
+ *   "attn_two_pass"  0/1/5  relative-key attention: 1 = two-pass fixed-bound softmax (default), 0 = online softmax,
+ *                           5 = two-pass with the row sums on the tensor core as well
+ *   "dwconv_ring" 0/1, "seanet_l0_fused" 0/1, "lstm_pdl" 0/1, "lstm_overlap" 0/1 (layer 2 on a side stream one chunk
+ *   behind layer 1), "seanet_sub_frames" n, "rvq_tensor" 0/1                                                         */
 int b2t_set_option(const char* name, int value);
 
 /* ---- batch descriptor (all arrays on the device, built by the host packer) --------------- */
