@@ -170,3 +170,52 @@ def weight_norm_weight(sd: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
     """w = g * v / |v| with the norm over (C_in, k) per output channel (torch weight_norm, dim=0)."""
     g_, v = sd[name + '.parametrizations.weight.original0'], sd[name + '.parametrizations.weight.original1']
     return g_ * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)
+
+
+# ---- mHuBERT-base (the reference's own `semantic_s`, SURVEY 8f rank 1) -------------------------------
+HUBERT = dict(hidden=768, heads=12, head_dim=64, ffn=3072, layers=12, conv_dim=512,
+              conv_kernel=(10, 3, 3, 3, 3, 2, 2), conv_stride=(5, 2, 2, 2, 2, 2, 2),
+              pos_kernel=128, pos_groups=16, ln_eps=1e-5)
+
+
+def synthetic_hubert_state_dict(seed: int = 0, n_layers: int = 12) -> Dict[str, torch.Tensor]:
+    """HF ``HubertModel`` names and shapes (``voidful/mhubert-base`` = the base config the reference loads at
+    ``audiotoken/encoder.py:72``): 7 bias-free strided convs with GroupNorm on the first, feature projection,
+    weight-normed grouped positional conv, ``n_layers`` post-LN transformer layers.  Conv weights use the He-style
+    scale of HF's init, Linear N(0, 0.02); norm gains/biases and Linear biases are perturbed away from 1/0."""
+    g = torch.Generator().manual_seed(seed)
+    H, F, C = HUBERT['hidden'], HUBERT['ffn'], HUBERT['conv_dim']
+    sd: Dict[str, torch.Tensor] = {}
+
+    def ln(prefix, n):
+        sd[prefix + '.weight'] = _randn(g, n, std=0.1, mean=1.0)
+        sd[prefix + '.bias'] = _randn(g, n, std=0.1)
+
+    def lin(prefix, n_out, n_in, std=0.02):
+        sd[prefix + '.weight'] = _randn(g, n_out, n_in, std=std)
+        sd[prefix + '.bias'] = _randn(g, n_out, std=0.02)
+
+    cin = 1
+    for i, k in enumerate(HUBERT['conv_kernel']):
+        sd[f'feature_extractor.conv_layers.{i}.conv.weight'] = _randn(g, C, cin, k, std=(2.0 / (cin * k)) ** 0.5)
+        cin = C
+    ln('feature_extractor.conv_layers.0.layer_norm', C)
+    ln('feature_projection.layer_norm', C)
+    lin('feature_projection.projection', H, C, std=0.03)
+    pk, pg = HUBERT['pos_kernel'], HUBERT['pos_groups']
+    v = _randn(g, H, H // pg, pk, std=2.0 * (1.0 / (pk * H)) ** 0.5)
+    sd['encoder.pos_conv_embed.conv.parametrizations.weight.original1'] = v
+    # weight_norm(dim=2): one gain per kernel tap, norm over (out, in/groups)
+    sd['encoder.pos_conv_embed.conv.parametrizations.weight.original0'] = (
+        v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt() * (1.0 + 0.1 * _randn(g, 1, 1, pk)))
+    sd['encoder.pos_conv_embed.conv.bias'] = _randn(g, H, std=0.02)
+    ln('encoder.layer_norm', H)
+    for i in range(n_layers):
+        p = f'encoder.layers.{i}.'
+        for nm in ('q_proj', 'k_proj', 'v_proj', 'out_proj'):
+            lin(p + 'attention.' + nm, H, H)
+        ln(p + 'layer_norm', H)
+        lin(p + 'feed_forward.intermediate_dense', F, H)
+        lin(p + 'feed_forward.output_dense', H, F)
+        ln(p + 'final_layer_norm', H)
+    return sd

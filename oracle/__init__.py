@@ -18,4 +18,9 @@ quantisers that are absent from ``/root/reference`` (``vector_quantize_pytorch``
 requirements.txt:10 — and ``encodec`` — unpinned, requirements.txt:5) are restated from their
 published algorithm (nearest codeword in Euclidean distance; residual VQ) and anchored on the
 reference's call sites (encoder.py:50-52, 100-101, 147-161, 180).
+
+``oracle/hubert.py`` (the reference's own mHuBERT ``semantic_s``) is pinned the same way against HF
+``HubertModel`` / ``Wav2Vec2FeatureExtractor`` (``tests/golden/make_golden_hubert.py``); it has no CUDA counterpart yet.
+``oracle/quantize.py::vq_ema_train_step`` (codebook training) restates the third-party package's published training
+forward and is **parity unpinned** against the package itself.
 """

@@ -193,3 +193,67 @@ def test_vq_ema_oracle_equals_onehot_formulation():
     used = torch.unique(ind)
     means = torch.stack([x[ind == k].mean(0) for k in used])
     assert torch.allclose(e0[used], means, rtol=1e-4)
+
+
+def test_hubert_oracle_matches_hf_golden(golden_dir):
+    """oracle/hubert.py (the reference's own semantic_s = mHuBERT-base + k-means) against outputs of
+    HF HubertModel / Wav2Vec2FeatureExtractor called the way reference encoder.py:88-103 calls them
+    (tests/golden/make_golden_hubert.py): normalisation, conv features (GroupNorm over the padded chunk), hidden
+    states 0 / 1 / 11 / 12 with padding masks, tokens."""
+    import numpy as np
+    import torch
+    from audiotoken_b200.weights import synthetic_codebook, synthetic_hubert_state_dict, synthetic_waveform
+    from oracle import hubert
+    g = np.load(os.path.join(golden_dir, 'hubert.npz'))
+    lengths, total = [int(v) for v in g['lengths']], int(g['total'])
+    sd = synthetic_hubert_state_dict(0)
+    wave = torch.zeros(len(lengths), total)
+    mask = torch.zeros(len(lengths), total)
+    for i, n in enumerate(lengths):
+        w = hubert.processor_normalize(synthetic_waveform(300 + i, n, 16000))
+        if i == 0:
+            assert np.abs(w[:64].numpy() - g['norm0']).max() < 2e-6
+        if i == 1:
+            assert abs(float(w.mean()) - g['norm1_stats'][0]) < 1e-6 and abs(float(w.std(unbiased=False)) - g['norm1_stats'][1]) < 1e-5
+        wave[i, :n] = w
+        mask[i, :n] = 1
+    assert [int(v) for v in hubert.feat_lengths(torch.tensor(lengths))] == [49, 34, 12]
+    feats = hubert.feature_encoder(wave, sd)
+    assert np.abs(feats[:, ::7, ::16].numpy() - g['feats']).max() < 2e-5 * np.abs(g['feats']).max()
+    hs, fm = hubert.hidden_states(wave, mask, sd)
+    assert fm.sum(1).tolist() == [49, 34, 12]
+
+    def rel(a, b):
+        a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+        return float((a - b).norm() / b.norm())
+    assert rel(hs[0][:, ::3], g['h0']) < 2e-6
+    assert rel(hs[1][:, ::3], g['h1']) < 5e-6
+    assert rel(hs[11], g['h11']) < 2e-5
+    assert rel(hs[12][:, ::3], g['h12']) < 2e-5
+    tok = hubert.tokens(hs, synthetic_codebook(1000, 768, seed=9))
+    want = torch.as_tensor(g['tokens'])
+    assert tok.shape == want.shape == (3, 1, 49) and tok.dtype == torch.int16
+    valid = fm[:, None, :]
+    assert float((tok[valid] == want[valid]).float().mean()) >= 0.995
+
+
+def test_hubert_ragged_equals_padded(golden_dir):
+    """The packed-batch restatement (no padding materialised; GroupNorm statistics over the padded frame count) equals
+    the padded computation on every valid frame, and a different padded length changes the result (the mHuBERT front
+    end, unlike the w2v-BERT fbank, is NOT padding-invariant)."""
+    import numpy as np
+    import torch
+    from audiotoken_b200.weights import synthetic_hubert_state_dict, synthetic_waveform
+    from oracle import hubert
+    g = np.load(os.path.join(golden_dir, 'hubert.npz'))
+    lengths, total = [int(v) for v in g['lengths']], int(g['total'])
+    sd = synthetic_hubert_state_dict(0)
+    clips = [hubert.processor_normalize(synthetic_waveform(300 + i, n, 16000)) for i, n in enumerate(lengths)]
+    rag = hubert.hidden_states_ragged(clips, total, sd)
+    for i, hs in enumerate(rag):
+        tv = hs[11].shape[0]
+        ref = torch.as_tensor(g['h11'])[i, :tv].double()
+        assert float((hs[11].double() - ref).norm() / ref.norm()) < 2e-5, i
+    other = hubert.hidden_states_ragged(clips[1:2], 2 * total, sd)[0]
+    ref = torch.as_tensor(g['h11'])[1, :other[11].shape[0]].double()
+    assert float((other[11].double() - ref).norm() / ref.norm()) > 1e-3
