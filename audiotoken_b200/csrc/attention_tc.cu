@@ -1,14 +1,20 @@
 // Relative-key flash attention on tcgen05 / TMEM / TMA (sm_100a)
 // (reference audiotoken/modeling_wav2vec2_bert.py:37-77; see attention.cu for the maths).
 //
-// One CTA = one (clip, 128-query tile), persistent over the 16 heads; 576 threads:
-//   warp 0    TMA producer : Q tile + distance embedding E once, then a 3-stage ring of 128-key K and V tiles
+// Two kernels share this file's layout and helpers:
+//   attention_tc2_kernel  (default)  two-pass, fixed row bound: QK^T once for the row maxima, a second time for
+//                                    P = 2^(score - bound); O accumulated in TMEM; TMA / S-issue / PV-issue in three
+//                                    converged warps.  Described in front of the kernel below.
+//   attention_tc_kernel   (attn_two_pass = 0)  the online-softmax predecessor, kept for A/B runs:
+//
+// One CTA = one (clip, 128-query tile, head); 320 threads:
+//   warp 0    TMA producer : Q tile + distance embedding E once, then a ring of 64-key K and V tiles
 //                            (all boxes 64 x rows out of the packed qkv matrix, SWIZZLE_128B).
-//   warp 1    MMA issuer   : R = Q.E^T (128x80), then per key tile S = Q.K^T (128x128x64, 4 tcgen05.mma) and
-//                            O_tile = P.V (128x64x128, 8 tcgen05.mma, V consumed MN-major straight from the TMA
+//   warp 1    MMA issuer   : R = Q.E^T (128x80), then per key tile S = Q.K^T (128x64x64, 4 tcgen05.mma) and
+//                            O_tile = P.V (128x64x64, 4 tcgen05.mma, V consumed MN-major straight from the TMA
 //                            layout); S and O_tile are double-buffered in TMEM so QK^T of tile i+1 overlaps the
 //                            softmax of tile i.
-//   warps 2-9 softmax      : thread = (query row = TMEM lane, 64-key half).  tcgen05.ld the S half row, scale + relative-key bias
+//   warps 2-9 softmax      : thread = (query row = TMEM lane, 32-key half).  tcgen05.ld the S half row, scale + relative-key bias
 //                            (gathered from the thread's own R row only inside the diagonal band, a per-row
 //                            constant elsewhere) + key mask, row max / exp2 / row sum without any shuffle,
 //                            P -> bf16 -> shared memory in the K-major SWIZZLE_128B layout the PV MMA reads,
