@@ -979,8 +979,13 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
   // runs on a side stream kChunk steps behind the first (one event per chunk), so two step kernels are resident at a
   // time; each layer keeps its own cell-state buffer.
   constexpr int kChunk = 32;
-  static thread_local cudaStream_t side = nullptr;
-  static thread_local std::vector<cudaEvent_t> evs;
+  // side stream and events belong to a device: one set per (host thread, device)
+  static thread_local cudaStream_t side_of[64] = {};
+  static thread_local std::vector<cudaEvent_t> evs_of[64];
+  int cur_dev = 0;
+  B2T_CUDA(cudaGetDevice(&cur_dev));
+  cudaStream_t& side = side_of[cur_dev & 63];
+  std::vector<cudaEvent_t>& evs = evs_of[cur_dev & 63];
   const bool overlap = g_lstm_overlap != 0 && b->t_max > kChunk;
   if (overlap && !side) B2T_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
   CUtensorMap mx[2], mh[2], mw[2];
