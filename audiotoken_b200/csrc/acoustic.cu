@@ -403,8 +403,7 @@ int rvq_launch(const b2t_acoustic_model* m, const float* emb, int rows, int n_q,
   if ((impl == B2T_IMPL_TENSOR || (impl == B2T_IMPL_AUTO && g_rvq_tensor)) && c2 != m->t.end())
     return b2t_rvq_tensor(emb, rows, c2->second, n_q, t[0], t[1], t[2], n_q, codes,
                           (unsigned int*)(m->t.count("rvq.stats") ? m->t.at("rvq.stats") : nullptr), st);
-  static bool cfg = false;
-  if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RvqSmem))); cfg = true; }
+  B2T_SMEM_OPT_IN(sizeof(RvqSmem), rvq_kernel);
   rvq_kernel<<<(rows + 63) / 64, 256, sizeof(RvqSmem), st>>>(emb, rows, t[0], t[1], t[2], n_q, codes);
   B2T_LAUNCH_CHECK();
   return B2T_OK;

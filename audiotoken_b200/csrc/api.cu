@@ -1,5 +1,6 @@
 // Library-level entry points: version, error text, device check, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -16,15 +17,41 @@ void b2t_set_error(const char* fmt, ...) {
 void b2t_count_launch(int n) { g_launches += n; }
 void b2t_reset_launch_count() { g_launches = 0; }
 
+// per device: a process may drive several GPUs (AudioToken(device='cuda:0') and ('cuda:1'))
+int b2t_device_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < B2T_MAX_DEVICES) ? dev : 0;
+}
+
 int b2t_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[B2T_MAX_DEVICES] = {};
+  const int dev = b2t_device_index();
+  if (sms[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 148;
   }
-  return sms;
+  return sms[dev];
+}
+
+static int g_debug_sync = -1;
+bool b2t_debug_sync() {
+  if (g_debug_sync < 0) {
+    const char* e = getenv("B2T_DEBUG_SYNC");
+    g_debug_sync = (e && *e && *e != '0') ? 1 : 0;
+  }
+  return g_debug_sync != 0;
+}
+void b2t_set_debug_sync(int on) { g_debug_sync = on ? 1 : 0; }
+int b2t_debug_sync_check(const char* file, int line) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    b2t_set_error("device fault in the kernel launched at %s:%d: %s", file, line, cudaGetErrorString(e));
+    fprintf(stderr, "b200tok: device fault in the kernel launched at %s:%d: %s\n", file, line, cudaGetErrorString(e));
+    return B2T_ERR_CUDA;
+  }
+  return B2T_OK;
 }
 
 int b2t_arch_ok() {
@@ -34,6 +61,17 @@ int b2t_arch_ok() {
     return B2T_ERR_CUDA;
   }
   return b2t_device_check(dev);
+}
+
+// developer hook (b2t_set_option("test_trap", 1)): one thread runs the device trap report, so that the host-side
+// reporting of a protocol time-out can be checked on a GPU without breaking a protocol
+__global__ void test_trap_kernel() { b2t_trap_report("test trap requested through b2t_set_option", 0xabcdu, 7u); }
+int b2t_test_trap() {
+  test_trap_kernel<<<1, 1>>>();
+  B2T_LAUNCH_CHECK();
+  cudaError_t e = cudaDeviceSynchronize();
+  b2t_set_error("test trap: cudaDeviceSynchronize -> %s", cudaGetErrorString(e));
+  return e == cudaSuccess ? B2T_OK : B2T_ERR_CUDA;
 }
 
 extern "C" {

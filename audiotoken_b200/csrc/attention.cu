@@ -381,21 +381,18 @@ extern "C" int b2t_relkey_attention(const void* qkv, const void* dist_emb, const
   dim3 grid(b->n_qtiles, kHeads);
   if (precision == B2T_PREC_FP32) {
     B2T_REQUIRE(impl != B2T_IMPL_TENSOR, B2T_ERR_ARG, "b2t_relkey_attention: tensor path is bf16 only");
-    static bool cfg = false;
-    if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(attention_simt_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem))); cfg = true; }
+    B2T_SMEM_OPT_IN(sizeof(SimtSmem), attention_simt_kernel<float, false>);
     attention_simt_kernel<float, false><<<grid, 256, sizeof(SimtSmem), st>>>(
         (const float*)qkv, (const float*)dist_emb, b->row_off, b->valid_rows, b->qtile_clip, b->qtile_q0, (float*)out);
   } else if (impl == B2T_IMPL_SIMT) {
-    static bool cfg = false;
-    if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(attention_simt_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem))); cfg = true; }
+    B2T_SMEM_OPT_IN(sizeof(SimtSmem), attention_simt_kernel<__nv_bfloat16, true>);
     attention_simt_kernel<__nv_bfloat16, true><<<grid, 256, sizeof(SimtSmem), st>>>(
         (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dist_emb, b->row_off, b->valid_rows, b->qtile_clip, b->qtile_q0,
         (__nv_bfloat16*)out);
   } else if (impl != B2T_IMPL_MMA_SYNC) {
     return b2t_attention_tensor_tc(qkv, dist_emb, b, out, st);
   } else {
-    static bool cfg = false;
-    if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem))); cfg = true; }
+    B2T_SMEM_OPT_IN(sizeof(MmaSmem), attention_mma_kernel);
     attention_mma_kernel<<<grid, 128, sizeof(MmaSmem), st>>>(
         (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dist_emb, b->row_off, b->valid_rows, b->qtile_clip, b->qtile_q0,
         (__nv_bfloat16*)out);

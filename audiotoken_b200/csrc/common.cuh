@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <assert.h>
 #include <stdio.h>
 #include "../../include/b200tok.h"
 
@@ -35,13 +36,41 @@ void b2t_count_launch(int n = 1);
       return B2T_ERR_CUDA;                                                          \
     }                                                                               \
     b2t_count_launch();                                                             \
+    if (b2t_debug_sync() && b2t_debug_sync_check(__FILE__, __LINE__) != B2T_OK) return B2T_ERR_CUDA; \
   } while (0)
 
-int b2t_num_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device attribute: opt in once per (call site, device).
+#define B2T_SMEM_OPT_IN(bytes, ...)                                                                     \
+  do {                                                                                                  \
+    static bool done__[B2T_MAX_DEVICES] = {};                                                           \
+    const int dev__ = b2t_device_index();                                                               \
+    if (!done__[dev__]) {                                                                               \
+      B2T_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      done__[dev__] = true;                                                                             \
+    }                                                                                                   \
+  } while (0)
+
+// B2T_DEBUG_SYNC=1 (environment) or b2t_set_option("debug_sync", 1): synchronise the device after every launch and
+// name the launch site whose kernel faulted (an asynchronous fault otherwise surfaces at some later, unrelated call).
+bool b2t_debug_sync();
+int b2t_debug_sync_check(const char* file, int line);
+void b2t_set_debug_sync(int on);
+
+int b2t_num_sms();          // of the current device
+int b2t_device_index();     // current device, clamped to [0, B2T_MAX_DEVICES)
+constexpr int B2T_MAX_DEVICES = 64;
 int b2t_arch_ok();   // B2T_OK or B2T_ERR_ARCH for the current device
 
 // ---- device helpers ----------------------------------------------------------------------------
 #define B2T_DEVICE __device__ __forceinline__
+
+// A protocol wait that ran out of its bound: say where (device printf + device assert, both reported by the host's
+// next synchronisation as cudaErrorAssert) instead of a bare trap that only leaves "unspecified launch failure".
+__device__ __noinline__ inline void b2t_trap_report(const char* what, unsigned a, unsigned b) {
+  printf("b200tok device trap: %s a=0x%x b=%u block=(%d,%d,%d) thread=%d\n", what, a, b, (int)blockIdx.x, (int)blockIdx.y,
+         (int)blockIdx.z, (int)threadIdx.x);
+  __assert_fail(what, __FILE__, __LINE__, "b2t_trap_report");
+}
 
 B2T_DEVICE float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 

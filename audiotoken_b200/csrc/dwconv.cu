@@ -195,7 +195,7 @@ B2T_DEVICE void mbar_wait_(uint32_t bar, uint32_t parity) {
   while (!ok) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && ++spins > (1u << 26)) __trap();
+    if (!ok && ++spins > (1u << 26)) b2t_trap_report("dwconv_ring mbar_wait ran out of its bound (bar smem address, parity)", bar, parity);
   }
 }
 
@@ -358,8 +358,7 @@ extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float
   if (b->n_ctiles <= 0) return B2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == B2T_PREC_BF16 && g_dwconv_ring) {
-    static bool cfg = false;
-    if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(dwconv_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem)); cfg = true; }
+    B2T_SMEM_OPT_IN(kRingSmem, dwconv_ring_kernel);
     int grid = b2t_num_sms();
     if (b->n_ctiles < grid) grid = b->n_ctiles;
     dwconv_ring_kernel<<<grid, kThreads, kRingSmem, st>>>((const __nv_bfloat16*)x, w_dw, ln_weight, ln_bias, b->row_off,

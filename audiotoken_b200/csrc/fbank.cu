@@ -240,13 +240,12 @@ fbank_stack_ln_kernel(const float* __restrict__ logmel, const float* __restrict_
 }
 
 int ensure_twiddles(cudaStream_t st) {
-  static bool done[64] = {false};
-  int dev = 0;
-  B2T_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && done[dev]) return B2T_OK;
+  static bool done[B2T_MAX_DEVICES] = {false};
+  const int dev = b2t_device_index();
+  if (done[dev]) return B2T_OK;
   init_twiddles_kernel<<<1, 256, 0, st>>>();
   B2T_LAUNCH_CHECK();
-  if (dev < 64) done[dev] = true;
+  done[dev] = true;
   return B2T_OK;
 }
 

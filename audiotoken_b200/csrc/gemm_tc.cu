@@ -391,7 +391,7 @@ int launch_cluster2(Kern kern, int pairs, int smem, cudaStream_t st, const CUten
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   B2T_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, K, p));
-  b2t_count_launch();
+  B2T_LAUNCH_CHECK();
   return B2T_OK;
 }
 
@@ -404,19 +404,11 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const b2t_gemm_args*
   if constexpr (BN == 256) {
     if (g_multicast && tiles_m >= 2) {
       using LP = SmemLayout<BN, true>;
-      static bool cfg_mc = false;
-      if (!cfg_mc) {
-        B2T_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::kTotal));
-        cfg_mc = true;
-      }
+      B2T_SMEM_OPT_IN(LP::kTotal, gemm_tc_kernel<BN, EPI, false, true>);
       return launch_cluster2(gemm_tc_kernel<BN, EPI, false, true>, ((tiles_m + 1) / 2) * tiles_n, LP::kTotal, st, ma, mw, a->K, p);
     }
   }
-  static bool configured = false;
-  if (!configured) {
-    B2T_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  B2T_SMEM_OPT_IN(L::kTotal, gemm_tc_kernel<BN, EPI>);
   const int tiles = tiles_m * tiles_n;
   int grid = b2t_num_sms();
   if (tiles < grid) grid = tiles;
@@ -451,11 +443,7 @@ int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, i
   if (rc != B2T_OK) return rc;
   rc = make_map(&mw, C2, K, 2 * D, 2 * D, 256);
   if (rc != B2T_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    B2T_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, kEpiArgmax, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  B2T_SMEM_OPT_IN(L::kTotal, gemm_tc_kernel<256, kEpiArgmax, true>);
   EpiParams p{half_norm, parts, slices, nullptr, nullptr, M, Kpad, 1.f, 0};
   const int tiles = ((M + kBM - 1) / kBM) * (Kpad / 256);
   int grid = b2t_num_sms();
@@ -465,6 +453,7 @@ int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, i
   return B2T_OK;
 }
 
+int b2t_test_trap();               // api.cu
 extern int g_attn_heads_per_cta;   // attention_tc.cu
 extern int g_attn_two_pass;
 extern bool g_rvq_tensor;          // acoustic.cu
@@ -478,6 +467,8 @@ extern bool g_dwconv_ring;         // dwconv.cu
 extern "C" int b2t_set_option(const char* name, int value) {
   B2T_REQUIRE(name, B2T_ERR_ARG, "b2t_set_option: null name");
   if (std::string(name) == "gemm_multicast") { g_multicast = value != 0; return B2T_OK; }
+  if (std::string(name) == "test_trap") { return value ? b2t_test_trap() : B2T_OK; }
+  if (std::string(name) == "debug_sync") { b2t_set_debug_sync(value); return B2T_OK; }
   if (std::string(name) == "dwconv_ring") { g_dwconv_ring = value != 0; return B2T_OK; }
   if (std::string(name) == "seanet_l0_fused") { b2t_seanet_set_l0_fused(value); return B2T_OK; }
   if (std::string(name) == "lstm_pdl") { b2t_seanet_set_lstm_pdl(value); return B2T_OK; }

@@ -65,6 +65,31 @@ extern "C" int b2t_profile_read(float* ms_per_class, double* gemm_flops) {
   return B2T_OK;
 }
 
+// ---- developer hook: in-situ determinism check -------------------------------------------------------------------
+// b2t_debug_stage_sums(buf, capacity): after every stage of b2t_semantic_encode a 64-bit position-weighted checksum
+// of the WHOLE workspace is written to buf[stage] (integer atomics: order independent).  Two runs of the same batch
+// from the same initial workspace contents must produce identical vectors; the first differing entry names the stage
+// whose kernel is not deterministic (tools/stage_sums.py).
+namespace {
+unsigned long long* g_sums = nullptr;
+int g_sums_cap = 0, g_sums_n = 0;
+__global__ void __launch_bounds__(256) workspace_sum_kernel(const uint4* __restrict__ p, size_t n16, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = p[i];
+    const unsigned long long a = ((unsigned long long)v.x << 32) | v.y, b = ((unsigned long long)v.z << 32) | v.w;
+    acc += (a ^ (b * 0x9E3779B97F4A7C15ull)) * (2 * (unsigned long long)i + 1);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+}  // namespace
+extern "C" int b2t_debug_stage_sums(unsigned long long* buf, int capacity) {
+  g_sums = buf; g_sums_cap = capacity; g_sums_n = 0;
+  return B2T_OK;
+}
+extern "C" int b2t_debug_stage_count(void) { return g_sums_n; }
+
 struct b2t_semantic_model {
   int n_layers;
   int codebook_size;
@@ -161,7 +186,16 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
     if (it == m->t.end()) { if (!missing) miss_name = n; missing = true; return nullptr; }
     return it->second;
   };
-#define RUN(call) do { int rc__ = (call); if (rc__ != B2T_OK) return rc__; } while (0)
+  g_sums_n = 0;
+  auto stage_sum = [&]() -> int {
+    if (g_sums == nullptr || g_sums_n >= g_sums_cap) return B2T_OK;
+    B2T_CUDA(cudaMemsetAsync(g_sums + g_sums_n, 0, 8, st));
+    workspace_sum_kernel<<<4 * b2t_num_sms(), 256, 0, st>>>((const uint4*)workspace, w.total / 16, g_sums + g_sums_n);
+    B2T_LAUNCH_CHECK();
+    ++g_sums_n;
+    return B2T_OK;
+  };
+#define RUN(call) do { int rc__ = (call); if (rc__ != B2T_OK) return rc__; rc__ = stage_sum(); if (rc__ != B2T_OK) return rc__; } while (0)
 #define NEED() B2T_REQUIRE(!missing, B2T_ERR_STATE, "b2t_semantic_encode: tensor '%s' not set", miss_name.c_str())
 
   auto gemm = [&](const void* A, int lda, const void* W, const void* bias, void* out, int ldo, float* resid,

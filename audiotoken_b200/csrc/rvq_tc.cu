@@ -373,8 +373,7 @@ int b2t_rvq_tensor(const float* emb, int rows, const void* c2, int n_q_total, co
   CUtensorMap map;
   int rc = make_map(&map, c2, n_q_total * kCodes, 2 * kD, 2 * kD, kBN / kCluster);
   if (rc != B2T_OK) return rc;
-  static bool cfg = false;
-  if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); cfg = true; }
+  B2T_SMEM_OPT_IN(kSmemBytes, rvq_tc_kernel);
   const int ctas = ((rows + kRows - 1) / kRows + kCluster - 1) / kCluster * kCluster;
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(ctas); lc.blockDim = dim3(kThreadsRvq); lc.dynamicSmemBytes = kSmemBytes; lc.stream = st;

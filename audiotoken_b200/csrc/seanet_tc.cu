@@ -774,11 +774,7 @@ template <int BN, typename Epi>
 int launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, int kb0, int kb1, int row0, int row1,
               int M, int N, const Epi& p, cudaStream_t st, int pdl = 0) {
   using L = Smem<BN>;
-  static bool configured = false;
-  if (!configured) {
-    B2T_CUDA(cudaFuncSetAttribute(seanet_tc_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  B2T_SMEM_OPT_IN(L::kTotal, seanet_tc_kernel<BN, Epi>);
   const int tiles = ((M + kBM - 1) / kBM) * (N / BN);
   if (tiles <= 0) return B2T_OK;
   int occ = (227 * 1024) / (L::kTotal + 1024);
@@ -922,8 +918,7 @@ int b2t_seanet_tc_encode(const SeanetTcWeights& wt, const float* wave, const b2t
       RUN(make_map_k(&mr, wt.res_w[0], 32, 64, 64, 32));
       L0Params lp{wave, b->wave_off, b->true_len, b->off[4], wt.conv0_w, wt.conv0_b, wt.k3_b[0], wt.res_b[0], w.ye[0], sb.c0, ns, M0,
                   g_l0_dbg};
-      static bool cfg = false;
-      if (!cfg) { B2T_CUDA(cudaFuncSetAttribute(seanet_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem)); cfg = true; }
+      B2T_SMEM_OPT_IN(kL0Smem, seanet_l0_kernel);
       int grid = 2 * b2t_num_sms();
       const int tiles0 = (M0 + kBM - 1) / kBM;
       if (tiles0 < grid) grid = tiles0;

@@ -45,7 +45,7 @@ B2T_DEVICE bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 B2T_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 26)) b2t_trap_report("mbar_wait ran out of its bound (bar smem address, parity)", bar, parity);
   }
 }
 // One lane of a CONVERGED warp.  Code guarded by this predicate inside warp-uniform control flow lets ptxas issue

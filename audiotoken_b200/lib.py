@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libb200tok.so')
+LIB_PATH = os.environ.get('B2T_LIB_PATH') or os.path.join(_HERE, 'lib', 'libb200tok.so')   # override: developer A/B builds
 
 PREC_BF16, PREC_FP32 = 0, 1
 EPI_BIAS, EPI_BIAS_SWISH, EPI_RESID, EPI_GLU, EPI_BIAS_MASK = 0, 1, 2, 3, 4

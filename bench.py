@@ -248,6 +248,9 @@ def main():
     from audiotoken_b200 import packing
     from audiotoken_b200.encoder import Wav2VecBertEncoder
 
+    for kv in filter(None, os.environ.get('B2T_OPTS', '').split(',')):     # developer A/B switches, e.g. attn_two_pass=0
+        k, v = kv.split('=')
+        L.check(L.load().b2t_set_option(k.encode(), int(v)), kv)
     lengths = shard_lengths(rank, args.workload)
     acoustic = args.workload == 'c4'
     sr = 24000 if acoustic else SR
@@ -352,16 +355,31 @@ def main():
         barrier()
         return max_over_ranks(s.elapsed_time(e) / steps)
 
-    for _ in range(max(args.warmup, 3)):
+    def fault_check(where: str):
+        """A device fault is asynchronous: surface it here, with a name, instead of in some tensor destructor."""
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f'bench.py: rank {rank}: device fault detected after {where}: {e}\n'
+                             f'  library says: {L.load().b2t_last_error().decode("utf-8", "replace")}\n'
+                             '  re-run with B2T_DEBUG_SYNC=1 to name the kernel\n')
+            sys.stderr.flush()
+            os._exit(13)
+
+    for i in range(max(args.warmup, 3)):
         step_resident()
+        fault_check(f'warm-up step {i} (resident)')
     sampler = ClockSampler(local)
     sampler.start()
     launches[0] = 0
     ms_res = timed(step_resident, args.steps)
     gpu_launches = launches[0]
     clocks = sampler.result()
+    fault_check('the timed resident steps')
     step_e2e()
+    fault_check('the e2e warm-up step')
     ms_e2e = timed(step_e2e, args.steps)
+    fault_check('the timed e2e steps')
 
     # instrumented steps: CUDA-event time per kernel class
     import ctypes as C
