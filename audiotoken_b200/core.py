@@ -2,15 +2,18 @@
 
 Same constructor and method signatures as the reference (audiotoken/core.py:27-289); the decode half
 (audiotoken/core.py:291-359) is out of scope of this build.  Differences that do not change results:
-  * weights are resolved lazily (nothing is downloaded at import time); without a checkpoint path the
-    encoders use seeded synthetic weights of the named architecture;
-  * ``encode_batch_files`` packs the segments of all files into ragged length-bucketed batches instead
-    of padding every segment to ``chunk_size`` seconds, reads files in a thread pool, copies tokens to
-    the host once per batch and writes every ``.npy`` exactly once (atomic rename);
+  * weights are resolved lazily from plain paths (config fields or AUDIOTOKEN_* environment variables; nothing is
+    downloaded); running without a checkpoint needs an explicit ``synthetic_weights=True`` (seeded synthetic weights
+    of the named architecture: benchmark / parity mode);
+  * ``encode_batch_files`` streams the corpus in bounded windows: reader threads prefetch files, each window is
+    packed into ragged length-bucketed batches instead of padding every segment to ``chunk_size`` seconds, tokens
+    come back once per batch on a side stream and a finished file's ``.npy`` is written at once, exactly once
+    (atomic rename), by writer threads;
   * ``device`` must be an sm_100 CUDA device — there is no CPU path.
 """
 from __future__ import annotations
 
+import logging
 import os
 import time
 from concurrent.futures import ThreadPoolExecutor
@@ -24,6 +27,8 @@ from . import io as aio
 from .configs import (AcousticEncoderConfig, AUDIO_EXTS, EncoderConfig, SemanticSConfig, Tokenizers,
                       Wav2VecBertConfig, num_codebooks_to_bandwidth)
 from .packing import bucket_by_rows, length_tokens, padded_rows
+
+logger = logging.getLogger('audiotoken_b200')
 
 
 class AudioToken:
@@ -54,18 +59,59 @@ class AudioToken:
 
     # reference core.py:92-118
     def load_encoder(self):
+        """Builds the encoder with the checkpoint the config (or AUDIOTOKEN_* environment) points at.  Explicit
+        ``state_dict=`` / ``codebook=`` keyword arguments win.  Without any weights the encoders would tokenise with
+        seeded synthetic weights of the named architecture: that is the benchmark / parity mode and has to be asked for
+        with ``synthetic_weights=True`` — otherwise it raises (the reference downloads its checkpoints; there is no
+        network here, so the files have to be provided)."""
         if self.encoder is not None:
             return
-        enc_kw = {k: v for k, v in self.kwargs.items() if k in ('state_dict', 'codebook', 'precision', 'n_layers', 'seed')}
+        from . import checkpoints as ck
+        kw = dict(self.kwargs)
+        enc_kw = {k: v for k, v in kw.items() if k in ('state_dict', 'codebook', 'precision', 'n_layers', 'seed')}
+        synthetic_ok = bool(kw.get('synthetic_weights', False))
+        cfg = self.model_config
+
+        def need(what, env):
+            if synthetic_ok:
+                logger.warning('AudioToken(%s): no %s given, using SEEDED SYNTHETIC weights (tokens are meaningless; '
+                               'benchmark / parity mode)', self.tokenizer_name, what)
+                return
+            raise FileNotFoundError(
+                f'AudioToken({self.tokenizer_name}): no {what}. Set the config field, pass state_dict=/codebook=, or set ${env}; '
+                'pass synthetic_weights=True to run with seeded synthetic weights (benchmarks / parity tests).')
+
         if self.tokenizer_name == Tokenizers.acoustic:
             from .acoustic import AcousticEncoder
-            self.encoder = AcousticEncoder(config=self.model_config, device=self.device, **enc_kw)
-        elif self.tokenizer_name == Tokenizers.semantic_s:
+            if 'state_dict' not in enc_kw:
+                path = ck.resolve(getattr(cfg, 'weights', None), ck.ENV_ENCODEC)
+                if path:
+                    enc_kw['state_dict'] = ck.load_encodec_state_dict(path)
+                else:
+                    need('EnCodec 24 kHz checkpoint', ck.ENV_ENCODEC)
+            enc_kw.pop('codebook', None)
+            enc_kw.pop('n_layers', None)
+            self.encoder = AcousticEncoder(config=cfg, device=self.device, **enc_kw)
+            return
+        if 'state_dict' not in enc_kw:
+            path = ck.resolve(getattr(cfg, 'weights', None), ck.ENV_W2VBERT)
+            if path:
+                enc_kw['state_dict'] = ck.load_w2vbert_state_dict(path)
+            else:
+                need('w2v-BERT 2.0 checkpoint', ck.ENV_W2VBERT)
+        if 'codebook' not in enc_kw:
+            path = ck.resolve(getattr(cfg, 'quantizer_path', None), ck.ENV_VQ)
+            if path:
+                enc_kw['codebook'] = (ck.load_kmeans_centroids(path) if path.endswith(('.bin', '.joblib'))
+                                      else ck.load_vq_codebook(path))
+            else:
+                need('quantizer (codebook) checkpoint', ck.ENV_VQ)
+        if self.tokenizer_name == Tokenizers.semantic_s:
             from .encoder import SemanticSEncoder
-            self.encoder = SemanticSEncoder(config=self.model_config, device=self.device, **enc_kw)
+            self.encoder = SemanticSEncoder(config=cfg, device=self.device, **enc_kw)
         else:
             from .encoder import Wav2VecBertEncoder
-            self.encoder = Wav2VecBertEncoder(config=self.model_config, device=self.device, quantize=True, **enc_kw)
+            self.encoder = Wav2VecBertEncoder(config=cfg, device=self.device, quantize=True, **enc_kw)
 
     # reference core.py:120-185
     def encode(self, audio, chunk_size: Optional[int] = None) -> torch.Tensor:
@@ -81,11 +127,12 @@ class AudioToken:
             assert audio.shape[0] == 1, "Audio must mono"
             return self._encode_single(audio)
         if isinstance(audio, (os.PathLike, Path, str)) and not isinstance(audio, bytes):
-            wave = aio.read_audio(audio, self.model_sample_rate)
             if chunk_size is None:
-                return self._encode_single(wave)
-            seg = int(chunk_size * self.model_sample_rate)
-            parts = [self._encode_single(wave[:, s:s + seg])[0] for s in range(0, wave.shape[-1], seg)]
+                return self._encode_single(aio.read_audio(audio, self.model_sample_rate))
+            # chunks are cut at the file's own rate and resampled one by one, as in batch mode and in the reference
+            # (utils.py:82-101), so encode(path, chunk_size) and encode_batch_files agree at chunk boundaries
+            parts = [self._encode_single(w)[0] for w in aio.read_audio_chunks(audio, self.model_sample_rate, chunk_size)
+                     if w.shape[-1] > 0]
             return torch.cat(parts, dim=-1)
         if isinstance(audio, bytes):
             raise NotImplementedError("Encoding bytes not supported yet")
@@ -118,8 +165,17 @@ class AudioToken:
         if self.tokenizer_name != Tokenizers.acoustic:
             raise NotImplementedError("semantic token -> audio decoding (GPT-2 + Bark, reference decoder.py:79-) is outside "
                                       "the scope of this build (SURVEY.md section 8f)")
+        from . import checkpoints as ck
         from .acoustic import AcousticDecoder
-        kw = {k: v for k, v in {**self.kwargs, **kwargs}.items() if k in ('state_dict', 'seed')}
+        allkw = {**self.kwargs, **kwargs}
+        kw = {k: v for k, v in allkw.items() if k in ('state_dict', 'seed')}
+        if 'state_dict' not in kw:
+            path = ck.resolve(getattr(self.model_config, 'weights', None), ck.ENV_ENCODEC)
+            if path:
+                kw['state_dict'] = ck.load_encodec_state_dict(path)
+            elif not allkw.get('synthetic_weights', False):
+                raise FileNotFoundError(f'AudioToken(acoustic).decode: no EnCodec checkpoint (set config.weights or ${ck.ENV_ENCODEC}, '
+                                        'or pass synthetic_weights=True)')
         self.decoder = AcousticDecoder(device=self.device, **kw)
 
     def decode(self, tokens, **kwargs) -> torch.Tensor:
@@ -137,48 +193,165 @@ class AudioToken:
 
 
 def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, token_rate: int, chunk_size: int,
-                 batch_size: int, num_workers: int, rel_dir: Optional[str]) -> Dict[str, float]:
-    """The batched file loop: read -> segment -> ragged batches -> encode -> one .npy per file."""
+                 batch_size: int, num_workers: int, rel_dir: Optional[str], window_rows: Optional[int] = None,
+                 on_error: str = 'log') -> Dict[str, float]:
+    """The batched file loop as a bounded-memory stream (reference core.py:259-287: DataLoader workers + prefetch +
+    per-batch saves):
+
+      reader threads (host only: file read + RIFF parse, at most 2 * num_workers files in flight)
+        -> window of whole files (<= window_rows token rows; default 4 ragged batches)
+        -> PCM decode + resample on the device, segment rules, length-bucketed ragged batches
+        -> encode (batch k+1 is launched before the tokens of batch k are copied back on a side stream)
+        -> a file whose segments are all done goes to the writer threads (one atomic .npy write per file).
+
+    Host memory is bounded by the files in flight plus one window; nothing is held until the end of the corpus and
+    every finished file is on disk before the next window starts.  `on_error`: 'log' (reference behaviour,
+    datasets.py:136-137: log the file and continue) or 'raise'."""
     t0 = time.time()
     pad = int(chunk_size * sample_rate)
     row_budget = min(max(1, batch_size) * encoder.rows_for(pad), getattr(encoder, 'max_rows_per_batch', 1 << 30))
+    window_rows = int(window_rows) if window_rows else 4 * row_budget
+    device = getattr(encoder, 'device', None)
+    on_gpu = device is not None and torch.device(device).type == 'cuda'
+    errors: Dict[str, str] = {}
+    stats = {'files': 0, 'segments': 0, 'audio_seconds': 0.0, 'windows': 0, 'batches': 0, 'peak_window_bytes': 0}
 
-    def load(path):
+    def fail(path, exc):
+        errors[path] = repr(exc)
+        logger.error('encode_batch_files: skipping %s: %r', path, exc)
+        if on_error == 'raise':
+            raise exc
+
+    def read(path):
         try:
             if not path.lower().endswith(AUDIO_EXTS):
                 raise NotImplementedError(f'unsupported extension: {path}')
-            chunks = aio.read_audio_chunks(path, sample_rate, chunk_size, device=getattr(encoder, 'device', None))
-            segs_ = []
-            for ci, wave in enumerate(chunks):                 # one segment per streamed chunk (datasets.py:88-105)
-                for s in aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size):
-                    s.chunk_index = ci
-                    segs_.append(s)
-            return segs_
-        except Exception as e:  # noqa: BLE001  (reference logs and continues, datasets.py:136-137)
+            return aio.read_wav_raw(path)
+        except Exception as e:  # noqa: BLE001
             return e
 
-    with ThreadPoolExecutor(num_workers) as ex:
-        loaded = list(ex.map(load, files))
-    segs, errors = [], {}
-    for path, res in zip(files, loaded):
-        if isinstance(res, Exception):
-            errors[path] = repr(res)
-        else:
-            segs.extend(res)
-    rows = [encoder.rows_for_tokens(length_tokens(int(s.wave.numel()), sample_rate, token_rate), pad) for s in segs]
-    per_file: Dict[str, Dict[int, np.ndarray]] = {}
-    audio_s = 0.0
-    for idx in bucket_by_rows(rows, row_budget):
-        clips = [segs[i].wave for i in idx]
-        toks = encoder.encode_packed(clips, pad, [rows[i] for i in idx])
-        host = [t.cpu().numpy() for t in toks]            # one sync per batch
-        for i, t in zip(idx, host):
-            s = segs[i]
-            per_file.setdefault(s.file_name, {})[s.chunk_index] = t[:, :s.config.length_tokens]
-            audio_s += s.config.length_seconds
-    for path, chunks in per_file.items():
+    copy_stream = torch.cuda.Stream(device=device) if on_gpu else None
+    writers = ThreadPoolExecutor(max(1, min(4, num_workers)))
+    write_futs = []
+
+    def write(path, chunks):
         dst = aio.token_path_flat(path, outdir) if rel_dir is None else aio.token_path_rel(path, outdir, rel_dir)
         aio.save_tokens_atomic(dst, [chunks[k] for k in sorted(chunks)])
+
+    def launch(clips, rws):
+        """encode one ragged batch; the per-clip token tensors are gathered into ONE device buffer on the compute
+        stream and an event marks the point the side stream may copy it from"""
+        toks = encoder.encode_packed(clips, pad, rws)
+        if not on_gpu:
+            return toks, None, None
+        flat = torch.cat([t.reshape(-1) for t in toks])
+        return [tuple(t.shape) for t in toks], flat, torch.cuda.current_stream(device).record_event()
+
+    def fetch(pending):
+        """tokens of a launched batch -> host arrays; waits only for that batch (side stream + event), so the next
+        batch, already launched, keeps the device busy meanwhile"""
+        shapes, flat, done, idx = pending
+        if flat is None:
+            return [t.cpu().numpy() for t in shapes], idx
+        host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            host.copy_(flat, non_blocking=True)
+            ev = copy_stream.record_event()
+        flat.record_stream(copy_stream)
+        ev.synchronize()
+        out, off, hv = [], 0, host.numpy()
+        for shp in shapes:
+            n = int(np.prod(shp))
+            out.append(hv[off:off + n].reshape(shp))
+            off += n
+        return out, idx
+
+    def run_window(window):
+        """window: list of (path, sr, pcm).  Encodes all of it and hands finished files to the writers."""
+        segs, nbytes = [], 0
+        for path, sr, pcm in window:
+            try:
+                nbytes += pcm.nbytes
+                for ci, wave in enumerate(aio.convert_chunks(sr, pcm, sample_rate, chunk_size, device if on_gpu else None)):
+                    for s in aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size):
+                        s.chunk_index = ci                 # one segment per streamed chunk (datasets.py:88-105)
+                        segs.append(s)
+            except Exception as e:  # noqa: BLE001
+                segs = [s for s in segs if s.file_name != path]
+                fail(path, e)
+        stats['peak_window_bytes'] = max(stats['peak_window_bytes'], nbytes)
+        if not segs:
+            return
+        rows = [encoder.rows_for_tokens(length_tokens(int(s.wave.numel()), sample_rate, token_rate), pad) for s in segs]
+        per_file: Dict[str, Dict[int, np.ndarray]] = {}
+        left: Dict[str, int] = {}
+        for s in segs:
+            left[s.file_name] = left.get(s.file_name, 0) + 1
+
+        def absorb(host, idx):
+            for i, t in zip(idx, host):
+                s = segs[i]
+                per_file.setdefault(s.file_name, {})[s.chunk_index] = np.array(t[:, :s.config.length_tokens])
+                stats['audio_seconds'] += s.config.length_seconds
+                left[s.file_name] -= 1
+                if left[s.file_name] == 0:                 # every chunk of the file is encoded: write it now
+                    write_futs.append((s.file_name, writers.submit(write, s.file_name, per_file.pop(s.file_name))))
+                    stats['files'] += 1
+
+        pending = None
+        for idx in bucket_by_rows(rows, row_budget):
+            launched = launch([segs[i].wave for i in idx], [rows[i] for i in idx])
+            stats['batches'] += 1
+            if pending is not None:
+                absorb(*fetch(pending))
+            pending = (*launched, idx)
+        if pending is not None:
+            absorb(*fetch(pending))
+        stats['segments'] += len(segs)
+        stats['windows'] += 1
+
+    def est_rows(sr, pcm):
+        return length_tokens(int(pcm.shape[0] * sample_rate / max(sr, 1)), sample_rate, token_rate)
+
+    max_in_flight = max(2, 2 * num_workers)
+    try:
+        with ThreadPoolExecutor(num_workers) as readers:
+            it = iter(files)
+            in_flight = []                       # (path, future) in file order
+            window, w_rows = [], 0
+
+            def top_up():
+                while len(in_flight) < max_in_flight:
+                    path = next(it, None)
+                    if path is None:
+                        return
+                    in_flight.append((path, readers.submit(read, path)))
+
+            top_up()
+            while in_flight:
+                path, fut = in_flight.pop(0)
+                res = fut.result()
+                top_up()                         # the readers prefetch while the device encodes the window below
+                if isinstance(res, Exception):
+                    fail(path, res)
+                    continue
+                sr, pcm = res
+                r = est_rows(sr, pcm)
+                if window and w_rows + r > window_rows:
+                    run_window(window)
+                    window, w_rows = [], 0
+                window.append((path, sr, pcm))
+                w_rows += r
+            if window:
+                run_window(window)
+    finally:
+        writers.shutdown(wait=True)
+    for path, f in write_futs:
+        e = f.exception()
+        if e is not None:
+            stats['files'] -= 1
+            fail(path, e)
     wall = time.time() - t0
-    return {'files': len(per_file), 'segments': len(segs), 'audio_seconds': audio_s, 'wall_seconds': wall,
-            'audio_seconds_per_second': audio_s / wall if wall > 0 else 0.0, 'errors': errors}
+    return {**stats, 'wall_seconds': wall, 'audio_seconds_per_second': stats['audio_seconds'] / wall if wall > 0 else 0.0,
+            'errors': errors}

@@ -45,12 +45,7 @@ constexpr int kSoftmaxWarps = 8;                 // two warps per TMEM lane quad
 #endif
 constexpr int kCtasPerSm = B2T_ATTN_CTAS, kTmemCols = 256;
 #endif
-#ifndef B2T_ATTN_DRAIN
-#define B2T_ATTN_DRAIN 0
-#endif
-#ifndef B2T_ATTN_SEQWAIT
-#define B2T_ATTN_SEQWAIT 0
-#endif
+
 constexpr int kPBuf = kQT * kKT * 2;             // one P buffer: kKT / 64 K-major blocks of 128 rows x 128 B
 constexpr int kThreadsAttn = 64 + 32 * kSoftmaxWarps;
 
@@ -503,18 +498,12 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       const uint32_t pb = (uint32_t)ip & 1u, pos = (uint32_t)(nkt + 2 * ip + 1), st = pos & 3u;
       const uint32_t bp = bar(tp::PFULL) + 8u * pb, bv = bar(tp::KVFULL) + 8u * st;
       const uint32_t pp = ((uint32_t)ip >> 1) & 1u, pv = (pos >> 2) & 1u;
-#if B2T_ATTN_SEQWAIT
+      // One wait after the other.  Probing both barriers in one loop iteration (two mbarrier.try_wait in flight in
+      // the warp, results AND-ed) is logically equivalent and ~1 % faster, but on the 8-GPU nodes it made about one
+      // CTA in 3 million proceed early (a wrong 128-row tile, or a launch failure): tools/kernel_soak.py, round-2 notes
+      // in profiles/.  Rule for this library: at most one potentially-blocking try_wait in flight per warp.
       mbar_wait(bp, pp);
       mbar_wait(bv, pv);
-#else
-      uint32_t spins = 0;
-      for (;;) {                                      // both probes in flight together
-        bool ok = mbar_try_wait(bp, pp);
-        ok &= mbar_try_wait(bv, pv);
-        if (ok) break;
-        if (++spins > (1u << 26)) b2t_trap_report("attention_tc2 PV issuer: P tile / V slot wait (key tile, ring position)", (unsigned)ip, pos);
-      }
-#endif
       tc_fence_after();
       if (leader) {
         const uint64_t dv = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4)), dp = dp0 + (uint64_t)(pb * (kPBuf >> 4));
@@ -530,19 +519,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         if (ip == nkt - 1) umma_commit(bar(tp::OFULL));
       }
     }
-#if B2T_ATTN_DRAIN
-    // Drain: nobody waits for the last tcgen05.commit arrivals on the slot-empty / P-empty barriers.  They are
-    // asynchronous writes into this CTA's shared memory; the CTA must not exit (and hand the shared memory to the
-    // next CTA of the SM) before every one of them has landed.
-    for (int s = 0; s < tp::kSlots; ++s) {
-      const int uses = (3 * nkt - s + 3) >> 2;                      // ring positions p < 3 nkt with p % 4 == s
-      if (uses > 0) mbar_wait(bar(tp::KVEMPTY) + 8u * s, (uint32_t)(uses - 1) & 1u);
-    }
-    for (int b = 0; b < 2; ++b) {
-      const int uses = (nkt - b + 1) >> 1;                          // key tiles ip < nkt with ip % 2 == b
-      if (uses > 0) mbar_wait(bar(tp::PEMPTY) + 8u * b, (uint32_t)(uses - 1) & 1u);
-    }
-#endif
     __syncwarp();
   } else if (warp == 1) {
     // ===== S issuer (whole warp waits, one elected lane issues) =====
@@ -563,18 +539,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       const uint32_t b = j & 1u, st = pos & 3u;
       const uint32_t bk = bar(tp::KVFULL) + 8u * st, bs = bar(tp::SEMPTY) + 8u * b;
       const uint32_t pk = (pos >> 2) & 1u, ps = ((j >> 1) & 1u) ^ 1u;
-#if B2T_ATTN_SEQWAIT
-      mbar_wait(bk, pk);
+      mbar_wait(bk, pk);                            // one wait after the other (see the PV issuer)
       mbar_wait(bs, ps);
-#else
-      uint32_t spins = 0;
-      for (;;) {                                    // both probes in flight together
-        bool ok = mbar_try_wait(bk, pk);
-        ok &= mbar_try_wait(bs, ps);
-        if (ok) break;
-        if (++spins > (1u << 26)) b2t_trap_report("attention_tc2 S issuer: K slot / S buffer wait (S tile, ring position)", j, pos);
-      }
-#endif
       tc_fence_after();
       if (leader) {
         const uint64_t dk = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4));

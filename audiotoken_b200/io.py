@@ -95,18 +95,23 @@ def read_audio(path, model_sample_rate: int, device=None) -> torch.Tensor:
     return convert_audio(audio, int(sr), model_sample_rate)
 
 
-def read_audio_chunks(path, model_sample_rate: int, chunk_size: int, device=None) -> List[torch.Tensor]:
-    """The reference's batch reader (utils.py:71-101): the file is streamed in chunks of `chunk_size` seconds AT ITS
-    OWN sample rate, every chunk must be mono and is resampled on its own with torchaudio's Resample — so a file
-    whose rate differs from the model's has filter edges at every chunk boundary.  Returns the resampled chunks
-    (fp32 [1, L_i]); on a CUDA `device` decode + resampling run on the GPU and the chunks stay there."""
+def read_wav_raw(path) -> Tuple[int, np.ndarray]:
+    """Host-only half of the batch reader: RIFF/WAV file -> (sample_rate, PCM array [L] or [L, C]) untouched.
+    Runs in the reader threads of the streaming file loop (no CUDA calls, releases the GIL in the file read)."""
     if not str(path).lower().endswith('.wav'):
         raise NotImplementedError(f'{path}: only .wav can be decoded offline (no ffmpeg/torchcodec in this image)')
     from scipy.io import wavfile
     sr, data = wavfile.read(str(path))
-    sr = int(sr)
     if data.ndim == 2 and data.shape[1] != 1:
         raise AssertionError(f'Audio needs to be mono, provided {data.shape[1]} channels for {path}')
+    return int(sr), data
+
+
+def convert_chunks(sr: int, data: np.ndarray, model_sample_rate: int, chunk_size: int, device=None) -> List[torch.Tensor]:
+    """Second half of the reference's batch reader (utils.py:82-101): the PCM stream is cut into chunks of `chunk_size`
+    seconds AT ITS OWN sample rate and every chunk is resampled on its own — so a file whose rate differs from the
+    model's has filter edges at every chunk boundary.  Returns fp32 [1, L_i] chunks; on a CUDA `device` PCM decode and
+    resampling run on the GPU (ingest.py) and the chunks stay there."""
     on_gpu = device is not None and torch.device(device).type == 'cuda' and data.dtype in (np.int16, np.float32)
     if on_gpu:
         from . import ingest
@@ -128,6 +133,12 @@ def read_audio_chunks(path, model_sample_rate: int, chunk_size: int, device=None
         out.append(ingest.convert_audio(piece, sr, model_sample_rate, device) if on_gpu
                    else convert_audio(piece, sr, model_sample_rate))
     return out
+
+
+def read_audio_chunks(path, model_sample_rate: int, chunk_size: int, device=None) -> List[torch.Tensor]:
+    """The reference's batch reader (utils.py:71-101) = read_wav_raw + convert_chunks."""
+    sr, data = read_wav_raw(path)
+    return convert_chunks(sr, data, model_sample_rate, chunk_size, device)
 
 
 def write_wav(path, wave: torch.Tensor, sample_rate: int) -> None:

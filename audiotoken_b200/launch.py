@@ -34,7 +34,7 @@ def run(args) -> dict:
         except Exception:  # noqa: BLE001
             durations.append(0.0)
     mine = shard_files(files, durations, world, rank)
-    tok = AudioToken(tokenizer=args.tokenizer, device=f'cuda:{local}')
+    tok = AudioToken(tokenizer=args.tokenizer, device=f'cuda:{local}', synthetic_weights=args.synthetic_weights)
     stats = {'files': 0, 'audio_seconds': 0.0, 'wall_seconds': 0.0}
     if mine:
         # audio_dir semantics (relative output layout) on an explicit shard of the directory
@@ -54,6 +54,8 @@ def main():
     ap.add_argument('--batch_size', type=int, default=64)
     ap.add_argument('--chunk_size', type=int, default=30)
     ap.add_argument('--num_workers', type=int, default=12)
+    ap.add_argument('--synthetic-weights', action='store_true',
+                    help='seeded synthetic weights instead of checkpoints (benchmarks; see audiotoken_b200/checkpoints.py)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', 1))
     if world > 1:

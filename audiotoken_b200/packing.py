@@ -103,6 +103,11 @@ def plan_semantic(lengths: Sequence[int], wave_offsets: Sequence[int], padded_sa
             raise ValueError('rows[i] must be in [1, T_i]')
     if np.any(valid_rows < 1):
         raise ValueError('a clip has no valid frame')
+    if np.any(rows_arr < valid_rows):
+        # the attention kernels take valid_rows[i] keys from clip i's packed rows: fewer rows than keys would read the
+        # next clip's rows (and differ from the reference, whose keys always cover the whole clip)
+        i = int(np.argmax(rows_arr < valid_rows))
+        raise ValueError(f'rows[{i}] = {int(rows_arr[i])} is smaller than the {int(valid_rows[i])} valid token rows of the clip')
     frame_off = np.zeros(n + 1, dtype=np.int64)
     frame_off[1:] = np.cumsum(n_valid)
     row_off = np.zeros(n + 1, dtype=np.int64)

@@ -66,7 +66,10 @@ def log_mel(wave: torch.Tensor, dtype=torch.float32, mel_in_bf16: bool = False) 
 
     `mel_in_bf16` reproduces the one autocast cast point of the front end on CUDA: the
     ``matmul(power, mel_filters)`` at processors.py:184 runs with bf16 inputs/outputs.
+    Device-generic: on a CUDA `wave` under ``torch.amp.autocast`` the plain matmul below is cast by autocast itself
+    (oracle/hf_reference.py runs it that way, as the reference is deployed).
     """
+    dev = wave.device
     w = wave.to(dtype) * (2 ** 15)
     B, L = w.shape
     N = num_frames(L)
@@ -75,18 +78,18 @@ def log_mel(wave: torch.Tensor, dtype=torch.float32, mel_in_bf16: bool = False) 
     pre = fr.clone()
     pre[:, :, 1:] = fr[:, :, 1:] - PREEMPH * fr[:, :, :-1]       # :171-172 (RHS = old values)
     pre[:, :, 0] = fr[:, :, 0] * (1 - PREEMPH)                   # :173
-    pre = pre * povey_window(dtype)                              # :175
-    buf = torch.zeros(B, N, NFFT, dtype=dtype)
+    pre = pre * povey_window(dtype).to(dev)                      # :175
+    buf = torch.zeros(B, N, NFFT, dtype=dtype, device=dev)
     buf[:, :, :FRAME] = pre
     spec = torch.fft.rfft(buf)                                   # :177
     power = spec.abs().pow(2.0)                                  # :181
-    M = mel_filters(dtype)
+    M = mel_filters(dtype).to(dev)
     if mel_in_bf16:
         mel = (power.to(torch.bfloat16).float() @ M.to(torch.bfloat16).float())
         mel = mel.to(torch.bfloat16).to(dtype)
     else:
         mel = power @ M                                          # :184
-    mel = torch.maximum(mel, torch.tensor(MEL_FLOOR, dtype=dtype))
+    mel = torch.maximum(mel.to(dtype), torch.tensor(MEL_FLOOR, dtype=dtype, device=dev))
     return torch.log(mel)                                        # :188
 
 
@@ -122,7 +125,7 @@ def features(wave: torch.Tensor, mask: torch.Tensor, pad_to_multiple_of: int = 2
     P = 0
     if pad_to_multiple_of > 0 and T % pad_to_multiple_of:
         P = pad_to_multiple_of - T % pad_to_multiple_of
-    x = torch.where(fm == 0, torch.tensor(1.0, dtype=dtype), x)  # :200 padding_value = 1
+    x = torch.where(fm == 0, torch.tensor(1.0, dtype=dtype, device=x.device), x)  # :200 padding_value = 1
     x = torch.nn.functional.pad(x, (0, 0, 0, P), value=1.0)      # :201
     am = torch.nn.functional.pad(fm[:, :, 0], (0, P), value=0.0) # :204 (first sub-frame)
     return x, am

@@ -127,6 +127,54 @@ def main():
         del model
 
 
+LONG_LENGTHS = [160000, 480000, 123456]        # 10 s (BASELINE configs[1]), 30 s (chunk_size, T = 1500), an odd length
+
+
+def long_rows(valid_rows: int):
+    """Rows of a clip kept in the long fixtures: the start, the rows around the left clamp (distance -64), a stride
+    over the body and the last valid rows."""
+    keep = set(range(0, 12)) | set(range(58, 72)) | set(range(0, valid_rows, 41)) | set(range(max(0, valid_rows - 12), valid_rows))
+    return np.array(sorted(r for r in keep if r < valid_rows), dtype=np.int64)
+
+
+def main_long():
+    """2-layer goldens at BASELINE shapes (T = 500 and T = 1500 in one batch padded to 30 s): pins the -64 clamp of the
+    relative-key bias (modeling_wav2vec2_bert.py:52), key masking over >1000 padded keys and long-row softmax to the
+    real reference.  Only selected rows of the hidden state are stored (fp32), tokens for every valid row."""
+    torch.manual_seed(0)
+    torch.set_num_threads(16)
+    proc_mod, att_mod = load_reference_modules()
+    processor = proc_mod.Wav2VecBertProcessor()
+    wave, mask = make_clips(LONG_LENGTHS, 480000, 16000)
+    with torch.no_grad():
+        out = processor(wave, mask, 2)
+    from transformers import Wav2Vec2BertConfig, Wav2Vec2BertModel
+    from transformers.models.wav2vec2_bert.modeling_wav2vec2_bert import Wav2Vec2BertSelfAttention
+    Wav2Vec2BertSelfAttention.forward = att_mod.forward          # reference encoder.py:14-15
+    n_layers = 2
+    sd = synthetic_w2vbert_state_dict(n_layers, seed=0)
+    model = Wav2Vec2BertModel(Wav2Vec2BertConfig(num_hidden_layers=n_layers))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and set(missing) <= {'masked_spec_embed'}
+    model.eval()
+    with torch.no_grad():
+        hs = model(out['input_features'], attention_mask=out['attention_mask'], output_hidden_states=True).hidden_states
+    emb = torch.nn.functional.layer_norm(hs[n_layers], (1024,))
+    cb = synthetic_codebook(2048, 1024, seed=4)
+    d = torch.cdist(emb.double(), cb.double().unsqueeze(0).expand(emb.shape[0], -1, -1))
+    tok = torch.argmin(d, dim=-1)
+    am = out['attention_mask']
+    save = dict(lengths=np.array(LONG_LENGTHS), total=480000, tokens=tok.numpy().astype(np.int16),
+                attention_mask=am.numpy().astype(np.uint8))
+    for i in range(len(LONG_LENGTHS)):
+        rows = long_rows(int(am[i].sum()))
+        save[f'rows_{i}'] = rows
+        save[f'hidden_{i}'] = hs[n_layers][i, rows].numpy().astype(np.float32)
+        save[f'features_{i}'] = out['input_features'][i, rows].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, 'conformer_long_l2.npz'), **save)
+    print('long', tuple(hs[n_layers].shape), {k: v.shape for k, v in save.items() if hasattr(v, 'shape')})
+
+
 def main_acoustic():
     """EnCodec stand-in (HF EncodecModel) on the synthetic weights: embeddings + RVQ-16 codes."""
     from transformers import EncodecConfig, EncodecModel
@@ -159,6 +207,9 @@ def main_acoustic():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'acoustic':
         main_acoustic()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'long':
+        main_long()
     else:
         main()
+        main_long()
         main_acoustic()

@@ -135,12 +135,12 @@ def test_acoustic_packed_equals_padded(enc, enc16, cuda_device, prec):
 
 
 def test_acoustic_audiotoken_api(cuda_device, tmp_path):
-    tok = AudioToken(tokenizer=Tokenizers.acoustic, device='cuda:0', num_codebooks=8)
+    tok = AudioToken(tokenizer=Tokenizers.acoustic, device='cuda:0', num_codebooks=8, synthetic_weights=True)
     assert tok.model_sample_rate == 24000
     x = synthetic_waveform(5, 24000, 24000).unsqueeze(0)
     t = tok.encode(x)
     assert t.shape == (1, 8, 75) and t.dtype == torch.int16 and t.device.type == 'cpu'
-    full = AudioToken(tokenizer='acoustic', device='cuda:0').encode(x)
+    full = AudioToken(tokenizer='acoustic', device='cuda:0', synthetic_weights=True).encode(x)
     assert full.shape == (1, 16, 75) and torch.equal(full[:, :8], t)       # RVQ prefix property
     files = []
     for i, n in enumerate((24000 * 2 + 4000, 9000, 24000 + 100)):
@@ -186,11 +186,11 @@ def test_acoustic_decode_matches_golden(cuda_device, golden_dir, tag):
 
 def test_acoustic_audiotoken_encode_decode_roundtrip_api(cuda_device):
     """AudioToken.decode for the acoustic tokenizer (reference core.py:317-357): shapes, dtype, determinism."""
-    tok = AudioToken(tokenizer=Tokenizers.acoustic, device='cuda:0', num_codebooks=8)
+    tok = AudioToken(tokenizer=Tokenizers.acoustic, device='cuda:0', num_codebooks=8, synthetic_weights=True)
     x = synthetic_waveform(5, 24000, 24000).unsqueeze(0)
     t = tok.encode(x)                                                     # [1, 8, 75]
     y = tok.decode(t)
     assert y.shape == (1, 24000) and y.dtype == torch.float32 and y.device.type == 'cpu'
     assert torch.equal(y, tok.decode(t.numpy()))
     with pytest.raises(NotImplementedError):
-        AudioToken(tokenizer=Tokenizers.semantic_m, device='cuda:0', n_layers=1).decode(torch.zeros(1, 1, 10, dtype=torch.long))
+        AudioToken(tokenizer=Tokenizers.semantic_m, device='cuda:0', n_layers=1, synthetic_weights=True).decode(torch.zeros(1, 1, 10, dtype=torch.long))

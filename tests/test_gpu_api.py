@@ -37,7 +37,7 @@ def test_encode_batch_files_matches_per_segment_reference_semantics(cuda_device,
         aio.write_wav(str(p), synthetic_waveform(70 + i, n, SR), SR)
         files.append(str(p))
     (indir / 'notes.txt').write_text('not audio')
-    tok = AudioToken(tokenizer=Tokenizers.semantic_m, device='cuda:0', n_layers=2)
+    tok = AudioToken(tokenizer=Tokenizers.semantic_m, device='cuda:0', n_layers=2, synthetic_weights=True)
     out1 = tmp_path / 'out_files'
     tok.encode_batch_files(batch_size=2, outdir=str(out1), chunk_size=chunk, num_workers=2, audio_files=files)
     for f in files:
@@ -61,7 +61,7 @@ def test_encode_batch_files_matches_per_segment_reference_semantics(cuda_device,
 
 
 def test_encode_single_inputs(cuda_device, tmp_path):
-    tok = AudioToken(tokenizer='semantic_s', device='cuda:0', n_layers=1)
+    tok = AudioToken(tokenizer='semantic_s', device='cuda:0', n_layers=1, synthetic_weights=True)
     assert tok.model_sample_rate == 16000 and tok.num_codebooks == 16
     x = synthetic_waveform(3, 16037, SR).unsqueeze(0)
     t = tok.encode(x)

@@ -10,7 +10,9 @@ import torch
 
 from audiotoken_b200 import io as aio
 from audiotoken_b200.configs import AudioConfig, Tokenizers, num_codebooks_to_bandwidth, AcousticEncoderConfig
+from audiotoken_b200 import packing
 from audiotoken_b200.sharding import lpt_shards, shard_files
+from audiotoken_b200.weights import synthetic_waveform
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -138,3 +140,70 @@ def test_acoustic_plan_tables():
     assert not q.aligned320 and [int(v) for v in q.lens[4]] == [2, 76] and q.tile_clip[0].size > 0
     with pytest.raises(ValueError):
         plan_acoustic([333], [0], [333], tiles=False)
+
+
+class _FakeEncoder:
+    """Host stand-in with the three calls encode_files makes; token j of a clip = (clip sum hash + j) mod 1000."""
+    device = None
+    max_rows_per_batch = 4000
+    calls = 0
+
+    def rows_for(self, padded_samples):
+        return packing.padded_rows(padded_samples)
+
+    def rows_for_tokens(self, n_tokens, padded_samples):
+        return max(1, min(n_tokens, self.rows_for(padded_samples)))
+
+    @staticmethod
+    def expected(clip, rows):
+        h = int(abs(float(clip.double().sum())) * 1000) % 997
+        return ((h + np.arange(rows)) % 1000).astype(np.int16)[None, :]
+
+    def encode_packed(self, clips, padded_samples, rows=None):
+        type(self).calls += 1
+        return [torch.from_numpy(self.expected(c, r)) for c, r in zip(clips, rows)]
+
+
+def test_streaming_file_loop_windows_writes_and_errors(tmp_path, caplog):
+    """encode_files with a host stand-in encoder: many small windows, every file written once with the tokens of its
+    chunks in order, unreadable / unsupported files logged and skipped (reference datasets.py:136-137)."""
+    from audiotoken_b200.core import encode_files
+    sr, chunk = 16000, 2
+    rng = np.random.default_rng(3)
+    indir = tmp_path / 'in'
+    indir.mkdir()
+    files, lens = [], {}
+    for i in range(23):
+        n = int(rng.integers(3300, 5 * sr))
+        p = indir / f'f{i:02d}.wav'
+        aio.write_wav(str(p), synthetic_waveform(i, n, sr), sr)
+        files.append(str(p))
+        lens[str(p)] = n
+    bad = indir / 'broken.wav'
+    bad.write_bytes(b'RIFFnonsense')
+    mp3 = indir / 'x.mp3'
+    mp3.write_bytes(b'\\x00' * 64)
+    files[5:5] = [str(bad), str(mp3)]
+    out = tmp_path / 'out'
+    _FakeEncoder.calls = 0
+    with caplog.at_level('ERROR', logger='audiotoken_b200'):
+        st = encode_files(_FakeEncoder(), files, aio.sanitize_path(out), sr, 50, chunk, batch_size=4, num_workers=3,
+                          rel_dir=None, window_rows=700)
+    assert st['files'] == 23 and set(st['errors']) == {str(bad), str(mp3)}
+    assert st['windows'] > 3 and _FakeEncoder.calls >= st['windows']
+    assert sum('skipping' in r.getMessage() for r in caplog.records) == 2
+    for f in files:
+        if f in st['errors']:
+            continue
+        got = np.load(aio.token_path_flat(f, str(out)))
+        wave = aio.read_audio(f, sr)
+        want = []
+        for a in range(0, wave.shape[1], chunk * sr):
+            seg = wave[0, a:a + chunk * sr]
+            if seg.numel() < 3200:
+                continue
+            want.append(_FakeEncoder.expected(seg, packing.length_tokens(seg.numel(), sr, 50)))
+        want = np.hstack(want)
+        assert got.dtype == np.int16 and got.shape == want.shape and np.array_equal(got, want), f
+    with pytest.raises(Exception):
+        encode_files(_FakeEncoder(), [str(bad)], aio.sanitize_path(out), sr, 50, chunk, 4, 2, None, on_error='raise')

@@ -257,3 +257,54 @@ def test_hubert_ragged_equals_padded(golden_dir):
     other = hubert.hidden_states_ragged(clips[1:2], 2 * total, sd)[0]
     ref = torch.as_tensor(g['h11'])[1, :other[11].shape[0]].double()
     assert float((other[11].double() - ref).norm() / ref.norm()) > 1e-3
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm())
+
+
+def _long_batch(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'conformer_long_l2.npz'))
+    lengths = [int(v) for v in g['lengths']]
+    total = int(g['total'])
+    wave = torch.zeros(len(lengths), total)
+    mask = torch.zeros(len(lengths), total)
+    for i, n in enumerate(lengths):
+        wave[i, :n] = synthetic_waveform(i, n, 16000)
+        mask[i, :n] = 1
+    return g, wave, mask
+
+
+def test_hf_reference_matches_long_golden(golden_dir):
+    """The secondary oracle (HF model + the restated relative-key SDPA attention + the device-generic front end) on the
+    CPU in fp32 against the fixture the REAL reference files produced at BASELINE shapes (10 s / 30 s clips padded to
+    30 s, T = 1500): pins oracle/hf_reference.py before the GPU tests run it under CUDA autocast."""
+    from oracle import hf_reference as R
+    g, wave, mask = _long_batch(golden_dir)
+    emb, am, hid = R.reference_embeddings(wave, mask, synthetic_w2vbert_state_dict(2, 0), 2, 'cpu', autocast=False)
+    assert np.array_equal(am.numpy().astype(np.uint8), g['attention_mask'])
+    for i in range(3):
+        rows = g[f'rows_{i}']
+        assert rel_err(hid[i, rows], torch.from_numpy(g[f'hidden_{i}'])) < 1e-6
+    tok = R.vq_eval_tokens(emb, synthetic_codebook(2048, 1024, 4)).view(3, -1).numpy()
+    m = g['attention_mask'].astype(bool)
+    assert (tok[m] == g['tokens'][m]).mean() >= 0.999
+
+
+def test_conformer_oracle_matches_long_golden(golden_dir):
+    """The plain restatement (oracle/conformer.py) at T = 1500: the -64 / +8 clamp of the relative-key bias and key
+    masking over >1000 padded keys against the real reference's output."""
+    g, wave, mask = _long_batch(golden_dir)
+    sd = synthetic_w2vbert_state_dict(2, 0)
+    feats, am = fbank.features(wave, mask)
+    for i in range(3):
+        rows = g[f'rows_{i}']
+        assert float((feats[i, rows] - torch.from_numpy(g[f'features_{i}'])).abs().max()) == 0.0
+    hs = conformer.hidden_states(feats, am, sd, 2)
+    for i in range(3):
+        rows = g[f'rows_{i}']
+        assert rel_err(hs[2][i, rows], torch.from_numpy(g[f'hidden_{i}'])) < 1e-5
+    idx, _ = quantize.nearest_centroid(conformer.final_embedding(hs[2]).reshape(-1, 1024), synthetic_codebook(2048, 1024, 4))
+    m = g['attention_mask'].astype(bool)
+    assert (idx.view(3, -1).numpy()[m] == g['tokens'][m]).mean() >= 0.999
