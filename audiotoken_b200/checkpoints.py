@@ -25,6 +25,7 @@ ENV_W2VBERT = 'AUDIOTOKEN_W2VBERT_WEIGHTS'
 ENV_VQ = 'AUDIOTOKEN_VQ_QUANTIZER'
 ENV_ENCODEC = 'AUDIOTOKEN_ENCODEC_WEIGHTS'
 ENV_KMEANS = 'AUDIOTOKEN_HUBERT_KMEANS'
+ENV_HUBERT = 'AUDIOTOKEN_HUBERT_WEIGHTS'
 
 
 def _load_tensor_file(path: str) -> Dict[str, torch.Tensor]:
@@ -62,6 +63,15 @@ def load_w2vbert_state_dict(path: str) -> Dict[str, torch.Tensor]:
         out[k] = v.float()
     if 'feature_projection.projection.weight' not in out:
         raise ValueError(f'{path}: not a Wav2Vec2BertModel state dict (feature_projection.projection.weight missing)')
+    return out
+
+
+def load_hubert_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """HF HubertModel tensors (``HubertModel.from_pretrained('voidful/mhubert-base')``, encoder.py:72)."""
+    sd = _load_tensor_file(path)
+    out = {(k[len('hubert.'):] if k.startswith('hubert.') else k): v.float() for k, v in sd.items()}
+    if 'feature_extractor.conv_layers.0.conv.weight' not in out:
+        raise ValueError(f'{path}: not a HubertModel state dict (feature_extractor.conv_layers.0.conv.weight missing)')
     return out
 
 

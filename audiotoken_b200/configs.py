@@ -86,6 +86,20 @@ class SemanticSConfig(EncoderConfig):
 
 
 @dataclass
+class HubertEncoderConfig(EncoderConfig):
+    """The reference's own semantic_s (configs.py:49-59): mHuBERT-base, hidden state 11, k-means 1000 centres."""
+    model_id: str = 'voidful/mhubert-base'
+    model_sample_rate: int = 16_000
+    model_token_rate: int = 50
+    output_layer: int = 11
+    codebook_size: int = 1000
+    hidden_size: int = 768
+    pad_token: Optional[int] = 0
+    weights: Optional[str] = None          # dir/file with HF HubertModel tensors
+    quantizer_path: Optional[str] = None   # joblib scikit-learn KMeans (mhubert_base_vp_en_es_fr_it3_L11_km1000.bin)
+
+
+@dataclass
 class AudioConfig:
     """Per-segment metadata; `length_tokens` is the number of tokens that are saved
     (reference configs.py:213-218: ceil(length_seconds * model_token_rate))."""

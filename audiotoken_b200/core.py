@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import io as aio
-from .configs import (AcousticEncoderConfig, AUDIO_EXTS, EncoderConfig, SemanticSConfig, Tokenizers,
+from .configs import (AcousticEncoderConfig, AUDIO_EXTS, EncoderConfig, HubertEncoderConfig, SemanticSConfig, Tokenizers,
                       Wav2VecBertConfig, num_codebooks_to_bandwidth)
 from .packing import bucket_by_rows, length_tokens, padded_rows
 
@@ -50,7 +50,12 @@ class AudioToken:
         if self.tokenizer_name == Tokenizers.acoustic:
             self.model_config = AcousticEncoderConfig(bandwidth=num_codebooks_to_bandwidth(self.num_codebooks))
         elif self.tokenizer_name == Tokenizers.semantic_s:
-            self.model_config = SemanticSConfig()
+            # BASELINE.json defines semantic_s as a shallower w2v-BERT cut + k-means (the default here); the reference's
+            # own semantic_s is mHuBERT-base + k-means (encoder.py:60-108): semantic_s_model='hubert'
+            which = self.kwargs.get('semantic_s_model', os.environ.get('AUDIOTOKEN_SEMANTIC_S', 'w2vbert'))
+            if which not in ('w2vbert', 'hubert'):
+                raise ValueError("semantic_s_model must be 'w2vbert' or 'hubert'")
+            self.model_config = HubertEncoderConfig() if which == 'hubert' else SemanticSConfig()
         elif self.tokenizer_name == Tokenizers.semantic_m:
             self.model_config = Wav2VecBertConfig()
         else:
@@ -92,6 +97,23 @@ class AudioToken:
             enc_kw.pop('codebook', None)
             enc_kw.pop('n_layers', None)
             self.encoder = AcousticEncoder(config=cfg, device=self.device, **enc_kw)
+            return
+        hubert = isinstance(cfg, HubertEncoderConfig)
+        if hubert:
+            from .hubert import HubertEncoder
+            if 'state_dict' not in enc_kw:
+                path = ck.resolve(cfg.weights, ck.ENV_HUBERT)
+                if path:
+                    enc_kw['state_dict'] = ck.load_hubert_state_dict(path)
+                else:
+                    need('mHuBERT checkpoint', ck.ENV_HUBERT)
+            if 'codebook' not in enc_kw:
+                path = ck.resolve(cfg.quantizer_path, ck.ENV_KMEANS)
+                if path:
+                    enc_kw['codebook'] = ck.load_kmeans_centroids(path)
+                else:
+                    need('k-means centres (joblib)', ck.ENV_KMEANS)
+            self.encoder = HubertEncoder(config=cfg, device=self.device, **enc_kw)
             return
         if 'state_dict' not in enc_kw:
             path = ck.resolve(getattr(cfg, 'weights', None), ck.ENV_W2VBERT)
@@ -140,6 +162,8 @@ class AudioToken:
 
     # reference core.py:187-196
     def _encode_single(self, audio: torch.Tensor) -> torch.Tensor:
+        if hasattr(self.encoder, 'encode_single'):            # mHuBERT: the processor transform comes first (core.py:188-189)
+            return self.encoder.encode_single(audio).cpu()
         input_batch = audio.to(self.device, torch.float32)
         attention_mask = torch.ones_like(input_batch)
         toks = self.encoder(input_batch, attention_mask)

@@ -35,16 +35,17 @@ __global__ void __launch_bounds__(256)
 attention_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ dist_emb,
                       const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
                       const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
-                      T* __restrict__ out) {
+                      T* __restrict__ out, int H /* hidden width = 64 * heads; qkv rows are 3 H wide */) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SimtSmem& s = *reinterpret_cast<SimtSmem*>(smem_raw);
+  const int QKV = 3 * H;
   const int clip = qtile_clip[blockIdx.x], q0 = qtile_q0[blockIdx.x], head = blockIdx.y;
   const int r0 = row_off[clip], rows = row_off[clip + 1] - r0, nkeys = valid_rows[clip];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < kQT * kHD; i += 256) {
     int qi = i >> 6, d = i & 63;
-    s.q[qi][d] = (q0 + qi < rows) ? ld_act(qkv + (size_t)(r0 + q0 + qi) * kQKV + head * kHD + d) : 0.f;
+    s.q[qi][d] = (q0 + qi < rows) ? ld_act(qkv + (size_t)(r0 + q0 + qi) * QKV + head * kHD + d) : 0.f;
   }
   for (int i = tid; i < kRel * kHD; i += 256) s.e[i >> 6][i & 63] = ld_act(dist_emb + i);
   __syncthreads();
@@ -65,9 +66,9 @@ attention_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ dist_emb,
     for (int i = tid; i < kKT * kHD; i += 256) {
       int kj = i >> 6, d = i & 63;
       bool ok = k0 + kj < nkeys;
-      const T* base = qkv + (size_t)(r0 + k0 + kj) * kQKV + head * kHD + d;
-      s.k[kj][d] = ok ? ld_act(base + kH) : 0.f;
-      s.v[kj][d] = ok ? ld_act(base + 2 * kH) : 0.f;
+      const T* base = qkv + (size_t)(r0 + k0 + kj) * QKV + head * kHD + d;
+      s.k[kj][d] = ok ? ld_act(base + H) : 0.f;
+      s.v[kj][d] = ok ? ld_act(base + 2 * H) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -112,7 +113,7 @@ attention_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ dist_emb,
     const int qpos = q0 + warp * 8 + i;
     if (qpos < rows) {
       float inv = 1.0f / l[i];
-      T* o = out + (size_t)(r0 + qpos) * kH + head * kHD;
+      T* o = out + (size_t)(r0 + qpos) * H + head * kHD;
       st_act(o + lane, o0[i] * inv);
       st_act(o + lane + 32, o1[i] * inv);
     }
@@ -369,28 +370,36 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 
 }  // namespace
 
-int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, cudaStream_t st);  // attention_tc.cu
+int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, int heads, cudaStream_t st);  // attention_tc.cu
 
 extern "C" int b2t_relkey_attention(const void* qkv, const void* dist_emb, const b2t_batch* b,
                                     void* out, int precision, int impl, void* stream) {
-  B2T_REQUIRE(qkv && dist_emb && b && out, B2T_ERR_ARG, "b2t_relkey_attention: null argument");
+  return b2t_attention(qkv, dist_emb, b, out, kHeads, precision, impl, stream);
+}
+
+extern "C" int b2t_attention(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, int heads,
+                             int precision, int impl, void* stream) {
+  B2T_REQUIRE(qkv && dist_emb && b && out, B2T_ERR_ARG, "b2t_attention: null argument");
+  B2T_REQUIRE(heads >= 1 && heads <= 64, B2T_ERR_ARG, "b2t_attention: heads must be in [1, 64] (got %d)", heads);
+  B2T_REQUIRE(heads == kHeads || impl != B2T_IMPL_MMA_SYNC, B2T_ERR_ARG, "b2t_attention: the mma.sync cross-check kernel is 16 heads only");
   int rc = b2t_arch_ok();
   if (rc != B2T_OK) return rc;
   if (b->n_qtiles <= 0) return B2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(b->n_qtiles, kHeads);
+  const int H = heads * kHD;
+  dim3 grid(b->n_qtiles, heads);
   if (precision == B2T_PREC_FP32) {
     B2T_REQUIRE(impl != B2T_IMPL_TENSOR, B2T_ERR_ARG, "b2t_relkey_attention: tensor path is bf16 only");
     B2T_SMEM_OPT_IN(sizeof(SimtSmem), attention_simt_kernel<float, false>);
     attention_simt_kernel<float, false><<<grid, 256, sizeof(SimtSmem), st>>>(
-        (const float*)qkv, (const float*)dist_emb, b->row_off, b->valid_rows, b->qtile_clip, b->qtile_q0, (float*)out);
+        (const float*)qkv, (const float*)dist_emb, b->row_off, b->valid_rows, b->qtile_clip, b->qtile_q0, (float*)out, H);
   } else if (impl == B2T_IMPL_SIMT) {
     B2T_SMEM_OPT_IN(sizeof(SimtSmem), attention_simt_kernel<__nv_bfloat16, true>);
     attention_simt_kernel<__nv_bfloat16, true><<<grid, 256, sizeof(SimtSmem), st>>>(
         (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dist_emb, b->row_off, b->valid_rows, b->qtile_clip, b->qtile_q0,
-        (__nv_bfloat16*)out);
+        (__nv_bfloat16*)out, H);
   } else if (impl != B2T_IMPL_MMA_SYNC) {
-    return b2t_attention_tensor_tc(qkv, dist_emb, b, out, st);
+    return b2t_attention_tensor_tc(qkv, dist_emb, b, out, heads, st);
   } else {
     B2T_SMEM_OPT_IN(sizeof(MmaSmem), attention_mma_kernel);
     attention_mma_kernel<<<grid, 128, sizeof(MmaSmem), st>>>(

@@ -415,7 +415,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                      const __grid_constant__ CUtensorMap map_e,
                      const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
                      const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
-                     __nv_bfloat16* __restrict__ out, long long* __restrict__ dbg /* developer timeline of one CTA, or null */) {
+                     __nv_bfloat16* __restrict__ out, long long* __restrict__ dbg /* developer timeline of one CTA, or null */,
+                     int H /* hidden width = 64 * heads (grid.y = heads); qkv rows are q | k | v, each H wide */) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -480,7 +481,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       const uint32_t st = (uint32_t)c & 3u;
       const int t2 = c - nkt;
       const int tile = t2 < 0 ? c : (t2 >> 1);
-      const int col = (t2 >= 0 && (t2 & 1)) ? 2 * kH : kH;
+      const int col = (t2 >= 0 && (t2 & 1)) ? 2 * H : H;
       mbar_wait(bar(tp::KVEMPTY) + 8u * st, (((uint32_t)c >> 2) & 1u) ^ 1u);
       if (leader) {
         mbar_expect_tx(bar(tp::KVFULL) + 8u * st, tp::kSlotBytes);
@@ -729,7 +730,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     if (qpos < rows) {
       const float inv = 1.0f / l;
       // one row per lane: 256-bit stores write whole 32-byte sectors
-      __nv_bfloat16* dst = out + (size_t)(r0 + qpos) * kH + head * kHD + wg * kDW;
+      __nv_bfloat16* dst = out + (size_t)(r0 + qpos) * H + head * kHD + wg * kDW;
 #pragma unroll
       for (int ch = 0; ch < kDW / 16; ++ch) {
         uint32_t w[8];
@@ -762,19 +763,20 @@ extern "C" void b2t_attention_set_dbg(long long* p) { g_attn_dbg = p; }
 int g_attn_two_pass = 1;        // b2t_set_option("attn_two_pass", 0/1): fixed-maximum two-pass kernel vs online softmax
 
 // host entry used by b2t_relkey_attention (attention.cu)
-int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, cudaStream_t st) {
+int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, int heads, cudaStream_t st) {
+  const int H = heads * kHD;
   B2T_REQUIRE(b->n_qtiles128 > 0 && b->qtile128_clip && b->qtile128_q0, B2T_ERR_ARG,
               "b2t_relkey_attention(tcgen05): the batch has no 128-row query tiles");
   CUtensorMap mq, mk, me;
-  int rc = make_map(&mq, qkv, b->total_rows, kQKV, kQKV, kQT);
+  int rc = make_map(&mq, qkv, b->total_rows, 3 * H, 3 * H, kQT);
   if (rc != B2T_OK) return rc;
-  rc = make_map(&mk, qkv, b->total_rows, kQKV, kQKV, kKT);
+  rc = make_map(&mk, qkv, b->total_rows, 3 * H, 3 * H, kKT);
   if (rc != B2T_OK) return rc;
   rc = make_map(&me, dist_emb, kRel, kHD, kHD, 80);
   if (rc != B2T_OK) return rc;
   B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc_kernel);
   const int hpc = 1;
-  dim3 grid(b->n_qtiles128, kHeads / hpc);
+  dim3 grid(b->n_qtiles128, heads / hpc);
 #if !B2T_ATTN_WIDE
   if (g_attn_two_pass) {
     // g_attn_two_pass bits: 1 = two-pass, 4 = row sums on the tensor core as well
@@ -782,11 +784,12 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
     B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc2_kernel<true>);
     auto kern = (g_attn_two_pass & 4) ? attention_tc2_kernel<true> : attention_tc2_kernel<false>;
     kern<<<grid, kThreadsAttn2, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip, b->qtile128_q0,
-                                                       (__nv_bfloat16*)out, g_attn_dbg);
+                                                       (__nv_bfloat16*)out, g_attn_dbg, H);
     B2T_LAUNCH_CHECK();
     return B2T_OK;
   }
 #endif
+  B2T_REQUIRE(heads == kHeads, B2T_ERR_ARG, "b2t_attention: the online-softmax tcgen05 kernel (attn_two_pass = 0) is 16 heads only");
   attention_tc_kernel<<<grid, kThreadsAttn, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
                                                                    b->qtile128_q0, (__nv_bfloat16*)out, hpc);
   B2T_LAUNCH_CHECK();

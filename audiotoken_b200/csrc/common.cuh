@@ -83,6 +83,7 @@ B2T_DEVICE float r16(float x) {
 // GEMM epilogues, and every consumer rounds to bf16 or tolerates 1e-6
 B2T_DEVICE float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 B2T_DEVICE float swishf_(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+B2T_DEVICE float geluf_(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }   // exact (erf) GELU
 
 B2T_DEVICE float warp_sum(float v) {
 #pragma unroll

@@ -38,11 +38,12 @@ B2T_DEVICE void epilogue_store(const EpiParams& p, int row, int col0, const floa
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = r16<kBF16>(acc[i]);
   }
-  if constexpr (EPI == B2T_EPI_BIAS || EPI == B2T_EPI_BIAS_SWISH) {
+  if constexpr (EPI == B2T_EPI_BIAS || EPI == B2T_EPI_BIAS_SWISH || EPI == B2T_EPI_BIAS_GELU) {
     OutT* o = reinterpret_cast<OutT*>(p.out) + (size_t)row * p.ldo + col0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       if constexpr (EPI == B2T_EPI_BIAS_SWISH) v[i] = swishf_(v[i]);
+      if constexpr (EPI == B2T_EPI_BIAS_GELU) v[i] = geluf_(v[i]);
     }
     if constexpr (kBF16 && NV % 8 == 0) {
 #pragma unroll

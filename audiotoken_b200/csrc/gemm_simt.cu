@@ -61,6 +61,7 @@ int launch_simt(const b2t_gemm_args* a, const EpiParams& p, cudaStream_t st) {
     case B2T_EPI_RESID: gemm_simt_kernel<T, B2T_EPI_RESID, kBF16><<<grid, 256, 0, st>>>(A, a->lda, W, a->K, p); break;
     case B2T_EPI_GLU: gemm_simt_kernel<T, B2T_EPI_GLU, kBF16><<<grid, 256, 0, st>>>(A, a->lda, W, a->K, p); break;
     case B2T_EPI_BIAS_MASK: gemm_simt_kernel<T, B2T_EPI_BIAS_MASK, kBF16><<<grid, 256, 0, st>>>(A, a->lda, W, a->K, p); break;
+    case B2T_EPI_BIAS_GELU: gemm_simt_kernel<T, B2T_EPI_BIAS_GELU, kBF16><<<grid, 256, 0, st>>>(A, a->lda, W, a->K, p); break;
     default: b2t_set_error("b2t_gemm: unknown epilogue %d", a->epilogue); return B2T_ERR_ARG;
   }
   B2T_LAUNCH_CHECK();
@@ -77,7 +78,7 @@ extern "C" int b2t_gemm(const b2t_gemm_args* a, void* stream) {
   B2T_REQUIRE(a->N % 64 == 0 && a->K % 16 == 0 && a->lda % 8 == 0, B2T_ERR_ARG,
               "b2t_gemm: N%%64, K%%16, lda%%8 must be 0 (N=%d K=%d lda=%d)", a->N, a->K, a->lda);
   const int e = a->epilogue;
-  B2T_REQUIRE(e >= B2T_EPI_BIAS && e <= B2T_EPI_BIAS_MASK, B2T_ERR_ARG, "b2t_gemm: unknown epilogue %d", e);
+  B2T_REQUIRE(e >= B2T_EPI_BIAS && e <= B2T_EPI_BIAS_GELU, B2T_ERR_ARG, "b2t_gemm: unknown epilogue %d", e);
   if (e == B2T_EPI_RESID || e == B2T_EPI_BIAS_MASK)
     B2T_REQUIRE(a->resid, B2T_ERR_ARG, "b2t_gemm: epilogue %d needs resid", e);
   else

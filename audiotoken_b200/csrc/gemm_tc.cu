@@ -104,6 +104,7 @@ B2T_DEVICE void epi_pack32(const EpiParams& p, int col0, const float (&acc)[32],
     for (int i = 0; i < 16; ++i) {
       float a = v[2 * i], b = v[2 * i + 1];
       if constexpr (EPI == B2T_EPI_BIAS_SWISH) { a = swishf_(a); b = swishf_(b); }
+      if constexpr (EPI == B2T_EPI_BIAS_GELU) { a = geluf_(a); b = geluf_(b); }
       pk[i] = pack2_bf16(a, b);
     }
   }
@@ -321,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
-        constexpr bool kPacked = (EPI == B2T_EPI_BIAS || EPI == B2T_EPI_BIAS_SWISH || (EPI == B2T_EPI_GLU && BN == 256));
+        constexpr bool kPacked = (EPI == B2T_EPI_BIAS || EPI == B2T_EPI_BIAS_SWISH || EPI == B2T_EPI_BIAS_GELU || (EPI == B2T_EPI_GLU && BN == 256));
         const int col_a = n0 + (part * kChunks + c) * 32;
         if constexpr (kPacked) {
           // 64 accumulator columns -> 128 B (BIAS/SWISH) or 64 B (GLU) of bf16 per row, stored coalesced
@@ -425,6 +426,7 @@ int dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mw, const b2t_gemm_ar
     case B2T_EPI_RESID: return launch_tc<BN, B2T_EPI_RESID>(ma, mw, a, p, st);
     case B2T_EPI_GLU: return launch_tc<BN, B2T_EPI_GLU>(ma, mw, a, p, st);
     case B2T_EPI_BIAS_MASK: return launch_tc<BN, B2T_EPI_BIAS_MASK>(ma, mw, a, p, st);
+    case B2T_EPI_BIAS_GELU: return launch_tc<BN, B2T_EPI_BIAS_GELU>(ma, mw, a, p, st);
   }
   b2t_set_error("b2t_gemm: unknown epilogue %d", a->epilogue);
   return B2T_ERR_ARG;

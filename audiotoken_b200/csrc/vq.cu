@@ -137,7 +137,8 @@ vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const flo
                    const float* __restrict__ hn, int K, const Cand* __restrict__ cand, int slices, float rel_eps,
                    const float* __restrict__ cmax_half_ptr /* max_k 0.5|c_k|^2 */,
                    int16_t* __restrict__ out, int32_t* __restrict__ out32,
-                   unsigned int* __restrict__ n_fallback, unsigned int* __restrict__ max_err) {
+                   unsigned int* __restrict__ n_fallback, unsigned int* __restrict__ max_err,
+                   int* __restrict__ rescan_rows, float* __restrict__ rescan_thr, int rescan_cap) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= M) return;
@@ -183,13 +184,47 @@ vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const flo
       atomicMax(max_err, __float_as_uint(obs));
     }
   } else {
-    if (lane == 0 && n_fallback) atomicAdd(n_fallback, 1u);
-    // re-scan, warp-cooperative and coalesced: 4 centroids per round, lanes stride the dimension; fp32
-    // filter against the running maximum, fp64 re-score of everything within the bound
-    float run = -INFINITY;
+    // not certified: four or more fast scores lie within the bound.  One warp re-scanning K centroids is a latency
+    // chain of milliseconds that the whole grid then waits for (measured: 1-2 such rows per 65 536-row batch made
+    // this kernel 5x longer), so the row is only queued here; vq_rescan_kernel resolves the queue with a CTA per row.
+    if (lane == 0) {
+      const unsigned int slot = atomicAdd(n_fallback, 1u);
+      if (slot < (unsigned int)rescan_cap) {
+        rescan_rows[slot] = r;
+        rescan_thr[2 * slot] = c.v1;                                           // best fast score
+        rescan_thr[2 * slot + 1] = (float)sqrt(xx) * cmax + cmax_half;         // scale of the error bounds
+      }
+    }
+    return;
+  }
+  if (lane == 0) {
+    if (out) out[r] = (int16_t)best;
+    if (out32) out32[r] = best;
+  }
+}
+
+// Exact resolution of the queued rows: one CTA per row (grid-stride over the queue), warp w scans the centroids
+// k = 4 w, 4 w + 1, ... interleaved in groups of 4 (coalesced: lanes stride the dimension); fp32 filter against the
+// threshold  best fast score - (eps_fast + eps_here) * scale  — the exact winner k* satisfies
+// a_here(k*) >= exact(k*) - eps_here*scale >= exact(i1) - eps_here*scale >= v1 - (eps_fast + eps_here)*scale —
+// fp64 re-score of what passes, smallest distance / smallest index wins, block-reduced through shared memory.
+// The queue has one slot per row, so it cannot overflow (a codebook of duplicated centroids queues every row).
+__global__ void __launch_bounds__(256)
+vq_rescan_kernel(const float* __restrict__ x, int ldx, int M, int D, const float* __restrict__ cb,
+                 const float* __restrict__ hn, int K, const unsigned int* __restrict__ n_queued,
+                 const int* __restrict__ rescan_rows, const float* __restrict__ rescan_thr, int rescan_cap,
+                 float eps_sum, int16_t* __restrict__ out, int32_t* __restrict__ out32) {
+  __shared__ double s_d[8];
+  __shared__ int s_i[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = min((int)*n_queued, rescan_cap);
+  for (int q = blockIdx.x; q < n; q += gridDim.x) {
+    const int r = rescan_rows[q];
+    const float thr = rescan_thr[2 * q] - eps_sum * rescan_thr[2 * q + 1];
+    const float* xr = x + (size_t)r * ldx;
     double bd = INFINITY;
     int bi = 0x7fffffff;
-    for (int k0 = 0; k0 < K; k0 += 4) {
+    for (int k0 = 4 * warp; k0 < K; k0 += 32) {
       float a4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int d = lane * 4; d < D; d += 128) {
         const float4 xv = *reinterpret_cast<const float4*>(xr + d);
@@ -207,18 +242,21 @@ vq_finalize_kernel(const float* __restrict__ x, int ldx, int M, int D, const flo
         const int k = k0 + u;
         if (k >= K) break;
         const float a = warp_sum(a4[u]) - __ldg(hn + k);
-        if (a >= run - 2.0f * delta) {
+        if (a >= thr) {
           const double dd = exact_dist(xr, cb + (size_t)k * D, D, lane);
           if (dd < bd || (dd == bd && k < bi)) { bd = dd; bi = k; }
         }
-        run = fmaxf(run, a);
       }
     }
-    best = bi;
-  }
-  if (lane == 0) {
-    if (out) out[r] = (int16_t)best;
-    if (out32) out32[r] = best;
+    if (lane == 0) { s_d[warp] = bd; s_i[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (s_d[w] < bd || (s_d[w] == bd && s_i[w] < bi)) { bd = s_d[w]; bi = s_i[w]; }
+      if (out) out[r] = (int16_t)bi;
+      if (out32) out32[r] = bi;
+    }
+    __syncthreads();
   }
 }
 
@@ -246,7 +284,7 @@ int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, i
 namespace {
 struct VqWs {
   float* xn; __nv_bfloat16* a2; __nv_bfloat16* c2; float* hn; Cand* parts; float* cmax; unsigned int* nfb;
-  unsigned int* maxerr; size_t total; int kpad; int slices;
+  unsigned int* maxerr; int* rescan_rows; float* rescan_thr; size_t total; int kpad; int slices;
 };
 VqWs vq_carve(void* base, int rows, int dim, int K) {
   VqWs w;
@@ -264,6 +302,8 @@ VqWs vq_carve(void* base, int rows, int dim, int K) {
   w.cmax = misc;
   w.nfb = (unsigned int*)misc + 4;
   w.maxerr = (unsigned int*)misc + 8;
+  w.rescan_rows = (int*)take((size_t)rows * 4);      // queue of uncertified rows: one slot per row
+  w.rescan_thr = (float*)take((size_t)rows * 8);
   w.total = off;
   return w;
 }
@@ -332,8 +372,17 @@ extern "C" int b2t_vq_argmin(const float* x, int ldx, int rows, int dim, const f
     rel_eps = 2.0f * (float)dim * 5.9604645e-8f;
   }
   vq_finalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(xs, lds, rows, dim, codebook, w.hn, codebook_size, w.parts,
-                                                     slices, rel_eps, w.cmax, out, out_i32, w.nfb, w.maxerr);
+                                                     slices, rel_eps, w.cmax, out, out_i32, w.nfb, w.maxerr,
+                                                     w.rescan_rows, w.rescan_thr, rows);
   B2T_LAUNCH_CHECK();
+  {
+    // queued rows (device-side count; usually 0-2): a small fixed grid, a CTA per row
+    const float eps_here = 2.0f * (float)dim * 5.9604645e-8f;      // sequential fp32 FMA dot of length D, 2x margin
+    int grid = b2t_num_sms();
+    vq_rescan_kernel<<<grid, 256, 0, st>>>(xs, lds, rows, dim, codebook, w.hn, codebook_size, w.nfb, w.rescan_rows,
+                                           w.rescan_thr, rows, rel_eps + eps_here, out, out_i32);
+    B2T_LAUNCH_CHECK();
+  }
   return B2T_OK;
 }
 

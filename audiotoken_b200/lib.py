@@ -16,18 +16,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('B2T_LIB_PATH') or os.path.join(_HERE, 'lib', 'libb200tok.so')   # override: developer A/B builds
 
 PREC_BF16, PREC_FP32 = 0, 1
-EPI_BIAS, EPI_BIAS_SWISH, EPI_RESID, EPI_GLU, EPI_BIAS_MASK = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_SWISH, EPI_RESID, EPI_GLU, EPI_BIAS_MASK, EPI_BIAS_GELU = 0, 1, 2, 3, 4, 5
 IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR, IMPL_MMA_SYNC = 0, 1, 2, 3
 
 EXPORTS = [
     'b2t_version', 'b2t_last_error', 'b2t_device_check', 'b2t_set_option', 'b2t_fbank_logmel', 'b2t_fbank_stats',
-    'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_add_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_dwconv_ln_swish',
+    'b2t_fbank_stack_ln', 'b2t_layernorm', 'b2t_add_layernorm', 'b2t_gemm', 'b2t_relkey_attention', 'b2t_attention', 'b2t_dwconv_ln_swish',
     'b2t_vq_workspace_bytes', 'b2t_vq_argmin', 'b2t_vq_debug_stats', 'b2t_semantic_create', 'b2t_semantic_destroy',
     'b2t_semantic_set_tensor', 'b2t_semantic_workspace_bytes', 'b2t_semantic_encode',
     'b2t_last_launch_count', 'b2t_profile_enable', 'b2t_profile_read',
     'b2t_acoustic_create', 'b2t_acoustic_destroy', 'b2t_acoustic_set_tensor', 'b2t_acoustic_workspace_bytes',
     'b2t_acoustic_encode', 'b2t_rvq_encode', 'b2t_acoustic_profile_read', 'b2t_ingest_resample',
     'b2t_acoustic_decode_workspace_bytes', 'b2t_acoustic_decode', 'b2t_vq_ema_workspace_bytes', 'b2t_vq_ema_update',
+    'b2t_hubert_create', 'b2t_hubert_destroy', 'b2t_hubert_set_tensor', 'b2t_hubert_workspace_bytes', 'b2t_hubert_encode',
+    'b2t_debug_stage_sums', 'b2t_debug_stage_count',
 ]
 
 
@@ -92,6 +94,7 @@ def load() -> C.CDLL:
     lib.b2t_gemm.argtypes = [C.POINTER(GemmArgs), vp]
     lib.b2t_add_layernorm.argtypes = [vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.b2t_relkey_attention.argtypes = [vp, vp, C.POINTER(Batch), vp, i32, i32, vp]
+    lib.b2t_attention.argtypes = [vp, vp, C.POINTER(Batch), vp, i32, i32, i32, vp]
     lib.b2t_dwconv_ln_swish.argtypes = [vp, vp, vp, vp, C.POINTER(Batch), vp, i32, vp]
     lib.b2t_vq_workspace_bytes.argtypes = [i32, i32, i32]
     lib.b2t_vq_workspace_bytes.restype = sz
@@ -126,6 +129,15 @@ def load() -> C.CDLL:
     lib.b2t_acoustic_profile_read.argtypes = [C.POINTER(C.c_float)]
     lib.b2t_rvq_encode.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.b2t_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    lib.b2t_hubert_create.argtypes = [i32, i32, i32]
+    lib.b2t_hubert_create.restype = vp
+    lib.b2t_hubert_destroy.argtypes = [vp]
+    lib.b2t_hubert_destroy.restype = None
+    lib.b2t_hubert_set_tensor.argtypes = [vp, C.c_char_p, vp]
+    lib.b2t_hubert_workspace_bytes.argtypes = [vp, vp]
+    lib.b2t_hubert_workspace_bytes.restype = sz
+    lib.b2t_hubert_encode.argtypes = [vp, vp, vp, vp, sz, i32, vp, i32, vp, vp, vp]
+    lib.b2t_debug_stage_sums.argtypes = [vp, i32]
     _lib = lib
     return lib
 

@@ -72,6 +72,21 @@ class SemanticPlan:
         return np.diff(self.row_off)
 
 
+def attention_work_lists(rows_arr, valid_rows):
+    """(clip, first query row) of every 64- and 128-query tile, heaviest (most keys) clips first so that the tail of the
+    grid is made of short clips."""
+    order = np.argsort(-np.asarray(valid_rows), kind='stable')
+    qc, qq, qc8, qq8 = [], [], [], []
+    for i in order:
+        q0 = np.arange(0, rows_arr[i], QTILE, dtype=np.int32)
+        qc.append(np.full(q0.shape, i, dtype=np.int32))
+        qq.append(q0)
+        q8 = np.arange(0, rows_arr[i], QTILE128, dtype=np.int32)
+        qc8.append(np.full(q8.shape, i, dtype=np.int32))
+        qq8.append(q8)
+    return np.concatenate(qc), np.concatenate(qq), np.concatenate(qc8), np.concatenate(qq8)
+
+
 def plan_semantic(lengths: Sequence[int], wave_offsets: Sequence[int], padded_samples: Sequence[int] | int,
                   rows: Optional[Sequence[int]] = None, pad_to_multiple_of: int = 2) -> SemanticPlan:
     """Plan a packed batch.
@@ -114,16 +129,7 @@ def plan_semantic(lengths: Sequence[int], wave_offsets: Sequence[int], padded_sa
     row_off[1:] = np.cumsum(rows_arr)
     if row_off[-1] >= 2 ** 31 or frame_off[-1] >= 2 ** 31:
         raise ValueError('batch too large for int32 offsets')
-    # attention work items, heaviest (most keys) first so the tail of the grid is made of short clips
-    order = np.argsort(-valid_rows, kind='stable')
-    qc, qq, qc8, qq8 = [], [], [], []
-    for i in order:
-        q0 = np.arange(0, rows_arr[i], QTILE, dtype=np.int32)
-        qc.append(np.full(q0.shape, i, dtype=np.int32))
-        qq.append(q0)
-        q8 = np.arange(0, rows_arr[i], QTILE128, dtype=np.int32)
-        qc8.append(np.full(q8.shape, i, dtype=np.int32))
-        qq8.append(q8)
+    qc, qq, qc8, qq8 = attention_work_lists(rows_arr, valid_rows)
     cc, ct = [], []
     for i in range(n):
         t0 = np.arange(0, rows_arr[i], CTILE, dtype=np.int32)
@@ -134,9 +140,9 @@ def plan_semantic(lengths: Sequence[int], wave_offsets: Sequence[int], padded_sa
         wave_off=np.asarray(wave_offsets, dtype=np.int64),
         frame_off=frame_off.astype(np.int32), stack_frames=stack.astype(np.int32),
         row_off=row_off.astype(np.int32), valid_rows=valid_rows.astype(np.int32),
-        qtile_clip=np.concatenate(qc), qtile_q0=np.concatenate(qq),
+        qtile_clip=qc, qtile_q0=qq,
         ctile_clip=np.concatenate(cc), ctile_t0=np.concatenate(ct),
-        qtile128_clip=np.concatenate(qc8), qtile128_q0=np.concatenate(qq8))
+        qtile128_clip=qc8, qtile128_q0=qq8)
 
 
 class DeviceBatch:

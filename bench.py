@@ -219,40 +219,61 @@ def workload_config(workload, lengths):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c3', choices=['c3', 'c2', 'c4'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    args = ap.parse_args()
-    if args.impl == 'reference':
-        run_reference_arm(args)
-        return
+class Ctx:
+    """process-wide state of the GPU arm: rank / device / collective helpers"""
 
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    rank = int(os.environ.get('RANK', 0))
-    local = int(os.environ.get('LOCAL_RANK', 0))
-    torch.cuda.set_device(local)
-    device = torch.device('cuda', local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
+    def __init__(self):
+        self.world = int(os.environ.get('WORLD_SIZE', 1))
+        self.rank = int(os.environ.get('RANK', 0))
+        self.local = int(os.environ.get('LOCAL_RANK', 0))
+        torch.cuda.set_device(self.local)
+        self.device = torch.device('cuda', self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_
+            self.dist = dist_
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            self.dist.init_process_group('nccl', device_id=self.device)
 
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def _reduce(self, v: float, op) -> float:
+        if self.dist is None:
+            return v
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def sum_over_ranks(self, v: float) -> float:
+        return self._reduce(v, self.dist.ReduceOp.SUM) if self.dist is not None else v
+
+    def max_over_ranks(self, v: float) -> float:
+        return self._reduce(v, self.dist.ReduceOp.MAX) if self.dist is not None else v
+
+    def fault_check(self, where: str):
+        """A device fault is asynchronous: surface it here, with a name, instead of in some tensor destructor."""
+        from audiotoken_b200 import lib as L
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f'bench.py: rank {self.rank}: device fault detected after {where}: {e}\n'
+                             f'  library says: {L.load().b2t_last_error().decode("utf-8", "replace")}\n'
+                             '  re-run with B2T_DEBUG_SYNC=1 to name the kernel\n')
+            sys.stderr.flush()
+            os._exit(13)
+
+
+def run_workload(ctx: Ctx, workload: str, steps: int, warmup: int, instrument: bool = True) -> dict:
+    """One workload on this rank's shard: resident and end-to-end timing (+ per-kernel-class CUDA-event breakdown)."""
     from audiotoken_b200 import lib as L
     from audiotoken_b200 import packing
     from audiotoken_b200.encoder import Wav2VecBertEncoder
-
-    for kv in filter(None, os.environ.get('B2T_OPTS', '').split(',')):     # developer A/B switches, e.g. attn_two_pass=0
-        k, v = kv.split('=')
-        L.check(L.load().b2t_set_option(k.encode(), int(v)), kv)
-    lengths = shard_lengths(rank, args.workload)
-    acoustic = args.workload == 'c4'
+    device, rank = ctx.device, ctx.rank
+    lengths = shard_lengths(rank, workload)
+    acoustic = workload == 'c4'
     sr = 24000 if acoustic else SR
     audio_s = float(lengths.sum() / sr)
     if acoustic:
@@ -289,26 +310,6 @@ def main():
     torch.cuda.synchronize()
     h2d_bytes = sum(h.numel() * 4 for h in host_waves)
     d2h_bytes = sum(h.numel() * 2 for h in host_tokens)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def sum_over_ranks(v: float) -> float:
-        if dist is None:
-            return v
-        t = torch.tensor([v], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    def max_over_ranks(ms: float) -> float:
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     launches = [0]
 
     def step_resident():
@@ -345,93 +346,185 @@ def main():
                 ht.copy_(tokens, non_blocking=True)
         comp.wait_stream(copy_stream)
 
-    def timed(fn, steps):
-        barrier()
+    def timed(fn, n):
+        ctx.barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         e.record()
-        barrier()
-        return max_over_ranks(s.elapsed_time(e) / steps)
+        ctx.barrier()
+        return ctx.max_over_ranks(s.elapsed_time(e) / n)
 
-    def fault_check(where: str):
-        """A device fault is asynchronous: surface it here, with a name, instead of in some tensor destructor."""
-        try:
-            torch.cuda.synchronize()
-        except Exception as e:  # noqa: BLE001
-            sys.stderr.write(f'bench.py: rank {rank}: device fault detected after {where}: {e}\n'
-                             f'  library says: {L.load().b2t_last_error().decode("utf-8", "replace")}\n'
-                             '  re-run with B2T_DEBUG_SYNC=1 to name the kernel\n')
-            sys.stderr.flush()
-            os._exit(13)
-
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         step_resident()
-        fault_check(f'warm-up step {i} (resident)')
-    sampler = ClockSampler(local)
+        ctx.fault_check(f'warm-up step {i} ({workload}, resident)')
+    sampler = ClockSampler(ctx.local)
     sampler.start()
     launches[0] = 0
-    ms_res = timed(step_resident, args.steps)
+    ms_res = timed(step_resident, steps)
     gpu_launches = launches[0]
     clocks = sampler.result()
-    fault_check('the timed resident steps')
+    ctx.fault_check(f'the timed resident steps ({workload})')
     step_e2e()
-    fault_check('the e2e warm-up step')
-    ms_e2e = timed(step_e2e, args.steps)
-    fault_check('the timed e2e steps')
+    ctx.fault_check(f'the e2e warm-up step ({workload})')
+    ms_e2e = timed(step_e2e, steps)
+    ctx.fault_check(f'the timed e2e steps ({workload})')
 
-    # instrumented steps: CUDA-event time per kernel class
-    import ctypes as C
-    lib = L.load()
-    lib.b2t_profile_enable(1)
-    cls_ms = np.zeros(6)
-    gemm_flops = 0.0
-    ac_ms = np.zeros(4)
-    for w, plan in (zip(dev_waves, plans) if acoustic else []):
-        enc.encode_plan(w, plan)
-        arr4 = (C.c_float * 4)()
-        L.check(lib.b2t_acoustic_profile_read(arr4), 'acoustic_profile_read')
-        ac_ms += np.array(list(arr4))
-    for w, plan in ([] if acoustic else zip(dev_waves, plans)):
-        enc.encode_plan(w, plan)
-        arr = (C.c_float * 6)()
-        fl = C.c_double(0)
-        L.check(lib.b2t_profile_read(arr, C.byref(fl)), 'profile_read')
-        cls_ms += np.array(list(arr))
-        gemm_flops += fl.value
-    lib.b2t_profile_enable(0)
+    res = dict(workload=workload, lengths=lengths, rows=rows, audio_s=audio_s, ms_res=ms_res, ms_e2e=ms_e2e,
+               gpu_launches=gpu_launches, clocks=clocks, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, acoustic=acoustic,
+               num_codebooks=getattr(enc, 'num_codebooks', 1), n_batches=len(batches))
+    if instrument:          # instrumented steps: CUDA-event time per kernel class
+        import ctypes as C
+        lib = L.load()
+        lib.b2t_profile_enable(1)
+        cls_ms, gemm_flops, ac_ms = np.zeros(6), 0.0, np.zeros(4)
+        for w, plan in zip(dev_waves, plans):
+            enc.encode_plan(w, plan)
+            if acoustic:
+                arr4 = (C.c_float * 4)()
+                L.check(lib.b2t_acoustic_profile_read(arr4), 'acoustic_profile_read')
+                ac_ms += np.array(list(arr4))
+            else:
+                arr = (C.c_float * 6)()
+                fl = C.c_double(0)
+                L.check(lib.b2t_profile_read(arr, C.byref(fl)), 'profile_read')
+                cls_ms += np.array(list(arr))
+                gemm_flops += fl.value
+        lib.b2t_profile_enable(0)
+        res.update(cls_ms=cls_ms, gemm_flops=gemm_flops, ac_ms=ac_ms)
+    del enc, dev_waves, host_waves, stage
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_files_e2e(ctx: Ctx, n_files: int) -> dict:
+    """The public file loop, WAV files -> .npy on disk (SURVEY 8d's end-to-end definition): the first `n_files` clips of
+    the shard are written as PCM16 WAV files (untimed), then AudioToken('semantic_m').encode_batch_files reads, decodes,
+    encodes and writes them (timed with the wall clock around the call; one warm-up call on a small subset)."""
+    import shutil
+    import tempfile
+    from audiotoken_b200 import AudioToken
+    from audiotoken_b200 import io as aio
+    lengths = shard_lengths(ctx.rank, 'c3')[:n_files]
+    base = '/dev/shm' if os.path.isdir('/dev/shm') and os.access('/dev/shm', os.W_OK) else None
+    root = tempfile.mkdtemp(prefix='b2t_files_', dir=base)
+    try:
+        indir, outdir = os.path.join(root, 'in'), os.path.join(root, 'out')
+        os.makedirs(indir)
+        wave = synth_on_device(lengths, 4242 + ctx.rank, ctx.device, SR).cpu()
+        off = 0
+        for i, n in enumerate(lengths):
+            aio.write_wav(os.path.join(indir, f'clip{i:05d}.wav'), wave[off:off + int(n)], SR)
+            off += int(n)
+        in_bytes = sum(os.path.getsize(os.path.join(indir, f)) for f in os.listdir(indir))
+        del wave
+        tok = AudioToken('semantic_m', device=str(ctx.device), synthetic_weights=True, precision='bf16')
+        tok.load_encoder()
+        warm = sorted(os.path.join(indir, f) for f in os.listdir(indir))[:16]
+        tok.encode_batch_files(batch_size=ROW_BUDGET // 1500, outdir=os.path.join(root, 'warm'), chunk_size=CHUNK_S, audio_files=warm,
+                               num_workers=min(16, os.cpu_count() or 1))
+        ctx.barrier()
+        t0 = time.perf_counter()
+        tok.encode_batch_files(batch_size=ROW_BUDGET // 1500, outdir=outdir, chunk_size=CHUNK_S, audio_dir=indir,
+                               num_workers=min(16, os.cpu_count() or 1))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        st = tok.last_stats
+        out_bytes = sum(os.path.getsize(os.path.join(outdir, f)) for f in os.listdir(outdir))
+        return {'value': st['audio_seconds'] / wall, 'unit': 'audio-s/s', 'wall_s': wall, 'files': st['files'],
+                'audio_seconds': st['audio_seconds'], 'errors': len(st['errors']), 'windows': st['windows'], 'batches': st['batches'],
+                'wav_bytes_read': int(in_bytes), 'npy_bytes_written': int(out_bytes), 'reader_threads': min(16, os.cpu_count() or 1),
+                'what': f'AudioToken(semantic_m).encode_batch_files: {st["files"]} PCM16 WAV files on {"/dev/shm" if base else "tmp"} -> '
+                        '.npy token files (file read + RIFF parse + GPU PCM decode + encode + D2H + npy write inside the timed region)'}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def load_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture (profiles/r02_traffic.json)."""
+    p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=['c3', 'c2', 'c4'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the acoustic_c4 and files_e2e legs of the default run')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+
+    ctx = Ctx()
+    world, rank = ctx.world, ctx.rank
+    from audiotoken_b200 import lib as L
+    for kv in filter(None, os.environ.get('B2T_OPTS', '').split(',')):     # developer A/B switches, e.g. attn_two_pass=0
+        k, v = kv.split('=')
+        L.check(L.load().b2t_set_option(k.encode(), int(v)), kv)
+
+    r = run_workload(ctx, args.workload, args.steps, args.warmup, instrument=True)
+    acoustic, lengths, rows = r['acoustic'], r['lengths'], r['rows']
+    ms_res, ms_e2e = r['ms_res'], r['ms_e2e']
+    cls_ms, gemm_flops, ac_ms = r['cls_ms'], r['gemm_flops'], r['ac_ms']
     peak_tf, peak_hbm, peak_src = measured_peaks()
     ach = gemm_flops / (cls_ms[2] / 1e3) / 1e12 if cls_ms[2] > 0 else 0.0
     if acoustic:
         # SURVEY 8d: 39.73 MFLOP per frame (encoder) + n_q * 2*1024*128 (RVQ)
         frames = float(rows.sum())
-        flops = frames * (39.73e6 + enc.num_codebooks * 2 * 1024 * 128)
+        flops = frames * (39.73e6 + r['num_codebooks'] * 2 * 1024 * 128)
         ach = flops / (ms_res / 1e3) / 1e12
 
-    total_audio_s = sum_over_ranks(audio_s)           # units all ranks processed per step
+    total_audio_s = ctx.sum_over_ranks(r['audio_s'])           # units all ranks processed per step
+    extras = {}
+    if world == 1 and not args.no_extras and args.workload == 'c3':
+        # driver-visible lines for the other two measurement rows (VERDICT r1 item 6): BASELINE configs[3] on this GPU
+        # and the public file loop, each a short pass after the main measurement
+        a = run_workload(ctx, 'c4', min(args.steps, 3), 3, instrument=False)
+        extras['acoustic_c4'] = {
+            'value': a['audio_s'] / (a['ms_res'] / 1e3), 'unit': 'audio-s/s', 'ms_per_step': a['ms_res'],
+            'e2e': {'value': a['audio_s'] / (a['ms_e2e'] / 1e3), 'unit': 'audio-s/s', 'ms_per_step': a['ms_e2e'],
+                    'h2d_bytes_per_step': int(a['h2d_bytes']), 'd2h_bytes_per_step': int(a['d2h_bytes'])},
+            'steps': min(args.steps, 3), 'gpu_launches': int(a['gpu_launches']), 'dtype': 'bf16',
+            'config': workload_config('c4', a['lengths'])}
+        extras['files_e2e'] = run_files_e2e(ctx, len(lengths))
     if rank == 0:
         value = total_audio_s / (ms_res / 1e3)
         e2e = total_audio_s / (ms_e2e / 1e3)
+        traffic = load_traffic()
+        n_gemm = 153 * r['n_batches']
         line = {
             'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_res, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': workload_config(args.workload, lengths), 'clocks': clocks,
-            'e2e': {'value': e2e, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d_bytes),
-                    'd2h_bytes_per_step': int(d2h_bytes)},
-            'gpu_launches': int(gpu_launches),
+            'config': workload_config(args.workload, lengths), 'clocks': r['clocks'],
+            'e2e': {'value': e2e, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(r['h2d_bytes']),
+                    'd2h_bytes_per_step': int(r['d2h_bytes'])},
+            'gpu_launches': int(r['gpu_launches']),
             'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all 153 launches per batch)',
                          'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
-                         'traffic': None, 'peak_source': peak_src,
+                         'flops_per_launch': gemm_flops / n_gemm if n_gemm else None,
+                         'ms_per_launch': float(cls_ms[2] / n_gemm) if n_gemm else None,
+                         'traffic': (traffic or {}).get('gemm_tc_kernel', {}).get('dram_bytes_per_launch'),
+                         'traffic_note': (traffic or {}).get('note'),
+                         'peak_source': peak_src,
                          'gemm_share_of_step': float(cls_ms[2] / cls_ms.sum()) if cls_ms.sum() > 0 else None},
             'breakdown_ms_per_step': dict(zip(['fbank', 'layernorm', 'gemm', 'attention', 'dwconv', 'vq'],
                                               [float(v) for v in cls_ms])),
         }
+        if traffic and not acoustic:
+            line['roofline']['hbm_classes'] = traffic.get('hbm_classes')
         if acoustic:
             # per phase (CUDA events inside the library, one instrumented step): algorithmic FLOPs of SURVEY 8d
             # front end = 15 208 448 MAC/frame (18 convs minus the final one), LSTM 4 194 304, final conv 458 752
-            ph_flops = [2 * 15208448.0 - 2 * 458752.0, 2 * 4194304.0, 2 * 458752.0, enc.num_codebooks * 2.0 * 1024 * 128]
+            ph_flops = [2 * 15208448.0 - 2 * 458752.0, 2 * 4194304.0, 2 * 458752.0, r['num_codebooks'] * 2.0 * 1024 * 128]
             phases = {}
             for nm, ms_p, fl in zip(['seanet_front_end', 'lstm', 'final_conv', 'rvq'], ac_ms, ph_flops):
                 phases[nm] = {'ms': float(ms_p), 'tflops_algorithmic': (frames * fl / (ms_p / 1e3) / 1e12) if ms_p > 0 else None}
@@ -442,15 +535,17 @@ def main():
                 phases['seanet_front_end']['hbm_peak_gbps'] = peak_hbm
             line['roofline'].update({'kernel': 'whole acoustic step: seanet_conv0 + seanet_tc_kernel (tcgen05 conv/LSTM GEMMs) + '
                                                'rvq_tc_kernel (tcgen05 bf16x3), SURVEY 8d FLOPs / step time',
-                                     'bound': 'tensor', 'gemm_share_of_step': None, 'phases': phases})
+                                     'bound': 'tensor', 'gemm_share_of_step': None, 'phases': phases, 'traffic': None,
+                                     'flops_per_launch': None, 'ms_per_launch': None})
             line['breakdown_ms_per_step'] = dict(zip(['seanet_front_end', 'lstm', 'final_conv', 'rvq'], [float(v) for v in ac_ms]))
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference_run_acoustic(3, 1) if acoustic else cpu_reference_run(lengths, steps=2, warmup=1)
             line['cpu_baseline'] = base
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == '__main__':

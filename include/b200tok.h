@@ -51,7 +51,8 @@ typedef enum {
   B2T_EPI_BIAS_SWISH = 1,  /* h = r16(acc + bias); out = r16(h * sigmoid(h))         */
   B2T_EPI_RESID = 2,       /* resid = [r16](resid + alpha * r16(acc + bias)) (fp32 stream) */
   B2T_EPI_GLU = 3,         /* W rows interleaved (a0,g0,a1,g1,..): out[:, j] = r16(r16(a_j) * sigmoid(r16(g_j))) */
-  B2T_EPI_BIAS_MASK = 4    /* out = row_valid ? r16(acc + bias) : 0, written to the fp32 stream */
+  B2T_EPI_BIAS_MASK = 4,   /* out = row_valid ? r16(acc + bias) : 0, written to the fp32 stream */
+  B2T_EPI_BIAS_GELU = 5    /* h = r16(acc + bias); out = r16(0.5 h (1 + erf(h / sqrt 2)))  (HuBERT convs / FFN) */
 } b2t_epilogue;
 
 typedef enum { B2T_IMPL_AUTO = 0, B2T_IMPL_SIMT = 1, B2T_IMPL_TENSOR = 2 /* tcgen05 */, B2T_IMPL_MMA_SYNC = 3 /* legacy mma.sync (attention only) */ } b2t_impl;
@@ -160,6 +161,10 @@ int b2t_gemm(const b2t_gemm_args* args, void* stream);
 /* reference audiotoken/modeling_wav2vec2_bert.py:37-77: softmax(q k^T / 8 + q E[clamp(j-i,-64,8)+64] / 8
  * + key padding) v.  qkv is [M, 3072] = q | k | v (16 heads x 64 each), dist_emb [73, 64],
  * out [M, 1024].  Keys >= valid_rows[clip] are masked; every row (incl. pad rows) is a query. */
+/* The same kernels for `heads` heads of 64: qkv [M, 3 * 64 * heads], out [M, 64 * heads].  A zero dist_emb gives
+ * plain scaled-dot-product attention with key masking (HuBERT, transformers modeling_hubert.py:236-259). */
+int b2t_attention(const void* qkv, const void* dist_emb, const b2t_batch* batch, void* out, int heads,
+                  int precision, int impl, void* stream);
 int b2t_relkey_attention(const void* qkv, const void* dist_emb, const b2t_batch* batch,
                          void* out, int precision, int impl, void* stream);
 
@@ -207,6 +212,52 @@ int b2t_vq_ema_update(const float* x, int ldx, int rows, int dim, const int32_t*
                       size_t workspace_bytes, void* stream);
 
 /* ---- whole semantic encoder (reference Wav2VecBertEncoder.forward, encoder.py:163-186) ------- */
+/* Developer hook (in-situ determinism check, tools/stage_sums.py): after every stage of b2t_semantic_encode a 64-bit
+ * position-weighted checksum of the whole workspace is written to buf[stage]; NULL switches it off. */
+int b2t_debug_stage_sums(unsigned long long* device_buf, int capacity);
+int b2t_debug_stage_count(void);
+
+/* ---- the reference's own semantic_s: mHuBERT-base + k-means (reference audiotoken/encoder.py:60-108) ---------------
+ * Ragged batch of UN-padded, already normalised clips (Wav2Vec2FeatureExtractor, encoder.py:20-26).  The strided
+ * feature encoder runs on per-level row tables whose offsets halve from level to level (off_l = off_0 >> l), so every
+ * conv layer after the first is ONE overlapping-row GEMM over the whole batch; the transformer runs on the compact
+ * valid frames (total_rows).  Planner: audiotoken_b200/hubert.py::plan_hubert.                                        */
+typedef struct {
+  int32_t n_clips;
+  int32_t total_rows;              /* sum of valid frames (transformer rows)                                   */
+  int32_t level0_rows;             /* allotted rows of level 0 (conv0 output); level l has level0_rows >> l    */
+  int32_t pos_rows;                /* rows of the zero-gapped group-major buffer of the positional conv        */
+  int32_t n_stat_tiles, n_apply_tiles;
+  int64_t total_samples;           /* sum of n_samples (size of the normalised copy)                           */
+  const int64_t* wave_off;         /* [n] first sample of clip i                                               */
+  const int64_t* norm_off;         /* [n] first sample of clip i in the normalised copy (prefix sums)          */
+  const int32_t* n_samples;        /* [n]                                                                      */
+  const int32_t* gn_count;         /* [n] conv0 frames of the PADDED chunk: GroupNorm denominator              */
+  const int32_t* off0;             /* [n+1] level-0 row offsets, multiples of 64                               */
+  const int32_t* row_off;          /* [n+1] compact row offsets                                                */
+  const int32_t* pos_off;          /* [n] row of frame 0 of clip i in the positional-conv buffer               */
+  const int32_t* stat_tile_clip;   /* 128-frame tiles over the conv0 frames that touch the clip (statistics)   */
+  const int32_t* stat_tile_f0;
+  const int32_t* stat_tile_first;  /* [n+1] first statistics tile of clip i                                    */
+  const int32_t* apply_tile_clip;  /* 128-frame tiles over the conv0 frames that lie inside the clip           */
+  const int32_t* apply_tile_f0;
+  b2t_batch attn;                  /* row_off / valid_rows / query tiles of the transformer rows               */
+} b2t_hubert_batch;
+
+typedef struct b2t_hubert_model b2t_hubert_model;
+b2t_hubert_model* b2t_hubert_create(int n_layers, int codebook_size, int precision);
+void b2t_hubert_destroy(b2t_hubert_model* m);
+/* tensor names: see csrc/hubert.cu */
+int b2t_hubert_set_tensor(b2t_hubert_model* m, const char* name, const void* device_ptr);
+size_t b2t_hubert_workspace_bytes(const b2t_hubert_model* m, const b2t_hubert_batch* batch);
+/* wave: fp32 samples; normalize != 0 applies the feature extractor's per-clip zero-mean / unit-variance step first
+ * (encoder.py:20-26), 0 = the samples are processor output already (the reference's encoder operator boundary);
+ * tokens int16 [total_rows]; tap_out (optional) fp32 [total_rows, 768] = hidden state `tap_layer` (0 = input of
+ * layer 0 ... n_layers), tap_feats (optional) fp32 [total_rows, 512] = the feature-encoder output of the valid frames. */
+int b2t_hubert_encode(const b2t_hubert_model* m, const float* wave, const b2t_hubert_batch* batch, void* workspace,
+                      size_t workspace_bytes, int normalize, int16_t* tokens, int tap_layer, float* tap_out,
+                      float* tap_feats, void* stream);
+
 typedef struct b2t_semantic_model b2t_semantic_model;
 
 b2t_semantic_model* b2t_semantic_create(int n_layers, int codebook_size, int precision);

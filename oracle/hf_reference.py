@@ -130,3 +130,24 @@ def acoustic_reference(wave: torch.Tensor, sd: Dict[str, torch.Tensor], n_q: int
             embs.append(emb.float().cpu())
             codes.append(c.transpose(0, 1).cpu())
     return torch.cat(embs), torch.cat(codes)
+
+
+# ---- the reference's own semantic_s: HF HubertModel called as encoder.py:93 calls it -----------------------------------
+def hubert_reference(wave: torch.Tensor, mask: torch.Tensor, sd: Dict[str, torch.Tensor], device='cpu',
+                     autocast: bool = False, tf32: bool = True) -> List[torch.Tensor]:
+    """wave [B, L] (processor output, zero right-padded), mask [B, L] -> hidden_states (fp32, CPU) of
+    ``HubertModel.forward(input_batch, attention_mask=attention_mask, output_hidden_states=True)``, optionally under
+    CUDA bf16 autocast (encoder.py:89)."""
+    from transformers import HubertConfig, HubertModel
+    device = torch.device(device)
+    model = HubertModel(HubertConfig())
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and set(missing) <= {'masked_spec_embed'}, (missing, unexpected)
+    model = model.to(device).eval()
+    if device.type == 'cuda':
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+    ctx = torch.amp.autocast(device_type='cuda', dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+    with torch.no_grad(), ctx:
+        hs = model.forward(wave.to(device), attention_mask=mask.to(device), output_hidden_states=True).hidden_states
+    return [h.float().cpu() for h in hs]
