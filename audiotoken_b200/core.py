@@ -291,49 +291,69 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
             off += n
         return out, idx
 
-    def run_window(window):
-        """window: list of (path, sr, pcm).  Encodes all of it and hands finished files to the writers."""
+    class WindowState:
+        """segments of one window + the bookkeeping that tells when a file is complete"""
+
+        def __init__(self, segs, rows):
+            self.segs, self.rows = segs, rows
+            self.per_file: Dict[str, Dict[int, np.ndarray]] = {}
+            self.left: Dict[str, int] = {}
+            for s_ in segs:
+                self.left[s_.file_name] = self.left.get(s_.file_name, 0) + 1
+
+        def absorb(self, host, idx):
+            for i, t in zip(idx, host):
+                s_ = self.segs[i]
+                self.per_file.setdefault(s_.file_name, {})[s_.chunk_index] = np.array(t[:, :s_.config.length_tokens])
+                stats['audio_seconds'] += s_.config.length_seconds
+                self.left[s_.file_name] -= 1
+                if self.left[s_.file_name] == 0:               # every chunk of the file is encoded: write it now
+                    write_futs.append((s_.file_name, writers.submit(write, s_.file_name, self.per_file.pop(s_.file_name))))
+                    stats['files'] += 1
+
+    def prepare(window):
+        """window: list of (path, sr, pcm) -> WindowState (PCM decode + resampling on the device, segment rules)."""
         segs, nbytes = [], 0
         for path, sr, pcm in window:
             try:
                 nbytes += pcm.nbytes
                 for ci, wave in enumerate(aio.convert_chunks(sr, pcm, sample_rate, chunk_size, device if on_gpu else None)):
-                    for s in aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size):
-                        s.chunk_index = ci                 # one segment per streamed chunk (datasets.py:88-105)
-                        segs.append(s)
+                    for s_ in aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size):
+                        s_.chunk_index = ci                # one segment per streamed chunk (datasets.py:88-105)
+                        segs.append(s_)
             except Exception as e:  # noqa: BLE001
-                segs = [s for s in segs if s.file_name != path]
+                segs = [s_ for s_ in segs if s_.file_name != path]
                 fail(path, e)
         stats['peak_window_bytes'] = max(stats['peak_window_bytes'], nbytes)
-        if not segs:
-            return
-        rows = [encoder.rows_for_tokens(length_tokens(int(s.wave.numel()), sample_rate, token_rate), pad) for s in segs]
-        per_file: Dict[str, Dict[int, np.ndarray]] = {}
-        left: Dict[str, int] = {}
-        for s in segs:
-            left[s.file_name] = left.get(s.file_name, 0) + 1
-
-        def absorb(host, idx):
-            for i, t in zip(idx, host):
-                s = segs[i]
-                per_file.setdefault(s.file_name, {})[s.chunk_index] = np.array(t[:, :s.config.length_tokens])
-                stats['audio_seconds'] += s.config.length_seconds
-                left[s.file_name] -= 1
-                if left[s.file_name] == 0:                 # every chunk of the file is encoded: write it now
-                    write_futs.append((s.file_name, writers.submit(write, s.file_name, per_file.pop(s.file_name))))
-                    stats['files'] += 1
-
-        pending = None
-        for idx in bucket_by_rows(rows, row_budget):
-            launched = launch([segs[i].wave for i in idx], [rows[i] for i in idx])
-            stats['batches'] += 1
-            if pending is not None:
-                absorb(*fetch(pending))
-            pending = (*launched, idx)
-        if pending is not None:
-            absorb(*fetch(pending))
+        rows = [encoder.rows_for_tokens(length_tokens(int(s_.wave.numel()), sample_rate, token_rate), pad) for s_ in segs]
         stats['segments'] += len(segs)
         stats['windows'] += 1
+        return WindowState(segs, rows)
+
+    ingest_stream = torch.cuda.Stream(device=device) if on_gpu else None
+
+    def prepare_async(window):
+        """prepare() on a side stream: the PCM upload and the decode / resampling kernels of the NEXT window run while
+        the compute stream is busy with the batches of the current one"""
+        if not on_gpu:
+            return prepare(window), None
+        with torch.cuda.stream(ingest_stream):
+            st_ = prepare(window)
+            ready = ingest_stream.record_event()
+        return st_, ready
+
+    def launch_window(st_, ready):
+        """all ragged batches of a prepared window, back to back (no host synchronisation in between)"""
+        comp = torch.cuda.current_stream(device) if on_gpu else None
+        if ready is not None:
+            comp.wait_event(ready)
+            for s_ in st_.segs:
+                s_.wave.record_stream(comp)
+        out = []
+        for idx in bucket_by_rows(st_.rows, row_budget):
+            out.append((*launch([st_.segs[i].wave for i in idx], [st_.rows[i] for i in idx]), idx))
+            stats['batches'] += 1
+        return out
 
     def est_rows(sr, pcm):
         return length_tokens(int(pcm.shape[0] * sample_rate / max(sr, 1)), sample_rate, token_rate)
@@ -343,7 +363,6 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
         with ThreadPoolExecutor(num_workers) as readers:
             it = iter(files)
             in_flight = []                       # (path, future) in file order
-            window, w_rows = [], 0
 
             def top_up():
                 while len(in_flight) < max_in_flight:
@@ -352,23 +371,41 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
                         return
                     in_flight.append((path, readers.submit(read, path)))
 
-            top_up()
-            while in_flight:
-                path, fut = in_flight.pop(0)
-                res = fut.result()
-                top_up()                         # the readers prefetch while the device encodes the window below
-                if isinstance(res, Exception):
-                    fail(path, res)
-                    continue
-                sr, pcm = res
-                r = est_rows(sr, pcm)
-                if window and w_rows + r > window_rows:
-                    run_window(window)
-                    window, w_rows = [], 0
-                window.append((path, sr, pcm))
-                w_rows += r
-            if window:
-                run_window(window)
+            carry = []
+
+            def next_window():
+                """whole files up to window_rows token rows (None at the end); the readers keep prefetching"""
+                window, w_rows = list(carry), sum(est_rows(sr, pcm) for _, sr, pcm in carry)
+                carry.clear()
+                top_up()
+                while in_flight:
+                    path, fut = in_flight.pop(0)
+                    res = fut.result()
+                    top_up()
+                    if isinstance(res, Exception):
+                        fail(path, res)
+                        continue
+                    sr, pcm = res
+                    r = est_rows(sr, pcm)
+                    if window and w_rows + r > window_rows:
+                        carry.append((path, sr, pcm))
+                        return window
+                    window.append((path, sr, pcm))
+                    w_rows += r
+                return window or None
+
+            # software pipeline over windows: launch every batch of window w, prepare window w + 1 (host work + side
+            # stream) while the device encodes, then collect the tokens of window w and hand finished files to the writers
+            w0 = next_window()
+            cur = prepare_async(w0) if w0 else None
+            while cur is not None:
+                st_, ready = cur
+                launched = launch_window(st_, ready)
+                nxt_files = next_window()
+                nxt = prepare_async(nxt_files) if nxt_files else None
+                for item in launched:
+                    st_.absorb(*fetch(item))
+                cur = nxt
     finally:
         writers.shutdown(wait=True)
     for path, f in write_futs:

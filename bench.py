@@ -211,6 +211,9 @@ def workload_config(workload, lengths):
     if workload == 'c4':
         name = ('acoustic encode_batch_files-equivalent: per-GPU shard of BASELINE configs[3] (1250 of 10000 clips x 20 s '
                 '@24 kHz); EnCodec SEANet encoder + LSTM + RVQ 16 codebooks')
+    if workload == 'hs':
+        name = ('semantic_s as the reference builds it (mHuBERT-base: 7-layer conv feature encoder + positional conv + 11 post-LN '
+                'transformer layers + k-means 1000) on the per-GPU shard of BASELINE configs[2] (1250 clips, U(2,30) s @16 kHz)')
     if workload == 'c2':
         name = f'semantic_m encode of 64 x 10 s @16 kHz clips (BASELINE configs[1] shape); conformer x{N_LAYERS} + VQ {CODEBOOK}'
     return {'workload': name, 'clips_per_gpu': int(len(lengths)), 'audio_seconds_per_gpu': float(lengths.sum() / (24000 if workload == 'c4' else SR)),
@@ -276,7 +279,21 @@ def run_workload(ctx: Ctx, workload: str, steps: int, warmup: int, instrument: b
     acoustic = workload == 'c4'
     sr = 24000 if acoustic else SR
     audio_s = float(lengths.sum() / sr)
-    if acoustic:
+    if workload == 'hs':
+        # the reference's own semantic_s (mHuBERT-base, hidden state 11, k-means 1000) on the c3 shard; raw waveforms in,
+        # per-clip normalisation on the device, ceil(n / 320) token rows per clip as the reference saves them
+        from audiotoken_b200.hubert import HubertEncoder, feat_lengths, plan_hubert
+        enc = HubertEncoder(device=str(device), precision='bf16')
+        t_pad = int(feat_lengths(CHUNK_S * sr))
+        rows = np.minimum(np.array([packing.length_tokens(int(n), sr, TOKEN_RATE) for n in lengths]), t_pad)
+        batches = packing.bucket_by_rows(rows.tolist(), 32768)
+
+        def make_plan(ln, offs, rws):
+            return plan_hubert(ln, offs, CHUNK_S * sr, rws)
+
+        _plain = enc.encode_plan
+        enc.encode_plan = lambda w, plan: _plain(w, plan, True)[:2]
+    elif acoustic:
         from audiotoken_b200.acoustic import AcousticEncoder, plan_acoustic
         rows = np.array([packing.length_tokens(int(n), sr, 75) for n in lengths])
         enc = AcousticEncoder(device=str(device))
@@ -374,6 +391,9 @@ def run_workload(ctx: Ctx, workload: str, steps: int, warmup: int, instrument: b
     res = dict(workload=workload, lengths=lengths, rows=rows, audio_s=audio_s, ms_res=ms_res, ms_e2e=ms_e2e,
                gpu_launches=gpu_launches, clocks=clocks, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, acoustic=acoustic,
                num_codebooks=getattr(enc, 'num_codebooks', 1), n_batches=len(batches))
+    if workload == 'hs':
+        instrument = False
+        res.update(cls_ms=np.zeros(6), gemm_flops=0.0, ac_ms=np.zeros(4))
     if instrument:          # instrumented steps: CUDA-event time per kernel class
         import ctypes as C
         lib = L.load()
@@ -455,7 +475,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c3', choices=['c3', 'c2', 'c4'])
+    ap.add_argument('--workload', default='c3', choices=['c3', 'c2', 'c4', 'hs'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the acoustic_c4 and files_e2e legs of the default run')
     args = ap.parse_args()

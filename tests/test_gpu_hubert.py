@@ -116,3 +116,43 @@ def test_hubert_long_ragged_batch_runs_and_is_deterministic(cuda_device):
     for x, y, r in zip(a, b, rows):
         assert x.shape == (1, r) and torch.equal(x, y)
         assert int(x.min()) >= 0 and int(x.max()) < 1000
+
+
+def test_audiotoken_semantic_s_hubert_api(cuda_device, tmp_path):
+    """AudioToken('semantic_s', semantic_s_model='hubert'): encode(array), and encode_batch_files == per-chunk reference
+    semantics (each streamed chunk normalised on its own, padded to chunk_size, ceil(n / 320) tokens saved)."""
+    import math
+    from audiotoken_b200 import AudioToken
+    from audiotoken_b200 import io as aio
+    sr, chunk = 16000, 2
+    tok = AudioToken('semantic_s', device='cuda:0', semantic_s_model='hubert', synthetic_weights=True, n_layers=2, precision='fp32')
+    x = synthetic_waveform(600, 20000, sr)
+    single = tok.encode(x[None].numpy())
+    assert single.shape == (1, 1, int(feat_lengths(20000))) and single.dtype == torch.int16
+    files = []
+    for i, n in enumerate((sr * 2, sr * 5 + 777, 4000)):
+        p = tmp_path / f'h{i}.wav'
+        aio.write_wav(str(p), synthetic_waveform(610 + i, n, sr), sr)
+        files.append(str(p))
+    out = tmp_path / 'out'
+    tok.encode_batch_files(batch_size=2, outdir=str(out), chunk_size=chunk, audio_files=files, num_workers=2)
+    assert tok.last_stats['files'] == 3 and not tok.last_stats['errors']
+    enc = tok.encoder
+    for f in files:
+        got = np.load(out / (os.path.basename(f).split('.')[0] + '.npy'))
+        wave = aio.read_audio(f, sr)
+        want = []
+        for a in range(0, wave.shape[1], chunk * sr):
+            seg = wave[0, a:a + chunk * sr]
+            if seg.numel() < 3200:
+                continue
+            # the reference: normalise the chunk, right-pad to chunk_size with a 0/1 mask, encoder(), keep ceil(n/320) tokens
+            xb = torch.zeros(1, chunk * sr)
+            mb = torch.zeros(1, chunk * sr)
+            xb[0, :seg.numel()] = OH.processor_normalize(seg)
+            mb[0, :seg.numel()] = 1
+            t = enc(xb.to(cuda_device), mb.to(cuda_device)).cpu()
+            want.append(t[0, :, :math.ceil(seg.numel() / sr * 50)].numpy())
+        want = np.hstack(want)
+        assert got.shape == want.shape and got.dtype == np.int16, (f, got.shape, want.shape)
+        assert (got == want).mean() >= 0.99, f          # device fp64-sum normalisation vs torch fp32 before the argmin
