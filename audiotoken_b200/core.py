@@ -238,7 +238,8 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
     device = getattr(encoder, 'device', None)
     on_gpu = device is not None and torch.device(device).type == 'cuda'
     errors: Dict[str, str] = {}
-    stats = {'files': 0, 'segments': 0, 'audio_seconds': 0.0, 'windows': 0, 'batches': 0, 'peak_window_bytes': 0}
+    stats = {'files': 0, 'segments': 0, 'audio_seconds': 0.0, 'windows': 0, 'batches': 0, 'peak_window_bytes': 0,
+             't_read_wait': 0.0, 't_prepare': 0.0, 't_launch': 0.0, 't_fetch': 0.0}     # host seconds per stage of the loop
 
     def fail(path, exc):
         errors[path] = repr(exc)
@@ -396,15 +397,21 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
 
             # software pipeline over windows: launch every batch of window w, prepare window w + 1 (host work + side
             # stream) while the device encodes, then collect the tokens of window w and hand finished files to the writers
-            w0 = next_window()
-            cur = prepare_async(w0) if w0 else None
+            def timed(key, fn, *a):
+                t = time.perf_counter()
+                r = fn(*a)
+                stats[key] += time.perf_counter() - t
+                return r
+
+            w0 = timed('t_read_wait', next_window)
+            cur = timed('t_prepare', prepare_async, w0) if w0 else None
             while cur is not None:
                 st_, ready = cur
-                launched = launch_window(st_, ready)
-                nxt_files = next_window()
-                nxt = prepare_async(nxt_files) if nxt_files else None
+                launched = timed('t_launch', launch_window, st_, ready)
+                nxt_files = timed('t_read_wait', next_window)
+                nxt = timed('t_prepare', prepare_async, nxt_files) if nxt_files else None
                 for item in launched:
-                    st_.absorb(*fetch(item))
+                    st_.absorb(*timed('t_fetch', fetch, item))
                 cur = nxt
     finally:
         writers.shutdown(wait=True)

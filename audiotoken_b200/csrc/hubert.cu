@@ -32,6 +32,8 @@
 #include <string>
 #include "common.cuh"
 
+void b2t_reset_launch_count();
+
 struct b2t_hubert_model {
   int n_layers;
   int codebook_size;
@@ -377,6 +379,7 @@ extern "C" int b2t_hubert_encode(const b2t_hubert_model* m, const float* wave, c
   B2T_REQUIRE(m && wave && b && workspace && tokens, B2T_ERR_ARG, "b2t_hubert_encode: null argument");
   int rc = b2t_arch_ok();
   if (rc != B2T_OK) return rc;
+  b2t_reset_launch_count();
   const int M = b->total_rows;
   if (M <= 0 || b->n_clips <= 0) return B2T_OK;
   B2T_REQUIRE(b->level0_rows % 64 == 0 && b->pos_rows >= kPosK, B2T_ERR_ARG, "b2t_hubert_encode: bad level tables");

@@ -95,13 +95,56 @@ def read_audio(path, model_sample_rate: int, device=None) -> torch.Tensor:
     return convert_audio(audio, int(sr), model_sample_rate)
 
 
+def _riff_pcm(path):
+    """(sample_rate, channels, numpy dtype, byte offset, byte count) of a plain PCM / IEEE-float RIFF file, or None for
+    anything this light parser does not handle (WAVE_FORMAT_EXTENSIBLE, 24-bit, RF64 ...: scipy reads those)."""
+    import struct
+    with open(path, 'rb') as f:
+        head = f.read(12)
+        if len(head) < 12 or head[:4] != b'RIFF' or head[8:12] != b'WAVE':
+            return None
+        fmt = None
+        while True:
+            hdr = f.read(8)
+            if len(hdr) < 8:
+                return None
+            cid, size = hdr[:4], struct.unpack('<I', hdr[4:])[0]
+            if cid == b'fmt ':
+                raw = f.read(size + (size & 1))
+                if size < 16:
+                    return None
+                tag, ch, rate, _, _, bits = struct.unpack('<HHIIHH', raw[:16])
+                dt = {(1, 16): np.int16, (1, 32): np.int32, (1, 8): np.uint8, (3, 32): np.float32}.get((tag, bits))
+                if dt is None or ch < 1:
+                    return None
+                fmt = (rate, ch, dt)
+            elif cid == b'data':
+                if fmt is None:
+                    return None
+                return fmt[0], fmt[1], fmt[2], f.tell(), size
+            else:
+                f.seek(size + (size & 1), 1)
+
+
 def read_wav_raw(path) -> Tuple[int, np.ndarray]:
     """Host-only half of the batch reader: RIFF/WAV file -> (sample_rate, PCM array [L] or [L, C]) untouched.
-    Runs in the reader threads of the streaming file loop (no CUDA calls, releases the GIL in the file read)."""
+    Runs in the reader threads of the streaming file loop: no CUDA calls, and for plain PCM16 / PCM32 / u8 / float32
+    files the payload is one `np.fromfile` (a single C call that releases the GIL, so 16 readers do not starve the
+    thread that launches kernels); other encodings go through scipy."""
     if not str(path).lower().endswith('.wav'):
         raise NotImplementedError(f'{path}: only .wav can be decoded offline (no ffmpeg/torchcodec in this image)')
-    from scipy.io import wavfile
-    sr, data = wavfile.read(str(path))
+    info = _riff_pcm(str(path))
+    if info is not None:
+        sr, ch, dt, offset, nbytes = info
+        item = np.dtype(dt).itemsize
+        avail = max(0, os.path.getsize(str(path)) - offset)
+        count = min(nbytes, avail) // (item * ch) * ch
+        data = np.fromfile(str(path), dtype=dt, count=count, offset=offset)
+        if ch > 1:
+            data = data.reshape(-1, ch)
+    else:
+        from scipy.io import wavfile
+        sr, data = wavfile.read(str(path))
     if data.ndim == 2 and data.shape[1] != 1:
         raise AssertionError(f'Audio needs to be mono, provided {data.shape[1]} channels for {path}')
     return int(sr), data

@@ -455,6 +455,7 @@ def run_files_e2e(ctx: Ctx, n_files: int) -> dict:
         return {'value': st['audio_seconds'] / wall, 'unit': 'audio-s/s', 'wall_s': wall, 'files': st['files'],
                 'audio_seconds': st['audio_seconds'], 'errors': len(st['errors']), 'windows': st['windows'], 'batches': st['batches'],
                 'wav_bytes_read': int(in_bytes), 'npy_bytes_written': int(out_bytes), 'reader_threads': min(16, os.cpu_count() or 1),
+                'host_seconds': {k: round(st[k], 3) for k in ('t_read_wait', 't_prepare', 't_launch', 't_fetch')},
                 'what': f'AudioToken(semantic_m).encode_batch_files: {st["files"]} PCM16 WAV files on {"/dev/shm" if base else "tmp"} -> '
                         '.npy token files (file read + RIFF parse + GPU PCM decode + encode + D2H + npy write inside the timed region)'}
     finally:
