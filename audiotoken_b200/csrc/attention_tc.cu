@@ -753,6 +753,357 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   }
   stamp();                                          // CTA done
 }
+
+// =====================================================================================================================
+// attention_tc3_kernel (attn_two_pass = 2): ONE pass over the keys, two accumulators, lazy integer rescaling.
+//
+// The two-pass kernel above computes Q K^T twice to know the row bound before the first exponential.  Here every S tile
+// is computed once.  As in the two-pass kernel a thread owns (query row, 32-key half h of every 64-key tile) — but each
+// half has its OWN running bound m_h, row sum l_h and accumulator O_h in TMEM: the P.V product of a tile is split along
+// the keys, the first two k16 MMAs (keys 0..31) accumulate into O_0, the last two (keys 32..63) into O_1 — the same four
+// MMAs as before, so the split is free, and no maximum is ever exchanged between threads (S 2 x 64 + O 2 x 64 = 256
+// TMEM columns).  m_h is an INTEGER in the log2 domain (ceil of the largest biased score seen) and only moves when a tile
+// exceeds it by more than 8: then the owning warp rescales its 32 rows of O_h in TMEM by the exact power of two
+// (tcgen05.ld / st; the wait for the P buffer already guarantees that the previous P.V is complete).
+// P = 2^(score - m_h) <= 2^8 is exact in its exponent, so the bf16 rounding of P does not depend on the rescaling
+// schedule.  At the end  O = (O_0 2^(m_0 - M) + O_1 2^(m_1 - M)) / (l_0 2^(m_0 - M) + l_1 2^(m_1 - M)).
+// Against the two-pass kernel: half the S MMAs, half the K loads, one TMEM read of S instead of two.
+// =====================================================================================================================
+B2T_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+B2T_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreadsAttn2, kCtasPerSm)      // 80 registers: 88 (maxnreg) cost the second CTA per SM
+attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ CUtensorMap map_e,
+                     const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
+                     const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
+                     __nv_bfloat16* __restrict__ out, int H, long long* __restrict__ dbg /* developer timeline, or null */) {
+  static_assert(kKT == 64 && kSoftmaxWarps == 8 && kTmemCols == 256, "single-pass kernel: 64-key tiles, 2 x 4 softmax warps");
+#ifdef B2T_ATTN_TIMELINE
+  // clock64 stamps of one mid-grid CTA: softmax thread 96 -> dbg[0..255], S issuer (thread 32) -> dbg[256..383],
+  // PV issuer (thread 64) -> dbg[384..511], TMA producer (thread 0) -> dbg[512..639]
+  const bool tlc = dbg != nullptr && blockIdx.x == 300 && blockIdx.y == 5;
+  int tln = 0;
+  auto stamp = [&](int base_, int cap) { if (tlc && tln < cap) dbg[base_ + tln++] = clock64(); };
+#else
+  auto stamp = [&](int, int) { (void)dbg; };
+#endif
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base + AttnSmem::kQ, sKV = base + AttnSmem::kKV, sP = base + AttnSmem::kP, sE = base + AttnSmem::kE;
+  __nv_bfloat16* sR = reinterpret_cast<__nv_bfloat16*>(gbase + AttnSmem::kR);
+  const uint32_t bars = base + AttnSmem::kBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + AttnSmem::kBars + 8 * tp::COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int clip = qtile_clip[blockIdx.x], q0 = qtile_q0[blockIdx.x];
+  const int r0 = row_off[clip], rows = row_off[clip + 1] - r0, nkeys = valid_rows[clip];
+  const int nkt = (nkeys + kKT - 1) / kKT;
+  const int head = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(tp::EFULL), 1); mbar_init(bar(tp::QFULL), 1); mbar_init(bar(tp::RFULL), 1); mbar_init(bar(tp::OFULL), 1);
+    for (int s = 0; s < tp::kSlots; ++s) { mbar_init(bar(tp::KVFULL + s), 1); mbar_init(bar(tp::KVEMPTY + s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(tp::SFULL + b), 1); mbar_init(bar(tp::SEMPTY + b), kSoftmaxWarps);
+      mbar_init(bar(tp::PFULL + b), kSoftmaxWarps); mbar_init(bar(tp::PEMPTY + b), 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_e); }
+  if (warp == 1) tmem_alloc(bars + 8u * tp::COUNT, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // S double buffer [0,128); accumulators O_0 [128,192) and O_1 [192,256); R (80 columns) borrows [128,208) until the first PV
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT, tR = tmem_base + 2 * kKT;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(bar(tp::EFULL), 80 * 128);
+      tma_load_2d(sE, &map_e, bar(tp::EFULL), 0, 0);
+      mbar_expect_tx(bar(tp::QFULL), kQT * 128);
+      tma_load_2d(sQ, &map_qkv, bar(tp::QFULL), head * kHD, r0 + q0);
+    }
+    // K(j) lives in slot j & 1, V(j) in slot 2 + (j & 1); the two streams are issued independently (non-blocking probes):
+    // an in-order K0 V0 K1 V1 stream would hold the next K load back until P.V two tiles earlier has released its V slot,
+    // i.e. K would be requested barely one tile ahead of its use and the load latency would sit on the critical path.
+    int kn = 0, vn = 0;
+    uint32_t spins = 0;
+    while (kn < nkt || vn < nkt) {
+      bool progress = false;
+      if (kn < nkt) {
+        const uint32_t st = (uint32_t)kn & 1u;
+        const bool ok = mbar_test_wait(bar(tp::KVEMPTY) + 8u * st, (((uint32_t)kn >> 1) & 1u) ^ 1u);
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(tp::KVFULL) + 8u * st, tp::kSlotBytes);
+            tma_load_2d(sKV + st * tp::kSlotBytes, &map_kv, bar(tp::KVFULL) + 8u * st, H + head * kHD, r0 + kn * kKT);
+          }
+          ++kn; progress = true;
+          if (threadIdx.x == 0) stamp(512, 128);                  // K(kn) issued
+        }
+      }
+      if (vn < nkt) {
+        const uint32_t st = 2u + ((uint32_t)vn & 1u);
+        const bool ok = mbar_test_wait(bar(tp::KVEMPTY) + 8u * st, (((uint32_t)vn >> 1) & 1u) ^ 1u);
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(tp::KVFULL) + 8u * st, tp::kSlotBytes);
+            tma_load_2d(sKV + st * tp::kSlotBytes, &map_kv, bar(tp::KVFULL) + 8u * st, 2 * H + head * kHD, r0 + vn * kKT);
+          }
+          ++vn; progress = true;
+        }
+      }
+      if (progress) spins = 0;
+      else if (++spins > (1u << 28)) b2t_trap_report("attention_tc3 TMA producer: K / V slot wait (next K tile, next V tile)", (unsigned)kn, (unsigned)vn);
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ===== PV issuer: keys 0..31 of every tile accumulate into O_0, keys 32..63 into O_1 =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
+    const uint64_t dkv = make_smem_desc(sKV), dp0 = make_smem_desc(sP);
+    for (int ip = 0; ip < nkt; ++ip) {
+      const uint32_t pb = (uint32_t)ip & 1u, st = 2u + ((uint32_t)ip & 1u);
+      if (threadIdx.x == 64) stamp(384, 128);                     // [3 ip] before the waits
+      mbar_wait(bar(tp::PFULL) + 8u * pb, ((uint32_t)ip >> 1) & 1u);       // one wait after the other (see the two-pass kernel)
+      if (threadIdx.x == 64) stamp(384, 128);                     // [3 ip + 1] P ready
+      mbar_wait(bar(tp::KVFULL) + 8u * st, ((uint32_t)ip >> 1) & 1u);
+      if (threadIdx.x == 64) stamp(384, 128);                     // [3 ip + 2] V landed
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dv = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4)), dp = dp0 + (uint64_t)(pb * (kPBuf >> 4));
+#pragma unroll
+        for (int kk = 0; kk < kKT / 16; ++kk)
+#ifdef B2T_TC3_ONEACC
+          umma_bf16(tO, dp + (uint64_t)(2 * kk), dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o, (ip != 0 || kk != 0) ? 1u : 0u);
+#else
+          umma_bf16(tO + (kk >> 1) * kHD, dp + (uint64_t)(2 * kk), dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o,
+                    (ip != 0 || (kk & 1) != 0) ? 1u : 0u);
+#endif
+        umma_commit(bar(tp::PEMPTY) + 8u * pb);
+        umma_commit(bar(tp::KVEMPTY) + 8u * st);
+        if (ip == nkt - 1) umma_commit(bar(tp::OFULL));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== S issuer =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T   (both K-major)
+    constexpr uint32_t idesc_r = make_idesc(128, 80);           // R = Q E^T
+    const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ), dkv = make_smem_desc(sKV);
+    mbar_wait(bar(tp::EFULL), 0);
+    mbar_wait(bar(tp::QFULL), 0);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tR, dq + (uint64_t)(2 * k), de + (uint64_t)(2 * k), idesc_r, k != 0);
+      umma_commit(bar(tp::RFULL));
+    }
+    for (int j = 0; j < nkt; ++j) {
+      const uint32_t b = (uint32_t)j & 1u, st = (uint32_t)j & 1u;
+      if (threadIdx.x == 32) stamp(256, 128);                     // [3 j] before the waits
+      mbar_wait(bar(tp::KVFULL) + 8u * st, ((uint32_t)j >> 1) & 1u);
+      if (threadIdx.x == 32) stamp(256, 128);                     // [3 j + 1] K landed
+      mbar_wait(bar(tp::SEMPTY) + 8u * b, (((uint32_t)j >> 1) & 1u) ^ 1u);
+      if (threadIdx.x == 32) stamp(256, 128);                     // [3 j + 2] S buffer free
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dk = dkv + (uint64_t)(st * (tp::kSlotBytes >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS + b * kKT, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
+        umma_commit(bar(tp::SFULL) + 8u * b);
+        umma_commit(bar(tp::KVEMPTY) + 8u * st);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax / output warps: thread = (query row = TMEM lane, 32-key half wg) with its own bound / sum / accumulator =====
+    constexpr int kWG = 2, kKW = 32;
+    const int quad = warp & 3;
+    const int wg = (warp - 3) >> 2;
+    const int r = quad * 32 + lane;
+    const int qpos = q0 + r;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
+    constexpr float kTau = 8.0f;
+    float* smax = reinterpret_cast<float*>(gbase + AttnSmem::kMax);   // [wg][row]
+    float* ssum = reinterpret_cast<float*>(gbase + AttnSmem::kSum);
+    const __nv_bfloat16* myR = sR + r * kRS;
+
+    // R row -> bf16 (the reference's einsum output dtype) -> shared memory; the two warps of a row split the columns
+    mbar_wait(bar(tp::RFULL), 0);
+    tc_fence_after();
+    {
+      uint32_t* rr = reinterpret_cast<uint32_t*>(sR + r * kRS);
+      uint32_t a[32];
+      tmem_ld_32x32_nowait(tR + lane_base + wg * 32, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) rr[(wg * 32 + i) >> 1] = pack_bf16x2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+      if (wg == kWG - 1) {
+        uint32_t c[16];
+        tmem_ld_32x32_x16_nowait(tR + lane_base + 64, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) rr[(64 + i) >> 1] = pack_bf16x2(__uint_as_float(c[i]), __uint_as_float(c[i + 1]));
+      }
+    }
+    tc_fence_before();
+    row_barrier<32 * kWG>(quad);                    // every R row is complete (and no R read is outstanding: O may be written)
+    const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
+
+    float m_run = -INFINITY, l = 0.f;
+    for (int i = 0; i < nkt; ++i) {
+      const int b = i & 1, k0 = i * kKT + wg * kKW;
+      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i] tile start
+      mbar_wait(bar(tp::SFULL + b), (i >> 1) & 1);
+      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 1] S ready
+      tc_fence_after();
+      float t[kKW];
+      {
+        uint32_t x[32];
+        tmem_ld_32x32_nowait(tS + lane_base + (uint32_t)(b * kKT + wg * kKW), x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(x[e]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(tp::SEMPTY + b));            // S slice in registers: hand the buffer back at once
+      const int dlo = k0 - qpos, dhi = k0 + kKW - 1 - qpos;
+      const bool band = !(dhi <= -kLeft || dlo >= kRight);        // outside the diagonal band the bias is one constant per row
+      const float cb = dhi <= -kLeft ? rl : rrt;
+      if (band) {
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) t[e] += __bfloat162float(myR[max(-kLeft, min(kRight, dlo + e)) + kLeft]);
+      }
+      if (k0 + kKW > nkeys) {
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
+      }
+      float m0 = fmaxf(t[0], t[1]), m1 = fmaxf(t[2], t[3]);
+#pragma unroll
+      for (int e = 4; e < kKW; e += 4) { m0 = fmaxf(m0, fmaxf(t[e], t[e + 1])); m1 = fmaxf(m1, fmaxf(t[e + 2], t[e + 3])); }
+      const float mt = fmaxf(m0, m1);
+      const float mts = band ? mt * kScale : fmaf(mt, kScale, cb);           // largest biased score of the slice, log2 domain
+#ifdef B2T_TC3_NOMAX
+      const bool grow = false;
+      const float m_new = 16.f + 0.f * mts;
+#else
+      const bool grow = mts > m_run + kTau;                                   // false for a fully masked slice (mts = -inf)
+      const float m_new = grow ? ceilf(mts) : m_run;
+#endif
+      const float off = (band ? 0.f : cb) - m_new;                            // p = 2^(raw * kScale + off)
+      const bool dead = m_new == -INFINITY;                                   // nothing valid seen yet: p = 0
+      float ls0 = 0.f, ls1 = 0.f;
+      uint4 v[kKW / 8];
+#pragma unroll
+      for (int ch = 0; ch < kKW / 8; ++ch) {
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pv[e] = dead ? 0.f : ex2a(fmaf(t[ch * 8 + e], kScale, off));
+        ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+        ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+        v[ch].x = pack_bf16x2(pv[0], pv[1]); v[ch].y = pack_bf16x2(pv[2], pv[3]);
+        v[ch].z = pack_bf16x2(pv[4], pv[5]); v[ch].w = pack_bf16x2(pv[6], pv[7]);
+      }
+      const int pb = i & 1;
+      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 2] exponentials done
+      mbar_wait(bar(tp::PEMPTY + pb), ((i >> 1) & 1) ^ 1u);        // P buffer free == every earlier P.V is complete
+      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 3] P buffer free
+      const float m_old = m_run;
+      m_run = m_new;
+      uint8_t* half = gbase + AttnSmem::kP + pb * kPBuf + r * 128;
+      const int ch0 = (wg * kKW) >> 3;
+#pragma unroll
+      for (int ch = 0; ch < kKW / 8; ++ch) *reinterpret_cast<uint4*>(half + (((ch0 + ch) ^ (r & 7)) << 4)) = v[ch];
+      // the bound of some row of this warp moved: rescale the warp's 32 rows of O_wg by the exact power of two (rows
+      // whose bound stayed: factor 1).  Done here, after the P tile has left the registers; P.V(i) cannot start before
+      // this warp's arrival below.  PEMPTY[pb] covered P.V(i-2); P.V(i-1) writes both accumulators too.
+      const bool resc = grow && i > 0 && m_old > -INFINITY;
+      if (__any_sync(0xffffffffu, resc)) {
+        mbar_wait(bar(tp::PEMPTY + (pb ^ 1)), ((i - 1) >> 1) & 1);
+        tc_fence_after();
+        const float f = resc ? ex2a(m_old - m_new) : 1.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t o[32];
+          tmem_ld_32x32_nowait(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+          tmem_st_32x32(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        l *= f;
+      }
+      l += ls0 + ls1;
+      fence_proxy_async();          // P visible to the tensor core (generic -> async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(tp::PFULL + pb));
+      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 4] P handed over
+    }
+    if (threadIdx.x == 96) stamp(0, 256);
+
+    // ---- output: merge the two accumulators
+    smax[wg * kQT + r] = m_run;
+    ssum[wg * kQT + r] = l;
+    row_barrier<32 * kWG>(quad);
+    const float ma = smax[r], mb = smax[kQT + r];
+    const float mm = fmaxf(ma, mb);                                          // finite: key 0 of the clip is always valid
+    const float fa = ex2a(ma - mm), fb = ex2a(mb - mm);                      // 2^(-inf) = 0 for a half that never saw a key
+    const float inv = 1.0f / (ssum[r] * fa + ssum[kQT + r] * fb);
+    const float ga = fa * inv, gb = fb * inv;
+    mbar_wait(bar(tp::OFULL), 0);
+    if (threadIdx.x == 96) stamp(0, 256);
+    tc_fence_after();
+    __nv_bfloat16* dst = out + (size_t)(r0 + qpos) * H + head * kHD + wg * 32;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t xa[16], xb[16];
+      tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(wg * 32 + 16 * ch), xa);
+      tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(kHD + wg * 32 + 16 * ch), xb);
+      tmem_ld_wait();
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        w[e] = pack_bf16x2(fmaf(__uint_as_float(xb[2 * e]), gb, __uint_as_float(xa[2 * e]) * ga),
+                           fmaf(__uint_as_float(xb[2 * e + 1]), gb, __uint_as_float(xa[2 * e + 1]) * ga));
+      if (qpos < rows)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"l"(dst + 16 * ch), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
 #endif  // !B2T_ATTN_WIDE
 
 }  // namespace
@@ -782,6 +1133,13 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
     // g_attn_two_pass bits: 1 = two-pass, 4 = row sums on the tensor core as well
     B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc2_kernel<false>);
     B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc2_kernel<true>);
+    if (g_attn_two_pass == 2) {          // single pass, split accumulators
+      B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc3_kernel);
+      attention_tc3_kernel<<<grid, kThreadsAttn2, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
+                                                                         b->qtile128_q0, (__nv_bfloat16*)out, H, g_attn_dbg);
+      B2T_LAUNCH_CHECK();
+      return B2T_OK;
+    }
     auto kern = (g_attn_two_pass & 4) ? attention_tc2_kernel<true> : attention_tc2_kernel<false>;
     kern<<<grid, kThreadsAttn2, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip, b->qtile128_q0,
                                                        (__nv_bfloat16*)out, g_attn_dbg, H);

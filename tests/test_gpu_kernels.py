@@ -235,6 +235,39 @@ def test_attention_bf16(cuda_device, impl, rows, valid):
     assert rel_err(out.float(), ref) < 1e-2, rel_err(out.float(), ref)
 
 
+@pytest.mark.parametrize('mode', [1, 2])
+def test_attention_tensor_large_dynamic_range(cuda_device, mode):
+    """Adversarial logits for the fixed-bound (mode 1: two-pass) and lazily rescaled (mode 2: single-pass) tcgen05
+    kernels: q, k scaled so that raw scores span hundreds of log2 units, the largest raw score and the largest relative
+    bias sit on DIFFERENT keys (the two-pass bound max raw + max bias is then tens of octaves above every real score),
+    a bias spike on the far-left bucket, rows whose maximum grows late (forces the rescale path), masked keys holding
+    the largest raw scores of all.  Checked against the fp64 formula."""
+    lib = L.load()
+    rows, valid = [700, 130, 64], [650, 130, 40]
+    g = torch.Generator().manual_seed(99)
+    M = sum(rows)
+    qkv = torch.randn(M, 3072, generator=g) * 0.7
+    qkv[:, :2048] *= 3.0                                     # q.k / 8 up to +-100: e^100 dynamic range within a row
+    # keys late in the first clip get a large norm along one direction every query shares: the row maximum grows at the end
+    qkv[:, 0:1024:64] += 2.0
+    qkv[600:650, 1024:2048:64] += 9.0
+    qkv[650:700, 1024:2048] *= 6.0                           # masked keys (>= valid_rows) with the largest raw scores
+    E = torch.randn(73, 64, generator=g) * 0.5
+    E[0] *= 8.0                                              # spike on the clamped far-left bucket (distance <= -64)
+    E[72] *= 5.0                                             # and on the far-right one
+    qkv, E = bf(qkv), bf(E)
+    plan = _attn_plan(rows, valid)
+    ref = _attn_oracle(qkv.double(), E.double(), rows, valid, False)
+    assert torch.isfinite(ref).all()
+    L.check(lib.b2t_set_option(b'attn_two_pass', mode), 'attn_two_pass')
+    try:
+        out = ops.relkey_attention(qkv.to(cuda_device, torch.bfloat16), E.to(cuda_device, torch.bfloat16), plan, 'bf16', L.IMPL_TENSOR)
+    finally:
+        L.check(lib.b2t_set_option(b'attn_two_pass', 1), 'attn_two_pass')
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.float(), ref.float()) < 1.5e-2, rel_err(out.float(), ref.float())
+
+
 # ---------------------------------------------------------------------------------- depthwise conv
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_dwconv_ln_swish(cuda_device, precision):
