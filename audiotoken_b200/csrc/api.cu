@@ -35,6 +35,29 @@ int b2t_num_sms() {
   return sms[dev];
 }
 
+// 32-byte record in mapped, portable host memory that device code fills in before a trap (b2t_trap_record)
+static unsigned* g_trap_rec = nullptr;
+unsigned* b2t_trap_rec() {
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 32, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      memset(p, 0, 32);
+      g_trap_rec = (unsigned*)p;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  return g_trap_rec;
+}
+static void b2t_trap_text(char* buf, size_t n) {
+  buf[0] = 0;
+  if (g_trap_rec && g_trap_rec[0])
+    snprintf(buf, n, "; device trap record: site 0x%x a=%u b=%u block=(%u,%u) thread=%u", g_trap_rec[0], g_trap_rec[1], g_trap_rec[2],
+             g_trap_rec[3], g_trap_rec[4], g_trap_rec[5]);
+}
+
 static int g_debug_sync = -1;
 bool b2t_debug_sync() {
   if (g_debug_sync < 0) {
@@ -47,8 +70,10 @@ void b2t_set_debug_sync(int on) { g_debug_sync = on ? 1 : 0; }
 int b2t_debug_sync_check(const char* file, int line) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
-    b2t_set_error("device fault in the kernel launched at %s:%d: %s", file, line, cudaGetErrorString(e));
-    fprintf(stderr, "b200tok: device fault in the kernel launched at %s:%d: %s\n", file, line, cudaGetErrorString(e));
+    char rec[160];
+    b2t_trap_text(rec, sizeof(rec));
+    b2t_set_error("device fault in the kernel launched at %s:%d: %s%s", file, line, cudaGetErrorString(e), rec);
+    fprintf(stderr, "b200tok: device fault in the kernel launched at %s:%d: %s%s\n", file, line, cudaGetErrorString(e), rec);
     return B2T_ERR_CUDA;
   }
   return B2T_OK;
@@ -65,12 +90,17 @@ int b2t_arch_ok() {
 
 // developer hook (b2t_set_option("test_trap", 1)): one thread runs the device trap report, so that the host-side
 // reporting of a protocol time-out can be checked on a GPU without breaking a protocol
-__global__ void test_trap_kernel() { b2t_trap_report("test trap requested through b2t_set_option", 0xabcdu, 7u); }
-int b2t_test_trap() {
-  test_trap_kernel<<<1, 1>>>();
+__global__ void test_trap_kernel(unsigned* rec) {
+  if (rec) b2t_trap_record(rec, 0x7e57u, 0xabcdu, 7u);
+  b2t_trap_report("test trap requested through b2t_set_option", 0xabcdu, 7u);
+}
+int b2t_test_trap(int light) {
+  test_trap_kernel<<<1, 1>>>(light ? b2t_trap_rec() : nullptr);
   B2T_LAUNCH_CHECK();
   cudaError_t e = cudaDeviceSynchronize();
-  b2t_set_error("test trap: cudaDeviceSynchronize -> %s", cudaGetErrorString(e));
+  char rec[160];
+  b2t_trap_text(rec, sizeof(rec));
+  b2t_set_error("test trap: cudaDeviceSynchronize -> %s%s", cudaGetErrorString(e), rec);
   return e == cudaSuccess ? B2T_OK : B2T_ERR_CUDA;
 }
 
@@ -95,5 +125,11 @@ int b2t_device_check(int device) {
 }
 
 int b2t_last_launch_count(void) { return g_launches; }
+
+int b2t_last_device_trap(unsigned* rec6) {
+  if (!g_trap_rec || g_trap_rec[0] == 0) return 0;
+  if (rec6) memcpy(rec6, g_trap_rec, 6 * sizeof(unsigned));
+  return 1;
+}
 
 }  // extern "C"

@@ -46,6 +46,9 @@ constexpr int kSoftmaxWarps = 8;                 // two warps per TMEM lane quad
 constexpr int kCtasPerSm = B2T_ATTN_CTAS, kTmemCols = 256;
 #endif
 
+#ifndef B2T_ATTN_POLL_SLEEP
+#define B2T_ATTN_POLL_SLEEP 0                   // ns the polling TMA producer sleeps when none of its streams can advance
+#endif
 constexpr int kPBuf = kQT * kKT * 2;             // one P buffer: kKT / 64 K-major blocks of 128 rows x 128 B
 constexpr int kThreadsAttn = 64 + 32 * kSoftmaxWarps;
 
@@ -87,6 +90,36 @@ B2T_DEVICE float ex2a(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA / ALU pipes (Cody-Waite: x = n + f, |f| <= 1/2, 2^f by a degree-3 minimax polynomial, n added to the
+// exponent field): relative error 1e-4, far below the bf16 rounding of P.  x <= 127; anything below -126 flushes to 0.
+B2T_DEVICE float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xr = x + 12582912.0f;                 // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
+  const float f = x - (xr - 12582912.0f);
+  float p = fmaf(f, 0.05550410866f, 0.24022650696f);
+  p = fmaf(p, f, 0.69314718056f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(xr) << 23));
+}
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): two results per issue slot
+B2T_DEVICE float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+B2T_DEVICE float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
 }
 B2T_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -754,6 +787,25 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   stamp();                                          // CTA done
 }
 
+// bounded wait whose time-out is recorded in mapped host memory (no ABI call in register-critical code, see common.cuh)
+B2T_DEVICE void mbar_wait_rec(uint32_t bar, uint32_t parity, unsigned* rec, uint32_t code, uint32_t bars) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) b2t_trap_record(rec, code, (bar - bars) >> 3, parity);
+  }
+}
+
+// Thread layout of the single-pass kernels: warpgroup 0 = TMA producer, S issuer, PV issuer and one idle warp; warpgroups 1 and 2 =
+// the eight softmax warps.  The CTA is launched with 80 registers per thread (two CTAs per SM); warpgroup 0 then gives
+// registers back (setmaxnreg.dec 24) and the softmax warpgroups take them (setmaxnreg.inc 104): at 80 registers the
+// softmax loop spilled its loop-invariant state and re-read it (LDL / S2R: long- and short-scoreboard stalls on 20 % of
+// the loop's samples in the ncu source view).
+constexpr int kThreadsAttn3 = 128 + 32 * kSoftmaxWarps;
+constexpr int kRegsIssue = 24, kRegsSoftmax = 104;
+static_assert(128 * kRegsIssue + 32 * kSoftmaxWarps * kRegsSoftmax <= kThreadsAttn3 * 80, "register pool of the CTA");
+template <int kRegs> B2T_DEVICE void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> B2T_DEVICE void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 // =====================================================================================================================
 // attention_tc3_kernel (attn_two_pass = 2): ONE pass over the keys, two accumulators, lazy integer rescaling.
 //
@@ -782,13 +834,15 @@ B2T_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
 }
 B2T_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kThreadsAttn2, kCtasPerSm)      // 80 registers: 88 (maxnreg) cost the second CTA per SM
+__global__ void __launch_bounds__(kThreadsAttn3, kCtasPerSm)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ CUtensorMap map_e,
                      const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
                      const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
-                     __nv_bfloat16* __restrict__ out, int H, long long* __restrict__ dbg /* developer timeline, or null */) {
+                     __nv_bfloat16* __restrict__ out, int H, long long* __restrict__ dbg /* developer timeline, or null */,
+                     unsigned* __restrict__ trap_rec) {
   static_assert(kKT == 64 && kSoftmaxWarps == 8 && kTmemCols == 256, "single-pass kernel: 64-key tiles, 2 x 4 softmax warps");
+  constexpr uint32_t kTrapSite = 0x300u;           // trap record: 0x300 | warp (mbarrier wait: a = barrier index, b = parity), 0x380 = TMA polling loop
 #ifdef B2T_ATTN_TIMELINE
   // clock64 stamps of one mid-grid CTA: softmax thread 96 -> dbg[0..255], S issuer (thread 32) -> dbg[256..383],
   // PV issuer (thread 64) -> dbg[384..511], TMA producer (thread 0) -> dbg[512..639]
@@ -798,6 +852,14 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 #else
   auto stamp = [&](int, int) { (void)dbg; };
 #endif
+#ifdef B2T_ATTN_TIMELINE
+  // per-CTA log (SM id, first and last clock of the CTA) behind the 1024 timeline words: gaps between CTAs of one SM
+  long long* cta_log = dbg ? dbg + 1024 + 3 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (cta_log && threadIdx.x == 0) {
+    uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    cta_log[0] = smid; cta_log[1] = clock64();
+  }
+#endif
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -805,6 +867,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   __nv_bfloat16* sR = reinterpret_cast<__nv_bfloat16*>(gbase + AttnSmem::kR);
   const uint32_t bars = base + AttnSmem::kBars;
   auto bar = [&](int i) { return bars + 8u * i; };
+  auto wait = [&](uint32_t b_, uint32_t parity_) { mbar_wait_rec(b_, parity_, trap_rec, kTrapSite | (threadIdx.x >> 5), bars); };
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + AttnSmem::kBars + 8 * tp::COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -833,6 +896,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT, tR = tmem_base + 2 * kKT;
 
   if (warp == 0) {
+    reg_dec<kRegsIssue>();
     // ===== TMA producer =====
     const bool leader = elect_one();
     if (leader) {
@@ -872,10 +936,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         }
       }
       if (progress) spins = 0;
-      else if (++spins > (1u << 28)) b2t_trap_report("attention_tc3 TMA producer: K / V slot wait (next K tile, next V tile)", (unsigned)kn, (unsigned)vn);
+      else if (B2T_ATTN_POLL_SLEEP > 0 ? (__nanosleep(B2T_ATTN_POLL_SLEEP), ++spins > (1u << 24)) : (++spins > (1u << 28))) b2t_trap_record(trap_rec, kTrapSite | 0x80u, (unsigned)kn, (unsigned)vn);
     }
     __syncwarp();
   } else if (warp == 2) {
+    reg_dec<kRegsIssue>();
     // ===== PV issuer: keys 0..31 of every tile accumulate into O_0, keys 32..63 into O_1 =====
     const bool leader = elect_one();
     constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
@@ -883,9 +948,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     for (int ip = 0; ip < nkt; ++ip) {
       const uint32_t pb = (uint32_t)ip & 1u, st = 2u + ((uint32_t)ip & 1u);
       if (threadIdx.x == 64) stamp(384, 128);                     // [3 ip] before the waits
-      mbar_wait(bar(tp::PFULL) + 8u * pb, ((uint32_t)ip >> 1) & 1u);       // one wait after the other (see the two-pass kernel)
+      wait(bar(tp::PFULL) + 8u * pb, ((uint32_t)ip >> 1) & 1u);       // one wait after the other (see the two-pass kernel)
       if (threadIdx.x == 64) stamp(384, 128);                     // [3 ip + 1] P ready
-      mbar_wait(bar(tp::KVFULL) + 8u * st, ((uint32_t)ip >> 1) & 1u);
+      wait(bar(tp::KVFULL) + 8u * st, ((uint32_t)ip >> 1) & 1u);
       if (threadIdx.x == 64) stamp(384, 128);                     // [3 ip + 2] V landed
       tc_fence_after();
       if (leader) {
@@ -905,13 +970,14 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
+    reg_dec<kRegsIssue>();
     // ===== S issuer =====
     const bool leader = elect_one();
     constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T   (both K-major)
     constexpr uint32_t idesc_r = make_idesc(128, 80);           // R = Q E^T
     const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ), dkv = make_smem_desc(sKV);
-    mbar_wait(bar(tp::EFULL), 0);
-    mbar_wait(bar(tp::QFULL), 0);
+    wait(bar(tp::EFULL), 0);
+    wait(bar(tp::QFULL), 0);
     tc_fence_after();
     if (leader) {
 #pragma unroll
@@ -921,9 +987,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     for (int j = 0; j < nkt; ++j) {
       const uint32_t b = (uint32_t)j & 1u, st = (uint32_t)j & 1u;
       if (threadIdx.x == 32) stamp(256, 128);                     // [3 j] before the waits
-      mbar_wait(bar(tp::KVFULL) + 8u * st, ((uint32_t)j >> 1) & 1u);
+      wait(bar(tp::KVFULL) + 8u * st, ((uint32_t)j >> 1) & 1u);
       if (threadIdx.x == 32) stamp(256, 128);                     // [3 j + 1] K landed
-      mbar_wait(bar(tp::SEMPTY) + 8u * b, (((uint32_t)j >> 1) & 1u) ^ 1u);
+      wait(bar(tp::SEMPTY) + 8u * b, (((uint32_t)j >> 1) & 1u) ^ 1u);
       if (threadIdx.x == 32) stamp(256, 128);                     // [3 j + 2] S buffer free
       tc_fence_after();
       if (leader) {
@@ -935,11 +1001,14 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    reg_dec<kRegsIssue>();                          // idle member of warpgroup 0
   } else {
     // ===== softmax / output warps: thread = (query row = TMEM lane, 32-key half wg) with its own bound / sum / accumulator =====
+    reg_inc<kRegsSoftmax>();
     constexpr int kWG = 2, kKW = 32;
     const int quad = warp & 3;
-    const int wg = (warp - 3) >> 2;
+    const int wg = (warp - 4) >> 2;
     const int r = quad * 32 + lane;
     const int qpos = q0 + r;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -950,7 +1019,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     const __nv_bfloat16* myR = sR + r * kRS;
 
     // R row -> bf16 (the reference's einsum output dtype) -> shared memory; the two warps of a row split the columns
-    mbar_wait(bar(tp::RFULL), 0);
+    wait(bar(tp::RFULL), 0);
     tc_fence_after();
     {
       uint32_t* rr = reinterpret_cast<uint32_t*>(sR + r * kRS);
@@ -971,12 +1040,18 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     row_barrier<32 * kWG>(quad);                    // every R row is complete (and no R read is outstanding: O may be written)
     const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
 
-    float m_run = -INFINITY, l = 0.f;
+    // "no key seen yet" is a large negative FINITE bound: 2^(-inf + 1e30) = 0 needs no special case in the loop, and
+    // 2^(kNone - m) = 0 in the final merge
+    constexpr float kNone = -1.0e30f;
+    float m_run = kNone, l = 0.f;
+    // byte offsets of this thread's four 16-byte chunks inside a P buffer (128-byte swizzle: chunk ^ (row & 7))
+    const uint32_t pofs = (uint32_t)(AttnSmem::kP + r * 128 + ((((wg * kKW) >> 3) ^ (r & 4)) << 4));
+    const uint32_t plo = (uint32_t)(r & 3) << 4;
     for (int i = 0; i < nkt; ++i) {
       const int b = i & 1, k0 = i * kKT + wg * kKW;
-      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i] tile start
-      mbar_wait(bar(tp::SFULL + b), (i >> 1) & 1);
-      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 1] S ready
+      if (threadIdx.x == 128) stamp(0, 256);                       // [5 i] tile start
+      wait(bar(tp::SFULL + b), (i >> 1) & 1);
+      if (threadIdx.x == 128) stamp(0, 256);                       // [5 i + 1] S ready
       tc_fence_after();
       float t[kKW];
       {
@@ -1005,43 +1080,45 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       for (int e = 4; e < kKW; e += 4) { m0 = fmaxf(m0, fmaxf(t[e], t[e + 1])); m1 = fmaxf(m1, fmaxf(t[e + 2], t[e + 3])); }
       const float mt = fmaxf(m0, m1);
       const float mts = band ? mt * kScale : fmaf(mt, kScale, cb);           // largest biased score of the slice, log2 domain
-#ifdef B2T_TC3_NOMAX
-      const bool grow = false;
-      const float m_new = 16.f + 0.f * mts;
-#else
       const bool grow = mts > m_run + kTau;                                   // false for a fully masked slice (mts = -inf)
       const float m_new = grow ? ceilf(mts) : m_run;
-#endif
       const float off = (band ? 0.f : cb) - m_new;                            // p = 2^(raw * kScale + off)
-      const bool dead = m_new == -INFINITY;                                   // nothing valid seen yet: p = 0
-      float ls0 = 0.f, ls1 = 0.f;
+      // scale + offset and the row sums as packed f32x2 operations (half the issue slots: the loop is issue-bound)
+      const float2 sc2 = make_float2(kScale, kScale), off2 = make_float2(off, off);
+      float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0;
       uint4 v[kKW / 8];
 #pragma unroll
       for (int ch = 0; ch < kKW / 8; ++ch) {
-        float pv[8];
+        float2 pv[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) pv[e] = dead ? 0.f : ex2a(fmaf(t[ch * 8 + e], kScale, off));
-        ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-        ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-        v[ch].x = pack_bf16x2(pv[0], pv[1]); v[ch].y = pack_bf16x2(pv[2], pv[3]);
-        v[ch].z = pack_bf16x2(pv[4], pv[5]); v[ch].w = pack_bf16x2(pv[6], pv[7]);
+        for (int e = 0; e < 4; ++e) {
+          const float2 xe = ffma2(make_float2(t[ch * 8 + 2 * e], t[ch * 8 + 2 * e + 1]), sc2, off2);
+#if defined(B2T_TC3_NOEXP)
+          pv[e] = make_float2(xe.x * 0.001f, xe.y * 0.001f);          // timing experiment only (wrong results)
+#else
+          pv[e] = make_float2(ex2a(xe.x), ex2a(xe.y));
+#endif
+        }
+        ls0 = fadd2(ls0, fadd2(pv[0], pv[1]));
+        ls1 = fadd2(ls1, fadd2(pv[2], pv[3]));
+        v[ch].x = pack_bf16x2(pv[0].x, pv[0].y); v[ch].y = pack_bf16x2(pv[1].x, pv[1].y);
+        v[ch].z = pack_bf16x2(pv[2].x, pv[2].y); v[ch].w = pack_bf16x2(pv[3].x, pv[3].y);
       }
       const int pb = i & 1;
-      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 2] exponentials done
-      mbar_wait(bar(tp::PEMPTY + pb), ((i >> 1) & 1) ^ 1u);        // P buffer free == every earlier P.V is complete
-      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 3] P buffer free
+      if (threadIdx.x == 128) stamp(0, 256);                       // [5 i + 2] exponentials done
+      wait(bar(tp::PEMPTY + pb), ((i >> 1) & 1) ^ 1u);        // P buffer free == every earlier P.V is complete
+      if (threadIdx.x == 128) stamp(0, 256);                       // [5 i + 3] P buffer free
       const float m_old = m_run;
       m_run = m_new;
-      uint8_t* half = gbase + AttnSmem::kP + pb * kPBuf + r * 128;
-      const int ch0 = (wg * kKW) >> 3;
+      uint8_t* half = gbase + pofs + pb * kPBuf;
 #pragma unroll
-      for (int ch = 0; ch < kKW / 8; ++ch) *reinterpret_cast<uint4*>(half + (((ch0 + ch) ^ (r & 7)) << 4)) = v[ch];
+      for (int ch = 0; ch < kKW / 8; ++ch) *reinterpret_cast<uint4*>(half + (((uint32_t)ch << 4) ^ plo)) = v[ch];
       // the bound of some row of this warp moved: rescale the warp's 32 rows of O_wg by the exact power of two (rows
       // whose bound stayed: factor 1).  Done here, after the P tile has left the registers; P.V(i) cannot start before
       // this warp's arrival below.  PEMPTY[pb] covered P.V(i-2); P.V(i-1) writes both accumulators too.
-      const bool resc = grow && i > 0 && m_old > -INFINITY;
+      const bool resc = grow && m_old != kNone;
       if (__any_sync(0xffffffffu, resc)) {
-        mbar_wait(bar(tp::PEMPTY + (pb ^ 1)), ((i - 1) >> 1) & 1);
+        wait(bar(tp::PEMPTY + (pb ^ 1)), ((i - 1) >> 1) & 1);
         tc_fence_after();
         const float f = resc ? ex2a(m_old - m_new) : 1.0f;
 #pragma unroll
@@ -1057,13 +1134,13 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         tc_fence_before();
         l *= f;
       }
-      l += ls0 + ls1;
+      l += (ls0.x + ls0.y) + (ls1.x + ls1.y);
       fence_proxy_async();          // P visible to the tensor core (generic -> async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(tp::PFULL + pb));
-      if (threadIdx.x == 96) stamp(0, 256);                       // [5 i + 4] P handed over
+      if (threadIdx.x == 128) stamp(0, 256);                       // [5 i + 4] P handed over
     }
-    if (threadIdx.x == 96) stamp(0, 256);
+    if (threadIdx.x == 128) stamp(0, 256);
 
     // ---- output: merge the two accumulators
     smax[wg * kQT + r] = m_run;
@@ -1071,11 +1148,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     row_barrier<32 * kWG>(quad);
     const float ma = smax[r], mb = smax[kQT + r];
     const float mm = fmaxf(ma, mb);                                          // finite: key 0 of the clip is always valid
-    const float fa = ex2a(ma - mm), fb = ex2a(mb - mm);                      // 2^(-inf) = 0 for a half that never saw a key
+    const float fa = ex2a(ma - mm), fb = ex2a(mb - mm);                      // 2^(kNone - mm) = 0 for a half that never saw a key
     const float inv = 1.0f / (ssum[r] * fa + ssum[kQT + r] * fb);
     const float ga = fa * inv, gb = fb * inv;
-    mbar_wait(bar(tp::OFULL), 0);
-    if (threadIdx.x == 96) stamp(0, 256);
+    wait(bar(tp::OFULL), 0);
+    if (threadIdx.x == 128) stamp(0, 256);
     tc_fence_after();
     __nv_bfloat16* dst = out + (size_t)(r0 + qpos) * H + head * kHD + wg * 32;
 #pragma unroll
@@ -1103,6 +1180,428 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+#ifdef B2T_ATTN_TIMELINE
+  if (cta_log && threadIdx.x == 0) cta_log[2] = clock64();
+#endif
+}
+
+// =====================================================================================================================
+// attention_tc4_kernel (attn_two_pass = 3, default): the single-pass kernel above made PERSISTENT.
+//
+// Measured on attention_tc3_kernel (per-CTA clock log, tools/attn_timeline3.py): a CTA costs 1770 clocks per 64-key tile
+// plus 12 000 clocks that do not depend on the clip length — launch gap (1850), barrier / TMEM set-up, the E and Q loads,
+// R = Q.E^T and its conversion, pipeline fill, the drain of the last P.V, the output.  For a 10 s clip (8 key tiles) that
+// fixed part is 46 % of the CTA.  Here 2 x #SM CTAs stay resident and walk over the (query tile, head) work items
+// (item = blockIdx.x + k gridDim.x, head-major, heaviest clips first), and every role runs ahead across item boundaries:
+//   * the TMA warp keeps three independent streams — next Q (as soon as the last S MMA of the current item has
+//     retired), K ring, V ring — with running slot counters;
+//   * R = Q.E^T is no longer a set-up phase with its own TMEM columns: it is issued as two PSEUDO TILES of the S ring
+//     (N = 64 and N = 16 MMAs against E, which now stays in shared memory), so the S issuer computes the next item's R
+//     while the softmax warps finish the current item;
+//   * the softmax warps convert those pseudo tiles into the bf16 R rows between their last P hand-off and the wait for
+//     the last P.V of the item — the drain latency of one item hides the set-up of the next;
+//   * no extra barrier protects O: the first P hand-off of the next item is issued by every softmax warp after its
+//     tcgen05.ld of O has completed.
+// Barriers and TMEM are set up once per CTA.  Shared memory: Q 16 K, K/V ring 32 K, P 2 x 16 K, E 10 K, R 128 x 74 bf16.
+// =====================================================================================================================
+namespace t4 {
+enum { EFULL = 0, QFULL, QEMPTY, OFULL, KVFULL, KVEMPTY = KVFULL + 4, SFULL = KVEMPTY + 4, SEMPTY = SFULL + 2,
+       PFULL = SEMPTY + 2, PEMPTY = PFULL + 2, COUNT = PEMPTY + 2 };
+constexpr int kRS = 74;                                       // R row stride (bf16): 37 words, odd -> conflict-free rows
+constexpr int kQ = 0;                                         // 16 KB
+constexpr int kKV = kQ + kQT * 128;                           // 4 slots x 8 KB: K in slots 0/1, V in slots 2/3
+constexpr int kP = kKV + 4 * kKT * 128;                       // 2 P buffers
+constexpr int kE = kP + 2 * kPBuf;                            // 80 x 128 B, resident
+constexpr int kR = kE + 80 * 128;
+constexpr int kML = kR + kQT * kRS * 2;                       // bound / row-sum exchange [2][kWG][128] fp32
+constexpr int kBars = kML + 2 * 2 * kQT * 4;
+constexpr int kTotal = kBars + 256 + 1024;
+constexpr int kSlotBytes = kKT * 128;
+static_assert(COUNT * 8 + 8 <= 256, "barrier area");
+static_assert(kE % 1024 == 0 && kP % 1024 == 0 && kKV % 1024 == 0, "swizzled tiles are 1024-byte aligned");
+static_assert(2 * (kTotal + 1024) <= 228 * 1024, "two CTAs per SM");
+struct Item { int r0, q0, rows, nkeys, nkt, head; };
+}  // namespace t4
+
+B2T_DEVICE t4::Item t4_item(int it, int n_qtiles, const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
+                            const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0) {
+  t4::Item w;
+  const int x = it % n_qtiles;
+  w.head = it / n_qtiles;
+  const int clip = qtile_clip[x];
+  w.q0 = qtile_q0[x];
+  w.r0 = row_off[clip];
+  w.rows = row_off[clip + 1] - w.r0;
+  w.nkeys = valid_rows[clip];
+  w.nkt = (w.nkeys + kKT - 1) / kKT;
+  return w;
+}
+
+__global__ void __launch_bounds__(kThreadsAttn3, kCtasPerSm)
+attention_tc4_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ CUtensorMap map_e,
+                     const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
+                     const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
+                     __nv_bfloat16* __restrict__ out, int H, int n_qtiles, int n_items, unsigned* __restrict__ trap_rec) {
+  static_assert(kKT == 64 && kSoftmaxWarps == 8 && kTmemCols == 256, "single-pass kernel: 64-key tiles, 2 x 4 softmax warps");
+  constexpr uint32_t kTrapSite = 0x400u;           // trap record: 0x400 | warp (mbarrier wait: a = barrier index, b = parity), 0x480 = TMA polling loop
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base + t4::kQ, sKV = base + t4::kKV, sP = base + t4::kP, sE = base + t4::kE;
+  __nv_bfloat16* sR = reinterpret_cast<__nv_bfloat16*>(gbase + t4::kR);
+  const uint32_t bars = base + t4::kBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  auto wait = [&](uint32_t b_, uint32_t parity_) { mbar_wait_rec(b_, parity_, trap_rec, kTrapSite | (threadIdx.x >> 5), bars); };
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + t4::kBars + 8 * t4::COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(t4::EFULL), 1); mbar_init(bar(t4::QFULL), 1); mbar_init(bar(t4::QEMPTY), 1); mbar_init(bar(t4::OFULL), 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(bar(t4::KVFULL + s), 1); mbar_init(bar(t4::KVEMPTY + s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(t4::SFULL + b), 1); mbar_init(bar(t4::SEMPTY + b), kSoftmaxWarps);
+      mbar_init(bar(t4::PFULL + b), kSoftmaxWarps); mbar_init(bar(t4::PEMPTY + b), 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_e); }
+  if (warp == 1) tmem_alloc(bars + 8u * t4::COUNT, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT;       // S ring [0,128); accumulators O_0 [128,192), O_1 [192,256)
+
+  if (warp == 0) {
+    reg_dec<kRegsIssue>();
+    // ===== TMA producer: three independent streams (next Q, K ring, V ring), non-blocking probes =====
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(bar(t4::EFULL), 80 * 128);
+      tma_load_2d(sE, &map_e, bar(t4::EFULL), 0, 0);
+    }
+    int itq = blockIdx.x, itk = blockIdx.x, itv = blockIdx.x;
+    uint32_t qn = 0, kg = 0, vg = 0;                              // running counts: Q loads, K tiles, V tiles
+    int kn = 0, vn = 0;                                           // tile inside the K / V stream's current item
+    t4::Item wk, wv;
+    if (itk < n_items) { wk = t4_item(itk, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0); wv = wk; }
+    uint32_t spins = 0;
+    while (itq < n_items || itk < n_items || itv < n_items) {
+      bool progress = false;
+      if (itq < n_items) {
+        const bool ok = mbar_test_wait(bar(t4::QEMPTY), (qn & 1u) ^ 1u);          // the previous item's last S MMA has retired
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          const t4::Item w = t4_item(itq, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+          if (leader) {
+            mbar_expect_tx(bar(t4::QFULL), kQT * 128);
+            tma_load_2d(sQ, &map_qkv, bar(t4::QFULL), w.head * kHD, w.r0 + w.q0);
+          }
+          ++qn; itq += G; progress = true;
+        }
+      }
+      if (itk < n_items) {
+        const uint32_t st = kg & 1u;
+        const bool ok = mbar_test_wait(bar(t4::KVEMPTY) + 8u * st, ((kg >> 1) & 1u) ^ 1u);
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(t4::KVFULL) + 8u * st, t4::kSlotBytes);
+            tma_load_2d(sKV + st * t4::kSlotBytes, &map_kv, bar(t4::KVFULL) + 8u * st, H + wk.head * kHD, wk.r0 + kn * kKT);
+          }
+          ++kg; progress = true;
+          if (++kn == wk.nkt) {
+            kn = 0; itk += G;
+            if (itk < n_items) wk = t4_item(itk, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+          }
+        }
+      }
+      if (itv < n_items) {
+        const uint32_t st = 2u + (vg & 1u);
+        const bool ok = mbar_test_wait(bar(t4::KVEMPTY) + 8u * st, ((vg >> 1) & 1u) ^ 1u);
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(t4::KVFULL) + 8u * st, t4::kSlotBytes);
+            tma_load_2d(sKV + st * t4::kSlotBytes, &map_kv, bar(t4::KVFULL) + 8u * st, 2 * H + wv.head * kHD, wv.r0 + vn * kKT);
+          }
+          ++vg; progress = true;
+          if (++vn == wv.nkt) {
+            vn = 0; itv += G;
+            if (itv < n_items) wv = t4_item(itv, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+          }
+        }
+      }
+      if (progress) spins = 0;
+      else if (B2T_ATTN_POLL_SLEEP > 0 ? (__nanosleep(B2T_ATTN_POLL_SLEEP), ++spins > (1u << 24)) : (++spins > (1u << 28))) b2t_trap_record(trap_rec, kTrapSite | 0x80u, kg, vg);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    reg_dec<kRegsIssue>();
+    // ===== S issuer: per item two pseudo tiles (R = Q.E^T, columns 0..63 and 64..79), then S = Q.K^T per key tile =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T, R[:, 0:64] = Q E[0:64]^T   (both K-major)
+    constexpr uint32_t idesc_r = make_idesc(128, 16);           // R[:, 64:80]
+    const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ), dkv = make_smem_desc(sKV);
+    wait(bar(t4::EFULL), 0);
+    uint32_t sg = 0, kg = 0, n = 0;
+    for (int it = blockIdx.x; it < n_items; it += G, ++n) {
+      const int x = it % n_qtiles;
+      const int nkt = (valid_rows[qtile_clip[x]] + kKT - 1) / kKT;
+      wait(bar(t4::QFULL), n & 1u);
+      for (int ps = 0; ps < 2; ++ps, ++sg) {
+        const uint32_t b = sg & 1u;
+        wait(bar(t4::SEMPTY) + 8u * b, ((sg >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t dep = de + (uint64_t)(ps * (64 * 128 >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tS + b * kKT, dq + (uint64_t)(2 * k), dep + (uint64_t)(2 * k), ps == 0 ? idesc_s : idesc_r, k != 0);
+          umma_commit(bar(t4::SFULL) + 8u * b);
+        }
+      }
+      for (int j = 0; j < nkt; ++j, ++sg, ++kg) {
+        const uint32_t b = sg & 1u, st = kg & 1u;
+        wait(bar(t4::KVFULL) + 8u * st, (kg >> 1) & 1u);          // one wait after the other (see the two-pass kernel)
+        wait(bar(t4::SEMPTY) + 8u * b, ((sg >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t dk = dkv + (uint64_t)(st * (t4::kSlotBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS + b * kKT, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
+          umma_commit(bar(t4::SFULL) + 8u * b);
+          umma_commit(bar(t4::KVEMPTY) + 8u * st);
+          if (j == nkt - 1) umma_commit(bar(t4::QEMPTY));                // Q may be overwritten by the next item's tile
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    reg_dec<kRegsIssue>();
+    // ===== PV issuer: keys 0..31 of every tile accumulate into O_0, keys 32..63 into O_1 =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (V MN-major)
+    const uint64_t dkv = make_smem_desc(sKV), dp0 = make_smem_desc(sP);
+    uint32_t pg = 0;
+    for (int it = blockIdx.x; it < n_items; it += G) {
+      const int x = it % n_qtiles;
+      const int nkt = (valid_rows[qtile_clip[x]] + kKT - 1) / kKT;
+      for (int ip = 0; ip < nkt; ++ip, ++pg) {
+        const uint32_t pb = pg & 1u, st = 2u + (pg & 1u);
+        // PFULL of an item's first tile also says: every softmax warp has finished reading the previous item's O
+        wait(bar(t4::PFULL) + 8u * pb, (pg >> 1) & 1u);
+        wait(bar(t4::KVFULL) + 8u * st, (pg >> 1) & 1u);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t dv = dkv + (uint64_t)(st * (t4::kSlotBytes >> 4)), dp = dp0 + (uint64_t)(pb * (kPBuf >> 4));
+#pragma unroll
+          for (int kk = 0; kk < kKT / 16; ++kk)
+            umma_bf16(tO + (kk >> 1) * kHD, dp + (uint64_t)(2 * kk), dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o,
+                      (ip != 0 || (kk & 1) != 0) ? 1u : 0u);
+          umma_commit(bar(t4::PEMPTY) + 8u * pb);
+          umma_commit(bar(t4::KVEMPTY) + 8u * st);
+          if (ip == nkt - 1) umma_commit(bar(t4::OFULL));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    reg_dec<kRegsIssue>();                          // idle member of warpgroup 0
+  } else {
+    // ===== softmax / output warps: thread = (query row = TMEM lane, 32-key half wg) with its own bound / sum / accumulator =====
+    reg_inc<kRegsSoftmax>();
+    constexpr int kWG = 2, kKW = 32;
+    const int quad = warp & 3;
+    const int wg = (warp - 4) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
+    constexpr float kTau = 8.0f;
+    constexpr float kNone = -1.0e30f;                        // "no key seen yet": finite, so 2^(-inf + 1e30) = 0 without a special case
+    float* sml = reinterpret_cast<float*>(gbase + t4::kML);  // [m | l][wg][row]
+    const __nv_bfloat16* myR = sR + r * t4::kRS;
+    const uint32_t pofs = (uint32_t)(t4::kP + r * 128 + ((((wg * kKW) >> 3) ^ (r & 4)) << 4));
+    const uint32_t plo = (uint32_t)(r & 3) << 4;
+    uint32_t sg = 0, pg = 0, n = 0;
+
+    // the two pseudo tiles of an item -> this thread's part of the bf16 R row (the reference's einsum output dtype)
+    auto take_r = [&]() {
+      uint32_t* rr = reinterpret_cast<uint32_t*>(sR + r * t4::kRS);
+      {
+        const uint32_t b = sg & 1u;
+        wait(bar(t4::SFULL) + 8u * b, (sg >> 1) & 1u);
+        tc_fence_after();
+        uint32_t a[32];
+        tmem_ld_32x32_nowait(tS + lane_base + b * kKT + wg * 32, a);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(t4::SEMPTY) + 8u * b);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) rr[(wg * 32 + i) >> 1] = pack_bf16x2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+        ++sg;
+      }
+      {
+        const uint32_t b = sg & 1u;
+        wait(bar(t4::SFULL) + 8u * b, (sg >> 1) & 1u);
+        tc_fence_after();
+        if (wg == kWG - 1) {
+          uint32_t c[16];
+          tmem_ld_32x32_x16_nowait(tS + lane_base + b * kKT, c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 10; i += 2) rr[(64 + i) >> 1] = pack_bf16x2(__uint_as_float(c[i]), __uint_as_float(c[i + 1]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(t4::SEMPTY) + 8u * b);
+        ++sg;
+      }
+    };
+
+    int it = blockIdx.x;
+    t4::Item w;
+    if (it < n_items) {
+      w = t4_item(it, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+      take_r();
+      row_barrier<32 * kWG>(quad);
+    }
+    while (it < n_items) {
+      const int qpos = w.q0 + r, nkeys = w.nkeys;
+      const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
+      float m_run = kNone, l = 0.f;
+      for (int i = 0; i < w.nkt; ++i, ++sg, ++pg) {
+        const uint32_t b = sg & 1u;
+        const int k0 = i * kKT + wg * kKW;
+        wait(bar(t4::SFULL) + 8u * b, (sg >> 1) & 1u);
+        tc_fence_after();
+        float t[kKW];
+        {
+          uint32_t x[32];
+          tmem_ld_32x32_nowait(tS + lane_base + b * kKT + wg * kKW, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(x[e]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(t4::SEMPTY) + 8u * b);       // S slice in registers: hand the buffer back at once
+        const int dlo = k0 - qpos, dhi = k0 + kKW - 1 - qpos;
+        const bool band = !(dhi <= -kLeft || dlo >= kRight);        // outside the diagonal band the bias is one constant per row
+        const float cb = dhi <= -kLeft ? rl : rrt;
+        if (band) {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) t[e] += __bfloat162float(myR[max(-kLeft, min(kRight, dlo + e)) + kLeft]);
+        }
+        if (k0 + kKW > nkeys) {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
+        }
+        float m0 = fmaxf(t[0], t[1]), m1 = fmaxf(t[2], t[3]);
+#pragma unroll
+        for (int e = 4; e < kKW; e += 4) { m0 = fmaxf(m0, fmaxf(t[e], t[e + 1])); m1 = fmaxf(m1, fmaxf(t[e + 2], t[e + 3])); }
+        const float mt = fmaxf(m0, m1);
+        const float mts = band ? mt * kScale : fmaf(mt, kScale, cb);           // largest biased score of the slice, log2 domain
+        const bool grow = mts > m_run + kTau;                                   // false for a fully masked slice (mts = -inf)
+        const float m_new = grow ? ceilf(mts) : m_run;
+        const float off = (band ? 0.f : cb) - m_new;                            // p = 2^(raw * kScale + off)
+        const float2 sc2 = make_float2(kScale, kScale), off2 = make_float2(off, off);
+        float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0;
+        uint4 v[kKW / 8];
+#pragma unroll
+        for (int ch = 0; ch < kKW / 8; ++ch) {
+          float2 pv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 xe = ffma2(make_float2(t[ch * 8 + 2 * e], t[ch * 8 + 2 * e + 1]), sc2, off2);
+            pv[e] = make_float2(ex2a(xe.x), ex2a(xe.y));
+          }
+          ls0 = fadd2(ls0, fadd2(pv[0], pv[1]));
+          ls1 = fadd2(ls1, fadd2(pv[2], pv[3]));
+          v[ch].x = pack_bf16x2(pv[0].x, pv[0].y); v[ch].y = pack_bf16x2(pv[1].x, pv[1].y);
+          v[ch].z = pack_bf16x2(pv[2].x, pv[2].y); v[ch].w = pack_bf16x2(pv[3].x, pv[3].y);
+        }
+        const uint32_t pb = pg & 1u;
+        wait(bar(t4::PEMPTY) + 8u * pb, ((pg >> 1) & 1u) ^ 1u);   // P buffer free == P.V two tiles back (and all before) complete
+        const float m_old = m_run;
+        m_run = m_new;
+        uint8_t* half = gbase + pofs + pb * kPBuf;
+#pragma unroll
+        for (int ch = 0; ch < kKW / 8; ++ch) *reinterpret_cast<uint4*>(half + (((uint32_t)ch << 4) ^ plo)) = v[ch];
+        // the bound of some row of this warp moved: rescale the warp's 32 rows of O_wg by the exact power of two (rows
+        // whose bound stayed: factor 1).  P.V(i) cannot start before this warp's arrival below; P.V(i-1) must have retired.
+        const bool resc = grow && m_old != kNone;                    // never on the first tile of an item
+        if (__any_sync(0xffffffffu, resc)) {
+          wait(bar(t4::PEMPTY) + 8u * (pb ^ 1u), ((pg - 1) >> 1) & 1u);
+          tc_fence_after();
+          const float f = resc ? ex2a(m_old - m_new) : 1.0f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o[32];
+            tmem_ld_32x32_nowait(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tmem_st_32x32(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          l *= f;
+        }
+        l += (ls0.x + ls0.y) + (ls1.x + ls1.y);
+        fence_proxy_async();          // P visible to the tensor core (generic -> async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(t4::PFULL) + 8u * pb);
+      }
+
+      // ---- item end.  Publish (bound, sum); once both warps of the row quad are past their last R read, turn the NEXT
+      //      item's pseudo tiles into R rows (this is what the drain of the last P.V hides); then merge and store O.
+      sml[wg * kQT + r] = m_run;
+      sml[2 * kQT + wg * kQT + r] = l;
+      const int it_next = it + G;
+      const t4::Item cur = w;
+      if (it_next < n_items) w = t4_item(it_next, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+      row_barrier<32 * kWG>(quad);
+      const float ma = sml[r], mb = sml[kQT + r];
+      const float la = sml[2 * kQT + r], lb = sml[3 * kQT + r];
+      if (it_next < n_items) take_r();
+      const float mm = fmaxf(ma, mb);                                          // > kNone: key 0 of the clip is always valid
+      const float fa = ex2a(ma - mm), fb = ex2a(mb - mm);                      // 2^(kNone - mm) = 0 for a half that never saw a key
+      const float inv = 1.0f / (la * fa + lb * fb);
+      const float ga = fa * inv, gb = fb * inv;
+      wait(bar(t4::OFULL), n & 1u);
+      tc_fence_after();
+      __nv_bfloat16* dst = out + (size_t)(cur.r0 + qpos) * H + cur.head * kHD + wg * 32;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t xa[16], xb[16];
+        tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(wg * 32 + 16 * ch), xa);
+        tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(kHD + wg * 32 + 16 * ch), xb);
+        tmem_ld_wait();
+        uint32_t wv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          wv[e] = pack_bf16x2(fmaf(__uint_as_float(xb[2 * e]), gb, __uint_as_float(xa[2 * e]) * ga),
+                              fmaf(__uint_as_float(xb[2 * e + 1]), gb, __uint_as_float(xa[2 * e + 1]) * ga));
+        if (qpos < cur.rows)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"l"(dst + 16 * ch), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]), "r"(wv[4]), "r"(wv[5]), "r"(wv[6]), "r"(wv[7])
+                       : "memory");
+      }
+      tc_fence_before();               // the O reads are complete before this warp's next P hand-off lets P.V overwrite O
+      row_barrier<32 * kWG>(quad);     // the next item's R rows are complete; the (bound, sum) slots may be rewritten
+      it = it_next; ++n;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 #endif  // !B2T_ATTN_WIDE
 
@@ -1111,6 +1610,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 int g_attn_heads_per_cta = 1;   // kept for the option plumbing; the kernel needs 1 (E and R borrow per-head buffers)
 long long* g_attn_dbg = nullptr;   // b2t_attention_set_dbg(device buffer of 128 int64): developer timeline
 extern "C" void b2t_attention_set_dbg(long long* p) { g_attn_dbg = p; }
+int g_attn_ctas = 0;            // b2t_set_option("attn_ctas", n): cap the persistent kernel's grid (tests: many items per CTA)
 int g_attn_two_pass = 1;        // b2t_set_option("attn_two_pass", 0/1): fixed-maximum two-pass kernel vs online softmax
 
 // host entry used by b2t_relkey_attention (attention.cu)
@@ -1135,8 +1635,18 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
     B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc2_kernel<true>);
     if (g_attn_two_pass == 2) {          // single pass, split accumulators
       B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc3_kernel);
-      attention_tc3_kernel<<<grid, kThreadsAttn2, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
-                                                                         b->qtile128_q0, (__nv_bfloat16*)out, H, g_attn_dbg);
+      attention_tc3_kernel<<<grid, kThreadsAttn3, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
+                                                                         b->qtile128_q0, (__nv_bfloat16*)out, H, g_attn_dbg, b2t_trap_rec());
+      B2T_LAUNCH_CHECK();
+      return B2T_OK;
+    }
+    if (g_attn_two_pass == 3) {          // single pass, persistent over (query tile, head) items
+      B2T_SMEM_OPT_IN(t4::kTotal, attention_tc4_kernel);
+      const int n_items = b->n_qtiles128 * heads;
+      int ctas = std::min(n_items, kCtasPerSm * b2t_num_sms());
+      if (g_attn_ctas > 0) ctas = std::min(ctas, g_attn_ctas);
+      attention_tc4_kernel<<<ctas, kThreadsAttn3, t4::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
+                                                                   b->qtile128_q0, (__nv_bfloat16*)out, H, b->n_qtiles128, n_items, b2t_trap_rec());
       B2T_LAUNCH_CHECK();
       return B2T_OK;
     }

@@ -57,6 +57,7 @@ int b2t_debug_sync_check(const char* file, int line);
 void b2t_set_debug_sync(int on);
 
 int b2t_num_sms();          // of the current device
+unsigned* b2t_trap_rec();   // mapped host record for b2t_trap_record (same pointer on host and device), or null
 int b2t_device_index();     // current device, clamped to [0, B2T_MAX_DEVICES)
 constexpr int B2T_MAX_DEVICES = 64;
 int b2t_arch_ok();   // B2T_OK or B2T_ERR_ARCH for the current device
@@ -70,6 +71,21 @@ __device__ __noinline__ inline void b2t_trap_report(const char* what, unsigned a
   printf("b200tok device trap: %s a=0x%x b=%u block=(%d,%d,%d) thread=%d\n", what, a, b, (int)blockIdx.x, (int)blockIdx.y,
          (int)blockIdx.z, (int)threadIdx.x);
   __assert_fail(what, __FILE__, __LINE__, "b2t_trap_report");
+}
+
+// The same for register-critical code (the single-pass attention kernels re-partition registers with setmaxnreg; an
+// ABI call such as the printf above makes ptxas spill the whole region around it): the site is recorded with plain
+// stores into a 32-byte record in MAPPED HOST memory (b2t_trap_rec(), passed as a kernel argument), which survives the
+// trap; the host reads it back through b2t_last_device_trap.  rec = {code, a, b, blockIdx.x, blockIdx.y, threadIdx.x}.
+B2T_DEVICE void b2t_trap_record(unsigned* rec, unsigned code, unsigned a, unsigned b) {
+  if (rec != nullptr) {
+    volatile unsigned* r = rec;
+    r[1] = a; r[2] = b; r[3] = blockIdx.x; r[4] = blockIdx.y; r[5] = threadIdx.x;
+    __threadfence_system();
+    r[0] = code;
+    __threadfence_system();
+  }
+  __trap();
 }
 
 B2T_DEVICE float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

@@ -455,9 +455,10 @@ int b2t_vq_scan_tensor(const void* A2, const void* C2, int M, int K, int Kpad, i
   return B2T_OK;
 }
 
-int b2t_test_trap();               // api.cu
+int b2t_test_trap(int light);      // api.cu
 extern int g_attn_heads_per_cta;   // attention_tc.cu
 extern int g_attn_two_pass;
+extern int g_attn_ctas;
 extern bool g_rvq_tensor;          // acoustic.cu
 extern int g_rvq_dbg;              // rvq_tc.cu
 void b2t_seanet_set_sub_frames(int n);   // seanet_tc.cu
@@ -469,7 +470,7 @@ extern bool g_dwconv_ring;         // dwconv.cu
 extern "C" int b2t_set_option(const char* name, int value) {
   B2T_REQUIRE(name, B2T_ERR_ARG, "b2t_set_option: null name");
   if (std::string(name) == "gemm_multicast") { g_multicast = value != 0; return B2T_OK; }
-  if (std::string(name) == "test_trap") { return value ? b2t_test_trap() : B2T_OK; }
+  if (std::string(name) == "test_trap") { return value ? b2t_test_trap(value == 2) : B2T_OK; }   // 2: through the mapped host record
   if (std::string(name) == "debug_sync") { b2t_set_debug_sync(value); return B2T_OK; }
   if (std::string(name) == "dwconv_ring") { g_dwconv_ring = value != 0; return B2T_OK; }
   if (std::string(name) == "seanet_l0_fused") { b2t_seanet_set_l0_fused(value); return B2T_OK; }
@@ -479,6 +480,7 @@ extern "C" int b2t_set_option(const char* name, int value) {
   if (std::string(name) == "rvq_dbg") { g_rvq_dbg = value; return B2T_OK; }
   if (std::string(name) == "rvq_tensor") { g_rvq_tensor = value != 0; return B2T_OK; }
   if (std::string(name) == "attn_two_pass") { g_attn_two_pass = value; return B2T_OK; }
+  if (std::string(name) == "attn_ctas") { g_attn_ctas = value; return B2T_OK; }
   if (std::string(name) == "attn_heads_per_cta") {
     B2T_REQUIRE(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, B2T_ERR_ARG, "attn_heads_per_cta must divide 16");
     g_attn_heads_per_cta = value;

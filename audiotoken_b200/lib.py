@@ -29,7 +29,7 @@ EXPORTS = [
     'b2t_acoustic_encode', 'b2t_rvq_encode', 'b2t_acoustic_profile_read', 'b2t_ingest_resample',
     'b2t_acoustic_decode_workspace_bytes', 'b2t_acoustic_decode', 'b2t_vq_ema_workspace_bytes', 'b2t_vq_ema_update',
     'b2t_hubert_create', 'b2t_hubert_destroy', 'b2t_hubert_set_tensor', 'b2t_hubert_workspace_bytes', 'b2t_hubert_encode',
-    'b2t_debug_stage_sums', 'b2t_debug_stage_count',
+    'b2t_debug_stage_sums', 'b2t_debug_stage_count', 'b2t_last_device_trap',
 ]
 
 
@@ -113,6 +113,8 @@ def load() -> C.CDLL:
     lib.b2t_semantic_workspace_bytes.restype = sz
     lib.b2t_semantic_encode.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(FbankTables), vp, sz, vp, i32, vp, vp]
     lib.b2t_last_launch_count.restype = i32
+    lib.b2t_last_device_trap.argtypes = [C.POINTER(C.c_uint32)]
+    lib.b2t_last_device_trap.restype = i32
     lib.b2t_profile_enable.argtypes = [i32]
     lib.b2t_acoustic_create.restype = vp
     lib.b2t_acoustic_destroy.argtypes = [vp]
@@ -146,6 +148,14 @@ def check(rc: int, what: str = '') -> None:
     if rc != 0:
         msg = load().b2t_last_error().decode('utf-8', 'replace')
         raise B2TError(f'{what} failed (status {rc}): {msg}')
+
+
+def device_trap_text() -> str:
+    """The record a register-critical kernel left in mapped host memory before it trapped (b2t_last_device_trap), or ''."""
+    rec = (C.c_uint32 * 6)()
+    if not load().b2t_last_device_trap(rec):
+        return ''
+    return (f'device trap record: site 0x{rec[0]:x} a={rec[1]} b={rec[2]} block=({rec[3]},{rec[4]}) thread={rec[5]}')
 
 
 def require_device(device: torch.device) -> None:

@@ -264,6 +264,7 @@ class Ctx:
         except Exception as e:  # noqa: BLE001
             sys.stderr.write(f'bench.py: rank {self.rank}: device fault detected after {where}: {e}\n'
                              f'  library says: {L.load().b2t_last_error().decode("utf-8", "replace")}\n'
+                             f'  {L.device_trap_text() or "no device trap record"}\n'
                              '  re-run with B2T_DEBUG_SYNC=1 to name the kernel\n')
             sys.stderr.flush()
             os._exit(13)

@@ -235,7 +235,7 @@ def test_attention_bf16(cuda_device, impl, rows, valid):
     assert rel_err(out.float(), ref) < 1e-2, rel_err(out.float(), ref)
 
 
-@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('mode', [1, 2, 3])
 def test_attention_tensor_large_dynamic_range(cuda_device, mode):
     """Adversarial logits for the fixed-bound (mode 1: two-pass) and lazily rescaled (mode 2: single-pass) tcgen05
     kernels: q, k scaled so that raw scores span hundreds of log2 units, the largest raw score and the largest relative
@@ -266,6 +266,34 @@ def test_attention_tensor_large_dynamic_range(cuda_device, mode):
         L.check(lib.b2t_set_option(b'attn_two_pass', 1), 'attn_two_pass')
     assert torch.isfinite(out.float()).all()
     assert rel_err(out.float(), ref.float()) < 1.5e-2, rel_err(out.float(), ref.float())
+
+
+def test_attention_persistent_items(cuda_device):
+    """The persistent single-pass kernel (attn_two_pass = 3) with its grid capped to 3 and to 7 CTAs: every CTA walks
+    over dozens of (query tile, head) items of different lengths, so R pseudo tiles, ring counters and barrier phases
+    carry across item boundaries.  Checked against the fp64 formula, and bit-for-bit against the one-item-per-CTA
+    single-pass kernel (same arithmetic, same tiles)."""
+    lib = L.load()
+    rows, valid = [300, 64, 130, 1, 257, 50, 128, 200], [290, 40, 130, 1, 257, 33, 128, 190]
+    g = torch.Generator().manual_seed(5)
+    qkv = bf(torch.randn(sum(rows), 3072, generator=g) * 0.9)
+    E = bf(torch.randn(73, 64, generator=g) * 0.5)
+    plan = _attn_plan(rows, valid)
+    ref = _attn_oracle(qkv.double(), E.double(), rows, valid, False)
+    outs = {}
+    try:
+        for mode, ctas in ((2, 0), (3, 0), (3, 3), (3, 7)):
+            L.check(lib.b2t_set_option(b'attn_two_pass', mode), 'attn_two_pass')
+            L.check(lib.b2t_set_option(b'attn_ctas', ctas), 'attn_ctas')
+            outs[(mode, ctas)] = ops.relkey_attention(qkv.to(cuda_device, torch.bfloat16), E.to(cuda_device, torch.bfloat16), plan,
+                                                      'bf16', L.IMPL_TENSOR).float().cpu()
+    finally:
+        L.check(lib.b2t_set_option(b'attn_two_pass', 1), 'attn_two_pass')
+        L.check(lib.b2t_set_option(b'attn_ctas', 0), 'attn_ctas')
+    for k, o in outs.items():
+        assert rel_err(o, ref.float()) < 1e-2, (k, rel_err(o, ref.float()))
+    for k in ((3, 0), (3, 3), (3, 7)):
+        assert torch.equal(outs[k], outs[(2, 0)]), k
 
 
 # ---------------------------------------------------------------------------------- depthwise conv

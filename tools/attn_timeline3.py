@@ -16,7 +16,8 @@ for rows_per_clip, n in ((500, 128), (1500, 48)):
     qkv = (torch.randn(M, 3072, device=dev) * 0.7).to(torch.bfloat16)
     E = torch.randn(73, 64, device=dev).to(torch.bfloat16)
     db = packing.DeviceBatch(plan, dev); out = torch.zeros(M, 1024, device=dev, dtype=torch.bfloat16)
-    dbg = torch.zeros(640, dtype=torch.int64, device=dev)
+    ncta = plan.n_qtiles128 * 16 if hasattr(plan, 'n_qtiles128') else len(plan.qtile128_clip) * 16
+    dbg = torch.zeros(1024 + 3 * ncta, dtype=torch.int64, device=dev)
     for it in range(2):
         lib.b2t_attention_set_dbg(dbg.data_ptr() if it else None)
         L.check(lib.b2t_relkey_attention(qkv.data_ptr(), E.data_ptr(), db.byref(), out.data_ptr(), L.PREC_BF16, L.IMPL_TENSOR, L.stream_ptr()), 'attn')
@@ -37,3 +38,19 @@ for rows_per_clip, n in ((500, 128), (1500, 48)):
     for j in range(min(nkt, 12)): print('   ', pv[3 * j:3 * j + 3].tolist())
     tm = full[512:640]; tm = tm[tm > 0] - t0
     print('TMA K issue times:', tm[:12].tolist())
+
+    log = full[1024:].reshape(-1, 3)
+    log = log[log[:, 1] > 0]
+    busy, gaps, durs = 0, [], []
+    for sm in np.unique(log[:, 0]):
+        c = log[log[:, 0] == sm]; c = c[np.argsort(c[:, 1])]
+        durs += (c[:, 2] - c[:, 1]).tolist()
+        # two CTAs are resident at a time: CTA k starts when CTA k-2 (or earlier) has ended; gap = start - the latest end before it
+        ends = np.sort(c[:, 2])
+        for k in range(2, len(c)):
+            prev = ends[ends <= c[k, 1]]
+            if len(prev): gaps.append(int(c[k, 1] - prev[-1]))
+        span = c[:, 2].max() - c[:, 1].min()
+        busy += (c[:, 2] - c[:, 1]).sum() / (2.0 * span)
+    print(f'CTA log: {len(log)} CTAs on {len(np.unique(log[:, 0]))} SMs; CTA duration median {np.median(durs):.0f} clocks (p10 {np.percentile(durs, 10):.0f}, p90 {np.percentile(durs, 90):.0f}); '
+          f'gap from a slot freeing to the next CTA start: median {np.median(gaps):.0f}, p90 {np.percentile(gaps, 90):.0f}; mean slot occupancy {busy / len(np.unique(log[:, 0])):.3f}')

@@ -1,6 +1,7 @@
 #!/bin/bash
+# developer A/B: attention sweep over variant builds of attention_tc.cu (tools/build_variants.py)
 V=audiotoken_b200/lib/variants
-for v in base nomax noresc oneacc all3; do
+for v in ${VARIANTS:-base}; do
   lp=""; [ $v != base ] && lp=$V/libb200tok_$v.so
-  B2T_LIB_PATH=$lp timeout 120 python tools/attn_sweep.py 2>&1 | grep "single-pass:\|two-pass:" | grep "24x1500\|64x500" | sed "s/^/[$v] /"
+  B2T_LIB_PATH=$lp timeout 120 python tools/attn_sweep.py 2>&1 | grep "single-pass\|persistent" | grep -v " vs " | sed "s/^/[$v] /"
 done
