@@ -1603,6 +1603,349 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
+
+// =====================================================================================================================
+// attention_tc5_kernel (attn_two_pass = 4): the single-pass kernel with P IN TENSOR MEMORY.
+//
+// ncu on attention_tc3_kernel: the softmax warps wait for a free P buffer on 45 % of the tiles — the two-slot V ring can
+// only request V(i) once P.V(i-2) has retired, which leaves one tile period for a TMA round trip — and a tile moves
+// 80 KB through shared memory (operand reads 48 KB, P write 16 KB, TMA 16 KB).  Here the bf16 P tile never touches
+// shared memory: a softmax thread writes its 32 probabilities as 16 packed words with tcgen05.st INTO THE S BUFFER it
+// has just read (its own 32 columns: no other thread's unread scores are touched) and P.V is issued with the A operand
+// in tensor memory (tcgen05.mma [d], [a_tmem], b_desc: keys 0..31 at columns 0..15, keys 32..63 at columns 32..47 of
+// the buffer; one k16 MMA reads 8 columns).  The S buffer is handed back by the COMMIT of P.V(i) instead of by the
+// softmax warps, so S(i+2) is issued one P.V later than before — still a whole softmax period ahead of its use.
+// The 32 KB of shared memory this frees turn the K and V rings into 4 + 4 slots (requests run three tiles ahead).
+// No generic->async proxy fence, no P-buffer barrier, no 16-byte swizzled stores in the loop.
+// =====================================================================================================================
+namespace t5 {
+enum { EFULL = 0, QFULL, RFULL, OFULL, KFULL, KEMPTY = KFULL + 4, VFULL = KEMPTY + 4, VEMPTY = VFULL + 4, SFULL = VEMPTY + 4,
+       PFULL = SFULL + 2, PVDONE = PFULL + 2, COUNT = PVDONE + 2 };
+constexpr int kRing = 4;
+constexpr int kRS = 74;                                       // R row stride (bf16): 37 words, odd -> conflict-free rows
+constexpr int kQ = 0;                                         // 16 KB
+constexpr int kK = kQ + kQT * 128;                            // 4 slots x 8 KB
+constexpr int kV = kK + kRing * kKT * 128;                    // 4 slots x 8 KB
+constexpr int kE = kV + kRing * kKT * 128;                    // 80 x 128 B
+constexpr int kR = kE + 80 * 128;
+constexpr int kML = kR + kQT * kRS * 2;                       // bound / row-sum exchange [2][kWG][128] fp32
+constexpr int kBars = kML + 2 * 2 * kQT * 4;
+constexpr int kTotal = kBars + 256 + 1024;
+constexpr int kSlotBytes = kKT * 128;
+static_assert(COUNT * 8 + 8 <= 256, "barrier area");
+static_assert(kE % 1024 == 0 && kK % 1024 == 0 && kV % 1024 == 0, "swizzled tiles are 1024-byte aligned");
+static_assert(2 * (kTotal + 1024) <= 228 * 1024, "two CTAs per SM");
+}  // namespace t5
+
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (128 rows = lanes, two bf16 per 32-bit column) is read from tensor memory
+B2T_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+B2T_DEVICE void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsAttn3, kCtasPerSm)
+attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ CUtensorMap map_e,
+                     const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
+                     const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
+                     __nv_bfloat16* __restrict__ out, int H, unsigned* __restrict__ trap_rec) {
+  static_assert(kKT == 64 && kSoftmaxWarps == 8 && kTmemCols == 256, "single-pass kernel: 64-key tiles, 2 x 4 softmax warps");
+  constexpr uint32_t kTrapSite = 0x500u;           // trap record: 0x500 | warp (mbarrier wait: a = barrier index, b = parity), 0x580 = TMA polling loop
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base + t5::kQ, sK = base + t5::kK, sV = base + t5::kV, sE = base + t5::kE;
+  __nv_bfloat16* sR = reinterpret_cast<__nv_bfloat16*>(gbase + t5::kR);
+  const uint32_t bars = base + t5::kBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  auto wait = [&](uint32_t b_, uint32_t parity_) { mbar_wait_rec(b_, parity_, trap_rec, kTrapSite | (threadIdx.x >> 5), bars); };
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + t5::kBars + 8 * t5::COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int clip = qtile_clip[blockIdx.x], q0 = qtile_q0[blockIdx.x];
+  const int r0 = row_off[clip], rows = row_off[clip + 1] - r0, nkeys = valid_rows[clip];
+  const int nkt = (nkeys + kKT - 1) / kKT;
+  const int head = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(t5::EFULL), 1); mbar_init(bar(t5::QFULL), 1); mbar_init(bar(t5::RFULL), 1); mbar_init(bar(t5::OFULL), 1);
+    for (int s = 0; s < t5::kRing; ++s) {
+      mbar_init(bar(t5::KFULL + s), 1); mbar_init(bar(t5::KEMPTY + s), 1);
+      mbar_init(bar(t5::VFULL + s), 1); mbar_init(bar(t5::VEMPTY + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(t5::SFULL + b), 1); mbar_init(bar(t5::PFULL + b), kSoftmaxWarps); mbar_init(bar(t5::PVDONE + b), 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_e); }
+  if (warp == 1) tmem_alloc(bars + 8u * t5::COUNT, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // S / P double buffer [0,128); accumulators O_0 [128,192) and O_1 [192,256); R (80 columns) borrows [128,208) until the first PV
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT, tR = tmem_base + 2 * kKT;
+
+  if (warp == 0) {
+    reg_dec<kRegsIssue>();
+    // ===== TMA producer: E, Q, then the K ring and the V ring as two independent streams (non-blocking probes) =====
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(bar(t5::EFULL), 80 * 128);
+      tma_load_2d(sE, &map_e, bar(t5::EFULL), 0, 0);
+      mbar_expect_tx(bar(t5::QFULL), kQT * 128);
+      tma_load_2d(sQ, &map_qkv, bar(t5::QFULL), head * kHD, r0 + q0);
+    }
+    int kn = 0, vn = 0;
+    uint32_t spins = 0;
+    while (kn < nkt || vn < nkt) {
+      bool progress = false;
+      if (kn < nkt) {
+        const uint32_t st = (uint32_t)kn & 3u;
+        const bool ok = mbar_test_wait(bar(t5::KEMPTY) + 8u * st, (((uint32_t)kn >> 2) & 1u) ^ 1u);
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(t5::KFULL) + 8u * st, t5::kSlotBytes);
+            tma_load_2d(sK + st * t5::kSlotBytes, &map_kv, bar(t5::KFULL) + 8u * st, H + head * kHD, r0 + kn * kKT);
+          }
+          ++kn; progress = true;
+        }
+      }
+      if (vn < nkt) {
+        const uint32_t st = (uint32_t)vn & 3u;
+        const bool ok = mbar_test_wait(bar(t5::VEMPTY) + 8u * st, (((uint32_t)vn >> 2) & 1u) ^ 1u);
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(t5::VFULL) + 8u * st, t5::kSlotBytes);
+            tma_load_2d(sV + st * t5::kSlotBytes, &map_kv, bar(t5::VFULL) + 8u * st, 2 * H + head * kHD, r0 + vn * kKT);
+          }
+          ++vn; progress = true;
+        }
+      }
+      if (progress) spins = 0;
+      else if (++spins > (1u << 28)) b2t_trap_record(trap_rec, kTrapSite | 0x80u, (unsigned)kn, (unsigned)vn);
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    reg_dec<kRegsIssue>();
+    // ===== PV issuer: A = P from tensor memory; keys 0..31 of every tile accumulate into O_0, keys 32..63 into O_1 =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (P K-major in TMEM, V MN-major in shared memory)
+    const uint64_t dv0 = make_smem_desc(sV);
+    for (int ip = 0; ip < nkt; ++ip) {
+      const uint32_t pb = (uint32_t)ip & 1u, st = (uint32_t)ip & 3u;
+      wait(bar(t5::PFULL) + 8u * pb, ((uint32_t)ip >> 1) & 1u);          // one wait after the other (see the two-pass kernel)
+      wait(bar(t5::VFULL) + 8u * st, ((uint32_t)ip >> 2) & 1u);
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dv = dv0 + (uint64_t)(st * (t5::kSlotBytes >> 4));
+#pragma unroll
+        for (int kk = 0; kk < kKT / 16; ++kk)
+          umma_bf16_ts(tO + (kk >> 1) * kHD, tS + pb * kKT + (kk >> 1) * 32 + (kk & 1) * 8, dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o,
+                       (ip != 0 || (kk & 1) != 0) ? 1u : 0u);
+        umma_commit(bar(t5::PVDONE) + 8u * pb);                           // the S / P buffer is free again
+        umma_commit(bar(t5::VEMPTY) + 8u * st);
+        if (ip == nkt - 1) umma_commit(bar(t5::OFULL));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    reg_dec<kRegsIssue>();
+    // ===== S issuer =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T   (both K-major)
+    constexpr uint32_t idesc_r = make_idesc(128, 80);           // R = Q E^T
+    const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ), dk0 = make_smem_desc(sK);
+    wait(bar(t5::EFULL), 0);
+    wait(bar(t5::QFULL), 0);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tR, dq + (uint64_t)(2 * k), de + (uint64_t)(2 * k), idesc_r, k != 0);
+      umma_commit(bar(t5::RFULL));
+    }
+    for (int j = 0; j < nkt; ++j) {
+      const uint32_t b = (uint32_t)j & 1u, st = (uint32_t)j & 3u;
+      wait(bar(t5::KFULL) + 8u * st, ((uint32_t)j >> 2) & 1u);
+      wait(bar(t5::PVDONE) + 8u * b, (((uint32_t)j >> 1) & 1u) ^ 1u);    // P.V(j-2) has consumed the P tile that lives in this buffer
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dk = dk0 + (uint64_t)(st * (t5::kSlotBytes >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS + b * kKT, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
+        umma_commit(bar(t5::SFULL) + 8u * b);
+        umma_commit(bar(t5::KEMPTY) + 8u * st);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    reg_dec<kRegsIssue>();                          // idle member of warpgroup 0
+  } else {
+    // ===== softmax / output warps: thread = (query row = TMEM lane, 32-key half wg) with its own bound / sum / accumulator =====
+    reg_inc<kRegsSoftmax>();
+    constexpr int kWG = 2, kKW = 32;
+    const int quad = warp & 3;
+    const int wg = (warp - 4) >> 2;
+    const int r = quad * 32 + lane;
+    const int qpos = q0 + r;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
+    constexpr float kTau = 8.0f;
+    constexpr float kNone = -1.0e30f;                        // "no key seen yet": finite, so 2^(-inf + 1e30) = 0 without a special case
+    float* sml = reinterpret_cast<float*>(gbase + t5::kML);  // [m | l][wg][row]
+    const __nv_bfloat16* myR = sR + r * t5::kRS;
+
+    // R row -> bf16 (the reference's einsum output dtype) -> shared memory; the two warps of a row split the columns
+    wait(bar(t5::RFULL), 0);
+    tc_fence_after();
+    {
+      uint32_t* rr = reinterpret_cast<uint32_t*>(sR + r * t5::kRS);
+      uint32_t a[32];
+      tmem_ld_32x32_nowait(tR + lane_base + wg * 32, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) rr[(wg * 32 + i) >> 1] = pack_bf16x2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+      if (wg == kWG - 1) {
+        uint32_t c[16];
+        tmem_ld_32x32_x16_nowait(tR + lane_base + 64, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 10; i += 2) rr[(64 + i) >> 1] = pack_bf16x2(__uint_as_float(c[i]), __uint_as_float(c[i + 1]));
+      }
+    }
+    tc_fence_before();
+    row_barrier<32 * kWG>(quad);                    // every R row is complete (and no R read is outstanding: O may be written)
+    const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
+
+    float m_run = kNone, l = 0.f;
+    const uint32_t tSP = tS + lane_base + (uint32_t)(wg * kKW);          // this thread's S slice; its P words go to the first 16 columns of it
+    for (int i = 0; i < nkt; ++i) {
+      const uint32_t b = (uint32_t)i & 1u;
+      const int k0 = i * kKT + wg * kKW;
+      wait(bar(t5::SFULL) + 8u * b, ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      float t[kKW];
+      {
+        uint32_t x[32];
+        tmem_ld_32x32_nowait(tSP + b * kKT, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(x[e]);
+      }
+      const int dlo = k0 - qpos, dhi = k0 + kKW - 1 - qpos;
+      const bool band = !(dhi <= -kLeft || dlo >= kRight);        // outside the diagonal band the bias is one constant per row
+      const float cb = dhi <= -kLeft ? rl : rrt;
+      if (band) {
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) t[e] += __bfloat162float(myR[max(-kLeft, min(kRight, dlo + e)) + kLeft]);
+      }
+      if (k0 + kKW > nkeys) {
+#pragma unroll
+        for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
+      }
+      float m0 = fmaxf(t[0], t[1]), m1 = fmaxf(t[2], t[3]);
+#pragma unroll
+      for (int e = 4; e < kKW; e += 4) { m0 = fmaxf(m0, fmaxf(t[e], t[e + 1])); m1 = fmaxf(m1, fmaxf(t[e + 2], t[e + 3])); }
+      const float mt = fmaxf(m0, m1);
+      const float mts = band ? mt * kScale : fmaf(mt, kScale, cb);           // largest biased score of the slice, log2 domain
+      const bool grow = mts > m_run + kTau;                                   // false for a fully masked slice (mts = -inf)
+      const float m_new = grow ? ceilf(mts) : m_run;
+      const float off = (band ? 0.f : cb) - m_new;                            // p = 2^(raw * kScale + off)
+      const float2 sc2 = make_float2(kScale, kScale), off2 = make_float2(off, off);
+      float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0;
+      uint32_t v[kKW / 2];
+#pragma unroll
+      for (int ch = 0; ch < kKW / 8; ++ch) {
+        float2 pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 xe = ffma2(make_float2(t[ch * 8 + 2 * e], t[ch * 8 + 2 * e + 1]), sc2, off2);
+          pv[e] = make_float2(ex2a(xe.x), ex2a(xe.y));
+        }
+        ls0 = fadd2(ls0, fadd2(pv[0], pv[1]));
+        ls1 = fadd2(ls1, fadd2(pv[2], pv[3]));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[ch * 4 + e] = pack_bf16x2(pv[e].x, pv[e].y);
+      }
+      tmem_st_32x32_x16(tSP + b * kKT, v);                          // P over the (already read) first half of this thread's S slice
+      const float m_old = m_run;
+      m_run = m_new;
+      // the bound of some row of this warp moved: rescale the warp's 32 rows of O_wg by the exact power of two (rows
+      // whose bound stayed: factor 1).  P.V(i) cannot start before this warp's arrival below; P.V(i-1) must have retired
+      // (S(i) being complete only says that P.V(i-2) has).
+      const bool resc = grow && m_old != kNone;                     // never on the first tile
+      if (__any_sync(0xffffffffu, resc)) {
+        wait(bar(t5::PVDONE) + 8u * (b ^ 1u), ((uint32_t)(i - 1) >> 1) & 1u);
+        tc_fence_after();
+        const float f = resc ? ex2a(m_old - m_new) : 1.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t o[32];
+          tmem_ld_32x32_nowait(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+          tmem_st_32x32(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+        }
+        l *= f;
+      }
+      l += (ls0.x + ls0.y) + (ls1.x + ls1.y);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(t5::PFULL) + 8u * b);
+    }
+
+    // ---- output: merge the two accumulators
+    sml[wg * kQT + r] = m_run;
+    sml[2 * kQT + wg * kQT + r] = l;
+    row_barrier<32 * kWG>(quad);
+    const float ma = sml[r], mb = sml[kQT + r];
+    const float mm = fmaxf(ma, mb);                                          // > kNone: key 0 of the clip is always valid
+    const float fa = ex2a(ma - mm), fb = ex2a(mb - mm);                      // 2^(kNone - mm) = 0 for a half that never saw a key
+    const float inv = 1.0f / (sml[2 * kQT + r] * fa + sml[3 * kQT + r] * fb);
+    const float ga = fa * inv, gb = fb * inv;
+    wait(bar(t5::OFULL), 0);
+    tc_fence_after();
+    __nv_bfloat16* dst = out + (size_t)(r0 + qpos) * H + head * kHD + wg * 32;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t xa[16], xb[16];
+      tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(wg * 32 + 16 * ch), xa);
+      tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(kHD + wg * 32 + 16 * ch), xb);
+      tmem_ld_wait();
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        w[e] = pack_bf16x2(fmaf(__uint_as_float(xb[2 * e]), gb, __uint_as_float(xa[2 * e]) * ga),
+                           fmaf(__uint_as_float(xb[2 * e + 1]), gb, __uint_as_float(xa[2 * e + 1]) * ga));
+      if (qpos < rows)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"l"(dst + 16 * ch), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
 #endif  // !B2T_ATTN_WIDE
 
 }  // namespace
@@ -1637,6 +1980,13 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
       B2T_SMEM_OPT_IN(AttnSmem::kTotal, attention_tc3_kernel);
       attention_tc3_kernel<<<grid, kThreadsAttn3, AttnSmem::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
                                                                          b->qtile128_q0, (__nv_bfloat16*)out, H, g_attn_dbg, b2t_trap_rec());
+      B2T_LAUNCH_CHECK();
+      return B2T_OK;
+    }
+    if (g_attn_two_pass == 4) {          // single pass, P in tensor memory
+      B2T_SMEM_OPT_IN(t5::kTotal, attention_tc5_kernel);
+      attention_tc5_kernel<<<grid, kThreadsAttn3, t5::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
+                                                                   b->qtile128_q0, (__nv_bfloat16*)out, H, b2t_trap_rec());
       B2T_LAUNCH_CHECK();
       return B2T_OK;
     }

@@ -235,7 +235,7 @@ def test_attention_bf16(cuda_device, impl, rows, valid):
     assert rel_err(out.float(), ref) < 1e-2, rel_err(out.float(), ref)
 
 
-@pytest.mark.parametrize('mode', [1, 2, 3])
+@pytest.mark.parametrize('mode', [1, 2, 3, 4])
 def test_attention_tensor_large_dynamic_range(cuda_device, mode):
     """Adversarial logits for the fixed-bound (mode 1: two-pass) and lazily rescaled (mode 2: single-pass) tcgen05
     kernels: q, k scaled so that raw scores span hundreds of log2 units, the largest raw score and the largest relative
@@ -282,7 +282,7 @@ def test_attention_persistent_items(cuda_device):
     ref = _attn_oracle(qkv.double(), E.double(), rows, valid, False)
     outs = {}
     try:
-        for mode, ctas in ((2, 0), (3, 0), (3, 3), (3, 7)):
+        for mode, ctas in ((2, 0), (4, 0), (3, 0), (3, 3), (3, 7)):
             L.check(lib.b2t_set_option(b'attn_two_pass', mode), 'attn_two_pass')
             L.check(lib.b2t_set_option(b'attn_ctas', ctas), 'attn_ctas')
             outs[(mode, ctas)] = ops.relkey_attention(qkv.to(cuda_device, torch.bfloat16), E.to(cuda_device, torch.bfloat16), plan,
@@ -292,7 +292,7 @@ def test_attention_persistent_items(cuda_device):
         L.check(lib.b2t_set_option(b'attn_ctas', 0), 'attn_ctas')
     for k, o in outs.items():
         assert rel_err(o, ref.float()) < 1e-2, (k, rel_err(o, ref.float()))
-    for k in ((3, 0), (3, 3), (3, 7)):
+    for k in ((4, 0), (3, 0), (3, 3), (3, 7)):
         assert torch.equal(outs[k], outs[(2, 0)]), k
 
 
