@@ -1954,7 +1954,7 @@ int g_attn_heads_per_cta = 1;   // kept for the option plumbing; the kernel need
 long long* g_attn_dbg = nullptr;   // b2t_attention_set_dbg(device buffer of 128 int64): developer timeline
 extern "C" void b2t_attention_set_dbg(long long* p) { g_attn_dbg = p; }
 int g_attn_ctas = 0;            // b2t_set_option("attn_ctas", n): cap the persistent kernel's grid (tests: many items per CTA)
-int g_attn_two_pass = 1;        // b2t_set_option("attn_two_pass", 0/1): fixed-maximum two-pass kernel vs online softmax
+int g_attn_two_pass = 4;        // b2t_set_option("attn_two_pass", v): 4 = single pass with P in tensor memory (default), 3 = persistent single pass, 2 = single pass, 1 = two-pass fixed bound, 0 = online softmax, 5 = two-pass + tensor-core row sums
 
 // host entry used by b2t_relkey_attention (attention.cu)
 int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_batch* b, void* out, int heads, cudaStream_t st) {

@@ -33,4 +33,4 @@ for name, rows in (('64x500', [500] * 64), ('24x1500', [1500] * 24), ('mix', lis
     ref = outs['online']
     for k in ('p-in-tmem', 'persistent', 'single-pass', 'two-pass', 'mma.sync'):
         print(f'   {k} vs online: rel {float((outs[k] - ref).norm() / ref.norm()):.2e}  max-abs {float((outs[k] - ref).abs().max()):.2e}', flush=True)
-lib.b2t_set_option(b'attn_two_pass', 1)
+lib.b2t_set_option(b'attn_two_pass', 4)
