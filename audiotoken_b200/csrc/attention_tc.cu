@@ -121,6 +121,20 @@ B2T_DEVICE float2 fadd2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+// 2^x for a pair on the FMA / ALU pipes (see ex2_poly): 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair.  x <= 127;
+// anything below -126 (masked keys: -inf) gives 2^-126 = 1e-38 instead of 0 — below every quantity it is added to.
+B2T_DEVICE float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f); x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 xr = fadd2(x, magic);                // the integer nearest to x lands in the low mantissa bits
+  const float2 n = fadd2(xr, nmagic);
+  const float2 f = fadd2(x, make_float2(-n.x, -n.y));
+  float2 p = ffma2(f, make_float2(0.05550410866f, 0.05550410866f), make_float2(0.24022650696f, 0.24022650696f));
+  p = ffma2(p, f, make_float2(0.69314718056f, 0.69314718056f));
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xr.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xr.y) << 23)));
+}
 B2T_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -1653,6 +1667,7 @@ B2T_DEVICE void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
       : "memory");
 }
 
+template <int kPoly>
 __global__ void __launch_bounds__(kThreadsAttn3, kCtasPerSm)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ CUtensorMap map_e,
@@ -1872,7 +1887,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 xe = ffma2(make_float2(t[ch * 8 + 2 * e], t[ch * 8 + 2 * e + 1]), sc2, off2);
-          pv[e] = make_float2(ex2a(xe.x), ex2a(xe.y));
+          // kPoly of the 4 pairs of a chunk take the polynomial (FMA pipe), the others MUFU.EX2: the XU pipe is the
+          // busiest unit of the loop (60 % of peak over the whole kernel, saturated inside this block)
+          pv[e] = e < kPoly ? ex2_poly2(xe) : make_float2(ex2a(xe.x), ex2a(xe.y));
         }
         ls0 = fadd2(ls0, fadd2(pv[0], pv[1]));
         ls1 = fadd2(ls1, fadd2(pv[2], pv[3]));
@@ -1946,6 +1963,437 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
+
+// =====================================================================================================================
+// attention_tc6_kernel (attn_two_pass = 6): persistent over (query tile, head) items AND P in tensor memory.
+//
+// attention_tc5_kernel still pays ~10 000 clocks per CTA that do not depend on the clip length (10 s clip: 8 key tiles x
+// 1 360 clocks of loop against 10 400 of launch gap, parameter loads, barrier / TMEM set-up, E and Q loads, R, pipeline
+// fill and drain).  Here 2 x #SM CTAs walk over the items (item = blockIdx.x + k gridDim.x, head-major, heaviest clips
+// first) exactly as attention_tc4_kernel does — R as two pseudo tiles of the S ring, next Q requested when the last S MMA
+// of an item retires, K / V rings running ahead across item boundaries, the next item's R rows converted while the last
+// P.V of the current one drains — with the P-in-TMEM data path of attention_tc5_kernel.  An S buffer is released by the
+// P.V commit when it held a key tile and by the eight softmax warps (RDONE) when it held a pseudo tile; every role
+// prefetches the next item's parameters one item ahead, and the TMA warp's K stream hands them to its V and Q streams
+// through a small shared-memory FIFO.
+// =====================================================================================================================
+namespace t6 {
+enum { EFULL = 0, QFULL, QEMPTY, OFULL, KFULL, KEMPTY = KFULL + 4, VFULL = KEMPTY + 4, VEMPTY = VFULL + 4, SFULL = VEMPTY + 4,
+       PFULL = SFULL + 2, PVDONE = PFULL + 2, RDONE = PVDONE + 2, COUNT = RDONE + 2 };
+constexpr int kFifo = t5::kBars + 256;                        // 8 x int4 item descriptors (TMA warp only)
+constexpr int kTotal = kFifo + 128 + 1024;
+constexpr int kRegsIssue = 40, kRegsSoftmax = 96;             // the three-stream TMA warp does not fit 24 registers
+static_assert(COUNT * 8 + 8 <= 256, "barrier area");
+static_assert(2 * (kTotal + 1024) <= 228 * 1024, "two CTAs per SM");
+static_assert(128 * kRegsIssue + 32 * kSoftmaxWarps * kRegsSoftmax <= kThreadsAttn3 * 80, "register pool of the CTA");
+}  // namespace t6
+
+template <int kPoly>
+__global__ void __launch_bounds__(kThreadsAttn3, kCtasPerSm)
+attention_tc6_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ CUtensorMap map_e,
+                     const int32_t* __restrict__ row_off, const int32_t* __restrict__ valid_rows,
+                     const int32_t* __restrict__ qtile_clip, const int32_t* __restrict__ qtile_q0,
+                     __nv_bfloat16* __restrict__ out, int H, int n_qtiles, int n_items, unsigned* __restrict__ trap_rec
+#ifdef B2T_ATTN_TIMELINE
+                     , long long* __restrict__ dbg
+#endif
+                     ) {
+#ifdef B2T_ATTN_TIMELINE
+  // clock64 stamps of softmax thread 128 of CTA 37, items 3..6: 16 stamps per item (see the STAMP sites)
+  int tln = 0;
+#define STAMP() do { if (dbg != nullptr && blockIdx.x == 37 && threadIdx.x == 128 && n >= 3 && n < 7 && tln < 1000) dbg[tln++] = clock64(); } while (0)
+#else
+#define STAMP() do { } while (0)
+#endif
+  static_assert(kKT == 64 && kSoftmaxWarps == 8 && kTmemCols == 256, "single-pass kernel: 64-key tiles, 2 x 4 softmax warps");
+  constexpr uint32_t kTrapSite = 0x600u;           // trap record: 0x600 | warp (mbarrier wait: a = barrier index, b = parity), 0x680 = TMA polling loop
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base + t5::kQ, sK = base + t5::kK, sV = base + t5::kV, sE = base + t5::kE;
+  __nv_bfloat16* sR = reinterpret_cast<__nv_bfloat16*>(gbase + t5::kR);
+  const uint32_t bars = base + t5::kBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  auto wait = [&](uint32_t b_, uint32_t parity_) { mbar_wait_rec(b_, parity_, trap_rec, kTrapSite | (threadIdx.x >> 5), bars); };
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gbase + t5::kBars + 8 * t6::COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const int n_my = (n_items - (int)blockIdx.x + G - 1) / G;     // items of this CTA (>= 1: the grid never exceeds n_items)
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(t6::EFULL), 1); mbar_init(bar(t6::QFULL), 1); mbar_init(bar(t6::QEMPTY), 1); mbar_init(bar(t6::OFULL), 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bar(t6::KFULL + s), 1); mbar_init(bar(t6::KEMPTY + s), 1);
+      mbar_init(bar(t6::VFULL + s), 1); mbar_init(bar(t6::VEMPTY + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(t6::SFULL + b), 1); mbar_init(bar(t6::PFULL + b), kSoftmaxWarps);
+      mbar_init(bar(t6::PVDONE + b), 1); mbar_init(bar(t6::RDONE + b), kSoftmaxWarps);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_kv); tma_prefetch_desc(&map_e); }
+  if (warp == 1) tmem_alloc(bars + 8u * t6::COUNT, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * kKT;       // S / P ring [0,128); accumulators O_0 [128,192), O_1 [192,256)
+
+  if (warp == 0) {
+    reg_dec<t6::kRegsIssue>();
+    // ===== TMA producer: next Q, K ring, V ring as three independent streams over the item sequence (non-blocking probes).
+    //       The K stream leads; it loads every item's parameters (prefetched one item ahead) and leaves {r0, q0, nkt, head}
+    //       in an 8-entry FIFO for the V and Q streams. =====
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(bar(t6::EFULL), 80 * 128);
+      tma_load_2d(sE, &map_e, bar(t6::EFULL), 0, 0);
+    }
+    int4* fifo = reinterpret_cast<int4*>(gbase + t6::kFifo);
+    int ok_ = 0, ov_ = 0, oq_ = 0;                                // item ordinals of the K / V / Q streams
+    uint32_t qn = 0, kg = 0, vg = 0;                              // running counts: Q loads, K tiles, V tiles
+    int kn = 0, vn = 0;                                           // tile inside the K / V stream's current item
+    t4::Item wk = t4_item(blockIdx.x, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0), wkn = wk;
+    if (1 < n_my) wkn = t4_item(blockIdx.x + G, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+    if (leader) fifo[0] = make_int4(wk.r0, wk.q0, wk.nkt, wk.head);
+    __syncwarp();
+    int vr0 = wk.r0, vnkt = wk.nkt, vhead = wk.head;
+    uint32_t spins = 0;
+    while (oq_ < n_my || ok_ < n_my || ov_ < n_my) {
+      bool progress = false;
+      const int pushed = min(ok_, n_my - 1);                      // highest ordinal whose descriptor is in the FIFO
+      if (oq_ < n_my && oq_ <= pushed) {
+        const bool ok = mbar_test_wait(bar(t6::QEMPTY), (qn & 1u) ^ 1u);          // the previous item's last S MMA has retired
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          const int4 e = fifo[oq_ & 7];
+          if (leader) {
+            mbar_expect_tx(bar(t6::QFULL), kQT * 128);
+            tma_load_2d(sQ, &map_qkv, bar(t6::QFULL), e.w * kHD, e.x + e.y);
+          }
+          ++qn; ++oq_; progress = true;
+        }
+      }
+      if (ok_ < n_my) {
+        const uint32_t st = kg & 3u;
+        const bool ok = mbar_test_wait(bar(t6::KEMPTY) + 8u * st, ((kg >> 2) & 1u) ^ 1u);
+        // moving on to the next item overwrites FIFO entry (ok_ + 1) & 7: both followers must be past ordinal ok_ - 7
+        const bool room = kn + 1 < wk.nkt || ok_ + 1 - min(oq_, ov_) < 8;
+        if (__shfl_sync(0xffffffffu, (int)(ok && room), 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(t6::KFULL) + 8u * st, t5::kSlotBytes);
+            tma_load_2d(sK + st * t5::kSlotBytes, &map_kv, bar(t6::KFULL) + 8u * st, H + wk.head * kHD, wk.r0 + kn * kKT);
+          }
+          ++kg; progress = true;
+          if (++kn == wk.nkt) {
+            kn = 0; ++ok_;
+            if (ok_ < n_my) {
+              wk = wkn;
+              if (leader) fifo[ok_ & 7] = make_int4(wk.r0, wk.q0, wk.nkt, wk.head);
+              __syncwarp();
+              if (ok_ + 1 < n_my) wkn = t4_item(blockIdx.x + (ok_ + 1) * G, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+            }
+          }
+        }
+      }
+      if (ov_ < n_my && ov_ <= pushed) {
+        const uint32_t st = vg & 3u;
+        const bool ok = mbar_test_wait(bar(t6::VEMPTY) + 8u * st, ((vg >> 2) & 1u) ^ 1u);
+        if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+          if (leader) {
+            mbar_expect_tx(bar(t6::VFULL) + 8u * st, t5::kSlotBytes);
+            tma_load_2d(sV + st * t5::kSlotBytes, &map_kv, bar(t6::VFULL) + 8u * st, 2 * H + vhead * kHD, vr0 + vn * kKT);
+          }
+          ++vg; progress = true;
+          if (++vn == vnkt) {
+            vn = 0; ++ov_;
+            if (ov_ < n_my && ov_ <= min(ok_, n_my - 1)) { const int4 e = fifo[ov_ & 7]; vr0 = e.x; vnkt = e.z; vhead = e.w; }
+            else vnkt = 0;                                        // descriptor not pushed yet: fetched below before the next V tile
+          }
+        }
+      }
+      if (ov_ < n_my && vnkt == 0 && ov_ <= min(ok_, n_my - 1)) { const int4 e = fifo[ov_ & 7]; vr0 = e.x; vnkt = e.z; vhead = e.w; progress = true; }
+      if (progress) spins = 0;
+      else if (++spins > (1u << 28)) b2t_trap_record(trap_rec, kTrapSite | 0x80u, kg, vg);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    reg_dec<t6::kRegsIssue>();
+    // ===== S issuer: per item two pseudo tiles (R = Q.E^T, columns 0..63 and 64..79), then S = Q.K^T per key tile =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(128, kKT);          // S = Q K^T, R[:, 0:64] = Q E[0:64]^T   (both K-major)
+    constexpr uint32_t idesc_r = make_idesc(128, 16);           // R[:, 64:80]
+    const uint64_t de = make_smem_desc(sE), dq = make_smem_desc(sQ), dk0 = make_smem_desc(sK);
+    wait(bar(t6::EFULL), 0);
+    uint32_t sg = 0, kg = 0, n = 0;
+    uint32_t cp0 = 0, cp1 = 0, cr0 = 0, cr1 = 0, prev0 = 0, prev1 = 0;   // per S buffer: key tiles / pseudo tiles issued, kind of the last occupant
+    auto release_wait = [&](uint32_t b) {                         // the previous occupant of buffer b has been consumed
+      const uint32_t prev = b ? prev1 : prev0;
+      if (prev == 1u) wait(bar(t6::PVDONE) + 8u * b, ((b ? cp1 : cp0) - 1u) & 1u);
+      else if (prev == 2u) wait(bar(t6::RDONE) + 8u * b, ((b ? cr1 : cr0) - 1u) & 1u);
+    };
+    int nkt_next = (valid_rows[qtile_clip[(int)blockIdx.x % n_qtiles]] + kKT - 1) / kKT;
+    for (int it = blockIdx.x; it < n_items; it += G, ++n) {
+      const int nkt = nkt_next;
+      if (it + G < n_items) nkt_next = (valid_rows[qtile_clip[(it + G) % n_qtiles]] + kKT - 1) / kKT;
+      wait(bar(t6::QFULL), n & 1u);
+      for (int ps = 0; ps < 2; ++ps, ++sg) {
+        const uint32_t b = sg & 1u;
+        release_wait(b);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t dep = de + (uint64_t)(ps * (64 * 128 >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tS + b * kKT, dq + (uint64_t)(2 * k), dep + (uint64_t)(2 * k), ps == 0 ? idesc_s : idesc_r, k != 0);
+          umma_commit(bar(t6::SFULL) + 8u * b);
+        }
+        if (b) { ++cr1; prev1 = 2u; } else { ++cr0; prev0 = 2u; }
+      }
+      for (int j = 0; j < nkt; ++j, ++sg, ++kg) {
+        const uint32_t b = sg & 1u, st = kg & 3u;
+        wait(bar(t6::KFULL) + 8u * st, (kg >> 2) & 1u);           // one wait after the other (see the two-pass kernel)
+        release_wait(b);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t dk = dk0 + (uint64_t)(st * (t5::kSlotBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS + b * kKT, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
+          umma_commit(bar(t6::SFULL) + 8u * b);
+          umma_commit(bar(t6::KEMPTY) + 8u * st);
+          if (j == nkt - 1) umma_commit(bar(t6::QEMPTY));          // Q may be overwritten by the next item's tile
+        }
+        if (b) { ++cp1; prev1 = 1u; } else { ++cp0; prev0 = 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    reg_dec<t6::kRegsIssue>();
+    // ===== PV issuer: A = P from tensor memory; keys 0..31 of every tile accumulate into O_0, keys 32..63 into O_1 =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_o = make_idesc(128, kHD, 1);       // O += P V    (P K-major in TMEM, V MN-major in shared memory)
+    const uint64_t dv0 = make_smem_desc(sV);
+    uint32_t sg = 0, vg = 0, cp0 = 0, cp1 = 0;
+    int nkt_next = (valid_rows[qtile_clip[(int)blockIdx.x % n_qtiles]] + kKT - 1) / kKT;
+    for (int it = blockIdx.x; it < n_items; it += G) {
+      const int nkt = nkt_next;
+      if (it + G < n_items) nkt_next = (valid_rows[qtile_clip[(it + G) % n_qtiles]] + kKT - 1) / kKT;
+      sg += 2;                                                    // the item's two pseudo tiles
+      for (int ip = 0; ip < nkt; ++ip, ++sg, ++vg) {
+        const uint32_t b = sg & 1u, st = vg & 3u;
+        // PFULL of an item's first tile also says: every softmax warp has finished reading the previous item's O
+        wait(bar(t6::PFULL) + 8u * b, (b ? cp1 : cp0) & 1u);
+        wait(bar(t6::VFULL) + 8u * st, (vg >> 2) & 1u);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t dv = dv0 + (uint64_t)(st * (t5::kSlotBytes >> 4));
+#pragma unroll
+          for (int kk = 0; kk < kKT / 16; ++kk)
+            umma_bf16_ts(tO + (kk >> 1) * kHD, tS + b * kKT + (kk >> 1) * 32 + (kk & 1) * 8, dv + (uint64_t)(kk * (16 * 128 >> 4)), idesc_o,
+                         (ip != 0 || (kk & 1) != 0) ? 1u : 0u);
+          umma_commit(bar(t6::PVDONE) + 8u * b);
+          umma_commit(bar(t6::VEMPTY) + 8u * st);
+          if (ip == nkt - 1) umma_commit(bar(t6::OFULL));
+        }
+        if (b) ++cp1; else ++cp0;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    reg_dec<t6::kRegsIssue>();                      // idle member of warpgroup 0
+  } else {
+    // ===== softmax / output warps: thread = (query row = TMEM lane, 32-key half wg) with its own bound / sum / accumulator =====
+    reg_inc<t6::kRegsSoftmax>();
+    constexpr int kWG = 2, kKW = 32;
+    const int quad = warp & 3;
+    const int wg = (warp - 4) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    constexpr float kScale = 0.125f * 1.4426950408889634f;   // log2 domain
+    constexpr float kTau = 8.0f;
+    constexpr float kNone = -1.0e30f;                        // "no key seen yet": finite, so 2^(-inf + 1e30) = 0 without a special case
+    float* sml = reinterpret_cast<float*>(gbase + t5::kML);  // [m | l][wg][row]
+    const __nv_bfloat16* myR = sR + r * t5::kRS;
+    const uint32_t tSP = tS + lane_base + (uint32_t)(wg * kKW);          // this thread's S slice; its P words go to the first 16 columns of it
+    uint32_t sg = 0, n = 0, cp0 = 0, cp1 = 0;
+
+    // the two pseudo tiles of an item -> this thread's part of the bf16 R row (the reference's einsum output dtype)
+    auto take_r = [&]() {
+      uint32_t* rr = reinterpret_cast<uint32_t*>(sR + r * t5::kRS);
+      {
+        const uint32_t b = sg & 1u;
+        wait(bar(t6::SFULL) + 8u * b, (sg >> 1) & 1u);
+        tc_fence_after();
+        uint32_t a[32];
+        tmem_ld_32x32_nowait(tSP + b * kKT, a);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(t6::RDONE) + 8u * b);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) rr[(wg * 32 + i) >> 1] = pack_bf16x2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+        ++sg;
+      }
+      {
+        const uint32_t b = sg & 1u;
+        wait(bar(t6::SFULL) + 8u * b, (sg >> 1) & 1u);
+        tc_fence_after();
+        if (wg == kWG - 1) {
+          uint32_t c[16];
+          tmem_ld_32x32_x16_nowait(tS + lane_base + b * kKT, c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 10; i += 2) rr[(64 + i) >> 1] = pack_bf16x2(__uint_as_float(c[i]), __uint_as_float(c[i + 1]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(t6::RDONE) + 8u * b);
+        ++sg;
+      }
+    };
+
+    int it = blockIdx.x;
+    t4::Item w = t4_item(it, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+    take_r();
+    row_barrier<32 * kWG>(quad);
+    while (it < n_items) {
+      const int it_next = it + G;
+      t4::Item wn = w;                                            // next item's parameters: in flight during this item
+      if (it_next < n_items) wn = t4_item(it_next, n_qtiles, row_off, valid_rows, qtile_clip, qtile_q0);
+      const int qpos = w.q0 + r, nkeys = w.nkeys;
+      const float rl = __bfloat162float(myR[0]) * kScale, rrt = __bfloat162float(myR[kRel - 1]) * kScale;
+      float m_run = kNone, l = 0.f;
+      STAMP();                                                    // [0] item start
+      for (int i = 0; i < w.nkt; ++i, ++sg) {
+        const uint32_t b = sg & 1u;
+        const int k0 = i * kKT + wg * kKW;
+        wait(bar(t6::SFULL) + 8u * b, (sg >> 1) & 1u);
+        if (i < 3) STAMP();                                       // [1..3] S ready, tiles 0..2
+        tc_fence_after();
+        float t[kKW];
+        {
+          uint32_t x[32];
+          tmem_ld_32x32_nowait(tSP + b * kKT, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(x[e]);
+        }
+        const int dlo = k0 - qpos, dhi = k0 + kKW - 1 - qpos;
+        const bool band = !(dhi <= -kLeft || dlo >= kRight);        // outside the diagonal band the bias is one constant per row
+        const float cb = dhi <= -kLeft ? rl : rrt;
+        if (band) {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) t[e] += __bfloat162float(myR[max(-kLeft, min(kRight, dlo + e)) + kLeft]);
+        }
+        if (k0 + kKW > nkeys) {
+#pragma unroll
+          for (int e = 0; e < kKW; ++e) if (k0 + e >= nkeys) t[e] = -INFINITY;
+        }
+        float m0 = fmaxf(t[0], t[1]), m1 = fmaxf(t[2], t[3]);
+#pragma unroll
+        for (int e = 4; e < kKW; e += 4) { m0 = fmaxf(m0, fmaxf(t[e], t[e + 1])); m1 = fmaxf(m1, fmaxf(t[e + 2], t[e + 3])); }
+        const float mt = fmaxf(m0, m1);
+        const float mts = band ? mt * kScale : fmaf(mt, kScale, cb);           // largest biased score of the slice, log2 domain
+        const bool grow = mts > m_run + kTau;                                   // false for a fully masked slice (mts = -inf)
+        const float m_new = grow ? ceilf(mts) : m_run;
+        const float off = (band ? 0.f : cb) - m_new;                            // p = 2^(raw * kScale + off)
+        const float2 sc2 = make_float2(kScale, kScale), off2 = make_float2(off, off);
+        float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0;
+        uint32_t v[kKW / 2];
+#pragma unroll
+        for (int ch = 0; ch < kKW / 8; ++ch) {
+          float2 pv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 xe = ffma2(make_float2(t[ch * 8 + 2 * e], t[ch * 8 + 2 * e + 1]), sc2, off2);
+            pv[e] = e < kPoly ? ex2_poly2(xe) : make_float2(ex2a(xe.x), ex2a(xe.y));
+          }
+          ls0 = fadd2(ls0, fadd2(pv[0], pv[1]));
+          ls1 = fadd2(ls1, fadd2(pv[2], pv[3]));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[ch * 4 + e] = pack_bf16x2(pv[e].x, pv[e].y);
+        }
+        tmem_st_32x32_x16(tSP + b * kKT, v);                          // P over the (already read) first half of this thread's S slice
+        const float m_old = m_run;
+        m_run = m_new;
+        const bool resc = grow && m_old != kNone;                     // never on the first tile of an item
+        if (__any_sync(0xffffffffu, resc)) {
+          // P.V(i-1) (the other buffer's latest key tile) must have retired before O is rescaled
+          wait(bar(t6::PVDONE) + 8u * (b ^ 1u), ((b ? cp0 : cp1) - 1u) & 1u);
+          tc_fence_after();
+          const float f = resc ? ex2a(m_old - m_new) : 1.0f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o[32];
+            tmem_ld_32x32_nowait(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tmem_st_32x32(tO + lane_base + (uint32_t)(wg * kHD + 32 * h), o);
+          }
+          l *= f;
+        }
+        l += (ls0.x + ls0.y) + (ls1.x + ls1.y);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(t6::PFULL) + 8u * b);
+        if (b) ++cp1; else ++cp0;
+      }
+
+      // ---- item end.  Publish (bound, sum); once both warps of the row quad are past their last R read, turn the NEXT
+      //      item's pseudo tiles into R rows (this is what the drain of the last P.V hides); then merge and store O.
+      STAMP();                                                    // [4] loop end
+      sml[wg * kQT + r] = m_run;
+      sml[2 * kQT + wg * kQT + r] = l;
+      row_barrier<32 * kWG>(quad);
+      STAMP();                                                    // [5] both warps of the quad done
+      const float ma = sml[r], mb = sml[kQT + r];
+      const float la = sml[2 * kQT + r], lb = sml[3 * kQT + r];
+      if (it_next < n_items) take_r();
+      STAMP();                                                    // [6] next item's R rows taken
+      const float mm = fmaxf(ma, mb);                                          // > kNone: key 0 of the clip is always valid
+      const float fa = ex2a(ma - mm), fb = ex2a(mb - mm);                      // 2^(kNone - mm) = 0 for a half that never saw a key
+      const float inv = 1.0f / (la * fa + lb * fb);
+      const float ga = fa * inv, gb = fb * inv;
+      wait(bar(t6::OFULL), n & 1u);
+      STAMP();                                                    // [7] last P.V retired
+      tc_fence_after();
+      __nv_bfloat16* dst = out + (size_t)(w.r0 + qpos) * H + w.head * kHD + wg * 32;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t xa[16], xb[16];
+        tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(wg * 32 + 16 * ch), xa);
+        tmem_ld_32x32_x16_nowait(tO + lane_base + (uint32_t)(kHD + wg * 32 + 16 * ch), xb);
+        tmem_ld_wait();
+        uint32_t wv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          wv[e] = pack_bf16x2(fmaf(__uint_as_float(xb[2 * e]), gb, __uint_as_float(xa[2 * e]) * ga),
+                              fmaf(__uint_as_float(xb[2 * e + 1]), gb, __uint_as_float(xa[2 * e + 1]) * ga));
+        if (qpos < w.rows)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"l"(dst + 16 * ch), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]), "r"(wv[4]), "r"(wv[5]), "r"(wv[6]), "r"(wv[7])
+                       : "memory");
+      }
+      STAMP();                                                    // [8] O stored
+      tc_fence_before();               // the O reads are complete before this warp's next P hand-off lets P.V overwrite O
+      row_barrier<32 * kWG>(quad);     // the next item's R rows are complete; the (bound, sum) slots may be rewritten
+      STAMP();                                                    // [9] item done
+      it = it_next; ++n; w = wn;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
 #endif  // !B2T_ATTN_WIDE
 
 }  // namespace
@@ -1953,6 +2401,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 int g_attn_heads_per_cta = 1;   // kept for the option plumbing; the kernel needs 1 (E and R borrow per-head buffers)
 long long* g_attn_dbg = nullptr;   // b2t_attention_set_dbg(device buffer of 128 int64): developer timeline
 extern "C" void b2t_attention_set_dbg(long long* p) { g_attn_dbg = p; }
+int g_attn_poly_exp = 1;        // b2t_set_option("attn_poly_exp", 0/1): one pair in four of the 2^x of the P-in-TMEM kernels on the FMA pipe
 int g_attn_ctas = 0;            // b2t_set_option("attn_ctas", n): cap the persistent kernel's grid (tests: many items per CTA)
 int g_attn_two_pass = 4;        // b2t_set_option("attn_two_pass", v): 4 = single pass with P in tensor memory (default), 3 = persistent single pass, 2 = single pass, 1 = two-pass fixed bound, 0 = online softmax, 5 = two-pass + tensor-core row sums
 
@@ -1984,9 +2433,27 @@ int b2t_attention_tensor_tc(const void* qkv, const void* dist_emb, const b2t_bat
       return B2T_OK;
     }
     if (g_attn_two_pass == 4) {          // single pass, P in tensor memory
-      B2T_SMEM_OPT_IN(t5::kTotal, attention_tc5_kernel);
-      attention_tc5_kernel<<<grid, kThreadsAttn3, t5::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip,
-                                                                   b->qtile128_q0, (__nv_bfloat16*)out, H, b2t_trap_rec());
+      auto kern5 = g_attn_poly_exp ? attention_tc5_kernel<1> : attention_tc5_kernel<0>;
+      B2T_SMEM_OPT_IN(t5::kTotal, attention_tc5_kernel<0>);
+      B2T_SMEM_OPT_IN(t5::kTotal, attention_tc5_kernel<1>);
+      kern5<<<grid, kThreadsAttn3, t5::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip, b->qtile128_q0,
+                                                    (__nv_bfloat16*)out, H, b2t_trap_rec());
+      B2T_LAUNCH_CHECK();
+      return B2T_OK;
+    }
+    if (g_attn_two_pass == 6) {          // single pass, P in tensor memory, persistent over (query tile, head) items
+      auto kern6 = g_attn_poly_exp ? attention_tc6_kernel<1> : attention_tc6_kernel<0>;
+      B2T_SMEM_OPT_IN(t6::kTotal, attention_tc6_kernel<0>);
+      B2T_SMEM_OPT_IN(t6::kTotal, attention_tc6_kernel<1>);
+      const int n_items = b->n_qtiles128 * heads;
+      int ctas = std::min(n_items, kCtasPerSm * b2t_num_sms());
+      if (g_attn_ctas > 0) ctas = std::min(ctas, g_attn_ctas);
+      kern6<<<ctas, kThreadsAttn3, t6::kTotal, st>>>(mq, mk, me, b->row_off, b->valid_rows, b->qtile128_clip, b->qtile128_q0,
+                                                    (__nv_bfloat16*)out, H, b->n_qtiles128, n_items, b2t_trap_rec()
+#ifdef B2T_ATTN_TIMELINE
+                                                    , g_attn_dbg
+#endif
+                                                    );
       B2T_LAUNCH_CHECK();
       return B2T_OK;
     }

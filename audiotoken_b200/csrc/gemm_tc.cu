@@ -459,6 +459,7 @@ int b2t_test_trap(int light);      // api.cu
 extern int g_attn_heads_per_cta;   // attention_tc.cu
 extern int g_attn_two_pass;
 extern int g_attn_ctas;
+extern int g_attn_poly_exp;
 extern bool g_rvq_tensor;          // acoustic.cu
 extern int g_rvq_dbg;              // rvq_tc.cu
 void b2t_seanet_set_sub_frames(int n);   // seanet_tc.cu
@@ -481,6 +482,7 @@ extern "C" int b2t_set_option(const char* name, int value) {
   if (std::string(name) == "rvq_tensor") { g_rvq_tensor = value != 0; return B2T_OK; }
   if (std::string(name) == "attn_two_pass") { g_attn_two_pass = value; return B2T_OK; }
   if (std::string(name) == "attn_ctas") { g_attn_ctas = value; return B2T_OK; }
+  if (std::string(name) == "attn_poly_exp") { g_attn_poly_exp = value; return B2T_OK; }
   if (std::string(name) == "attn_heads_per_cta") {
     B2T_REQUIRE(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, B2T_ERR_ARG, "attn_heads_per_cta must divide 16");
     g_attn_heads_per_cta = value;

@@ -13,6 +13,8 @@ from oracle import conformer, fbank, quantize
 
 pytestmark = pytest.mark.gpu
 
+ATTN_DEFAULT = 4          # library default of the attn_two_pass option (attention_tc.cu::g_attn_two_pass)
+
 
 def rel_err(a, b):
     a, b = a.double().cpu(), b.double().cpu()
@@ -235,7 +237,7 @@ def test_attention_bf16(cuda_device, impl, rows, valid):
     assert rel_err(out.float(), ref) < 1e-2, rel_err(out.float(), ref)
 
 
-@pytest.mark.parametrize('mode', [1, 2, 3, 4])
+@pytest.mark.parametrize('mode', [1, 2, 3, 4, 6])
 def test_attention_tensor_large_dynamic_range(cuda_device, mode):
     """Adversarial logits for the fixed-bound (mode 1: two-pass) and lazily rescaled (mode 2: single-pass) tcgen05
     kernels: q, k scaled so that raw scores span hundreds of log2 units, the largest raw score and the largest relative
@@ -263,16 +265,17 @@ def test_attention_tensor_large_dynamic_range(cuda_device, mode):
     try:
         out = ops.relkey_attention(qkv.to(cuda_device, torch.bfloat16), E.to(cuda_device, torch.bfloat16), plan, 'bf16', L.IMPL_TENSOR)
     finally:
-        L.check(lib.b2t_set_option(b'attn_two_pass', 4), 'attn_two_pass')
+        L.check(lib.b2t_set_option(b'attn_two_pass', ATTN_DEFAULT), 'attn_two_pass')
     assert torch.isfinite(out.float()).all()
     assert rel_err(out.float(), ref.float()) < 1.5e-2, rel_err(out.float(), ref.float())
 
 
 def test_attention_persistent_items(cuda_device):
-    """The persistent single-pass kernel (attn_two_pass = 3) with its grid capped to 3 and to 7 CTAs: every CTA walks
-    over dozens of (query tile, head) items of different lengths, so R pseudo tiles, ring counters and barrier phases
-    carry across item boundaries.  Checked against the fp64 formula, and bit-for-bit against the one-item-per-CTA
-    single-pass kernel (same arithmetic, same tiles)."""
+    """The persistent single-pass kernels (attn_two_pass = 3: P in shared memory, 6: P in tensor memory) with their grid
+    capped to 3 and to 7 CTAs: every CTA walks over dozens of (query tile, head) items of different lengths, so R pseudo
+    tiles, ring counters and barrier phases carry across item boundaries.  Checked against the fp64 formula, and — with
+    the polynomial exponential switched off — bit-for-bit against the one-item-per-CTA single-pass kernel (same
+    arithmetic, same tiles; an integer bound makes the result independent of the rescaling schedule)."""
     lib = L.load()
     rows, valid = [300, 64, 130, 1, 257, 50, 128, 200], [290, 40, 130, 1, 257, 33, 128, 190]
     g = torch.Generator().manual_seed(5)
@@ -282,18 +285,25 @@ def test_attention_persistent_items(cuda_device):
     ref = _attn_oracle(qkv.double(), E.double(), rows, valid, False)
     outs = {}
     try:
-        for mode, ctas in ((2, 0), (4, 0), (3, 0), (3, 3), (3, 7)):
+        for mode, ctas, poly in ((2, 0, 0), (4, 0, 0), (3, 0, 0), (3, 3, 0), (3, 7, 0), (6, 0, 0), (6, 3, 0), (6, 7, 0),
+                                 (4, 0, 1), (6, 0, 1), (6, 5, 1)):
             L.check(lib.b2t_set_option(b'attn_two_pass', mode), 'attn_two_pass')
             L.check(lib.b2t_set_option(b'attn_ctas', ctas), 'attn_ctas')
-            outs[(mode, ctas)] = ops.relkey_attention(qkv.to(cuda_device, torch.bfloat16), E.to(cuda_device, torch.bfloat16), plan,
-                                                      'bf16', L.IMPL_TENSOR).float().cpu()
+            L.check(lib.b2t_set_option(b'attn_poly_exp', poly), 'attn_poly_exp')
+            outs[(mode, ctas, poly)] = ops.relkey_attention(qkv.to(cuda_device, torch.bfloat16), E.to(cuda_device, torch.bfloat16),
+                                                            plan, 'bf16', L.IMPL_TENSOR).float().cpu()
     finally:
-        L.check(lib.b2t_set_option(b'attn_two_pass', 4), 'attn_two_pass')
+        L.check(lib.b2t_set_option(b'attn_two_pass', ATTN_DEFAULT), 'attn_two_pass')
         L.check(lib.b2t_set_option(b'attn_ctas', 0), 'attn_ctas')
+        L.check(lib.b2t_set_option(b'attn_poly_exp', 1), 'attn_poly_exp')
     for k, o in outs.items():
         assert rel_err(o, ref.float()) < 1e-2, (k, rel_err(o, ref.float()))
-    for k in ((4, 0), (3, 0), (3, 3), (3, 7)):
-        assert torch.equal(outs[k], outs[(2, 0)]), k
+    for k, o in outs.items():
+        if k[2] == 0:
+            assert torch.equal(o, outs[(2, 0, 0)]), k
+        else:                               # degree-3 polynomial on a quarter of the exponentials: 1e-4 relative on P
+            assert rel_err(o, outs[(2, 0, 0)]) < 2e-3, (k, rel_err(o, outs[(2, 0, 0)]))
+            assert torch.equal(o, outs[(4, 0, 1)]), k
 
 
 # ---------------------------------------------------------------------------------- depthwise conv

@@ -17,7 +17,7 @@ for name, rows in (('64x500', [500] * 64), ('24x1500', [1500] * 24), ('mix', lis
     E = torch.randn(73, 64, device=dev).to(torch.bfloat16)
     flops = sum(4096.0 * r * r for r in rows)
     outs = {}
-    for label, impl, two in (('p-in-tmem', L.IMPL_TENSOR, 4), ('persistent', L.IMPL_TENSOR, 3), ('single-pass', L.IMPL_TENSOR, 2), ('two-pass', L.IMPL_TENSOR, 1), ('online', L.IMPL_TENSOR, 0), ('mma.sync', L.IMPL_MMA_SYNC, 0)):
+    for label, impl, two in (('persist-tmem', L.IMPL_TENSOR, 6), ('p-in-tmem', L.IMPL_TENSOR, 4), ('persistent', L.IMPL_TENSOR, 3), ('single-pass', L.IMPL_TENSOR, 2), ('two-pass', L.IMPL_TENSOR, 1), ('online', L.IMPL_TENSOR, 0), ('mma.sync', L.IMPL_MMA_SYNC, 0)):
         lib.b2t_set_option(b'attn_two_pass', two)
         db = packing.DeviceBatch(plan, dev); out = torch.zeros(M, 1024, device=dev, dtype=torch.bfloat16)
         for _ in range(2):
@@ -31,6 +31,6 @@ for name, rows in (('64x500', [500] * 64), ('24x1500', [1500] * 24), ('mix', lis
         outs[label] = out.float().cpu()
         print(f'{name} {label}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s', flush=True)
     ref = outs['online']
-    for k in ('p-in-tmem', 'persistent', 'single-pass', 'two-pass', 'mma.sync'):
+    for k in ('persist-tmem', 'p-in-tmem', 'persistent', 'single-pass', 'two-pass', 'mma.sync'):
         print(f'   {k} vs online: rel {float((outs[k] - ref).norm() / ref.norm()):.2e}  max-abs {float((outs[k] - ref).abs().max()):.2e}', flush=True)
 lib.b2t_set_option(b'attn_two_pass', 4)

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out/r2
 O=gpurun_out/r2
 timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider --timeout 600 > $O/tests_f.log 2>&1; echo "tests exit=$?"; tail -4 $O/tests_f.log
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $O/bench_f.json 2> $O/bench_f.err; echo "bench exit=$?"; tail -2 $O/bench_f.err
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/bench_f.json 2> $O/bench_f.err; echo "bench exit=$?"; tail -2 $O/bench_f.err
 python - <<'PY'
 import json
 d=json.loads([l for l in open('gpurun_out/r2/bench_f.json') if l.startswith('{')][-1])
