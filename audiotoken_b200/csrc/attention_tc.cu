@@ -91,50 +91,6 @@ B2T_DEVICE float ex2a(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA / ALU pipes (Cody-Waite: x = n + f, |f| <= 1/2, 2^f by a degree-3 minimax polynomial, n added to the
-// exponent field): relative error 1e-4, far below the bf16 rounding of P.  x <= 127; anything below -126 flushes to 0.
-B2T_DEVICE float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float xr = x + 12582912.0f;                 // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
-  const float f = x - (xr - 12582912.0f);
-  float p = fmaf(f, 0.05550410866f, 0.24022650696f);
-  p = fmaf(p, f, 0.69314718056f);
-  p = fmaf(p, f, 1.0f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(xr) << 23));
-}
-// packed fp32 pairs (sm_100 FFMA2 / FADD2): two results per issue slot
-B2T_DEVICE float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-B2T_DEVICE float2 fadd2(float2 a, float2 b) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-// 2^x for a pair on the FMA / ALU pipes (see ex2_poly): 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair.  x <= 127;
-// anything below -126 (masked keys: -inf) gives 2^-126 = 1e-38 instead of 0 — below every quantity it is added to.
-B2T_DEVICE float2 ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.0f); x.y = fmaxf(x.y, -126.0f);
-  const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
-  const float2 xr = fadd2(x, magic);                // the integer nearest to x lands in the low mantissa bits
-  const float2 n = fadd2(xr, nmagic);
-  const float2 f = fadd2(x, make_float2(-n.x, -n.y));
-  float2 p = ffma2(f, make_float2(0.05550410866f, 0.05550410866f), make_float2(0.24022650696f, 0.24022650696f));
-  p = ffma2(p, f, make_float2(0.69314718056f, 0.69314718056f));
-  p = ffma2(p, f, make_float2(1.0f, 1.0f));
-  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xr.x) << 23)),
-                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xr.y) << 23)));
-}
 B2T_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -81,8 +81,29 @@ B2T_DEVICE void resid_chunk_coalesced(const EpiParams& p, float4* stg, int row_b
 }
 
 // bf16 epilogues (BIAS / SWISH / GLU): values of 32 accumulator columns -> packed bf16 (uint32 pairs)
+#ifndef B2T_GEMM_DIRECT_STORE
+#define B2T_GEMM_DIRECT_STORE 1
+#endif
+#ifndef B2T_GEMM_SWISH_POLY
+#define B2T_GEMM_SWISH_POLY 1
+#endif
 template <int EPI>
 B2T_DEVICE void epi_pack32(const EpiParams& p, int col0, const float (&acc)[32], uint32_t* pk) {
+  if constexpr (EPI == B2T_EPI_BIAS_SWISH && B2T_GEMM_SWISH_POLY != 0) {
+    // two XU-pipe operations per element instead of 3.5: the bf16 rounding of the linear output (an autocast rounding
+    // point) is ONE packed conversion per pair, unpacked with a shift and a mask; swish2 = polynomial 2^x + MUFU.RCP
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      const uint32_t r0 = pack2_bf16(acc[i] + b.x, acc[i + 1] + b.y), r1 = pack2_bf16(acc[i + 2] + b.z, acc[i + 3] + b.w);
+      const float2 s0 = swish2(make_float2(__uint_as_float(r0 << 16), __uint_as_float(r0 & 0xffff0000u)));
+      const float2 s1 = swish2(make_float2(__uint_as_float(r1 << 16), __uint_as_float(r1 & 0xffff0000u)));
+      pk[i >> 1] = pack2_bf16(s0.x, s0.y);
+      pk[(i >> 1) + 1] = pack2_bf16(s1.x, s1.y);
+    }
+    return;
+  }
   float v[32];
   if (p.bias != nullptr) {
 #pragma unroll
@@ -315,7 +336,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
+            #ifdef B2T_GEMM_RELEASE_ARRIVE
             if constexpr (kMC) mbar_arrive_cluster(mapa_rank0(tempty_bar(acc)));
+#else
+            if constexpr (kMC) mbar_arrive_cluster_relaxed(mapa_rank0(tempty_bar(acc)));
+#endif
+              // TMEM hand-back: the accumulator reads have completed, nothing in memory to publish (the release form cost a MEMBAR.ALL.GPU per tile: 12 % of the kernel's stall samples)
             else mbar_arrive(tempty_bar(acc));
           }
         }
@@ -336,8 +362,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; ++i) pk4[i] = make_uint4(glu_pk[4 * i], glu_pk[4 * i + 1], glu_pk[4 * i + 2], glu_pk[4 * i + 3]);
             const int ocol = (EPI == B2T_EPI_GLU) ? (n0 + part * kChunks * 32) / 2 : col_a;
+#if B2T_GEMM_DIRECT_STORE
+            // row-per-lane 256-bit stores (whole 32-byte sectors): no staging through shared memory, no warp syncs in the
+            // epilogue chain.  The epilogue warps never wait for the MMA in the K = 1024 shapes (ncu: no samples on their
+            // accumulator-full wait): per-thread latency, not bandwidth, bounds those GEMMs.
+            if (row < p.M) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + ocol;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"l"(dst + 16 * i), "r"(pk4[2 * i].x), "r"(pk4[2 * i].y), "r"(pk4[2 * i].z), "r"(pk4[2 * i].w),
+                               "r"(pk4[2 * i + 1].x), "r"(pk4[2 * i + 1].y), "r"(pk4[2 * i + 1].z), "r"(pk4[2 * i + 1].w)
+                             : "memory");
+            }
+#else
             store_rows_coalesced(reinterpret_cast<uint4*>(stg), reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, p.M,
                                  m0 + quad * 32, ocol, lane, pk4);
+#endif
           }
         } else {
           if constexpr (EPI == kEpiArgmax) {
@@ -467,10 +508,12 @@ void b2t_seanet_set_lstm_pdl(int on);
 void b2t_seanet_set_lstm_overlap(int on);
 void b2t_seanet_set_l0_fused(int on);
 extern bool g_dwconv_ring;         // dwconv.cu
+extern bool g_ffn_resid_epilogue;  // pipeline.cu
 
 extern "C" int b2t_set_option(const char* name, int value) {
   B2T_REQUIRE(name, B2T_ERR_ARG, "b2t_set_option: null name");
   if (std::string(name) == "gemm_multicast") { g_multicast = value != 0; return B2T_OK; }
+  if (std::string(name) == "ffn_resid_epilogue") { g_ffn_resid_epilogue = value != 0; return B2T_OK; }
   if (std::string(name) == "test_trap") { return value ? b2t_test_trap(value == 2) : B2T_OK; }   // 2: through the mapped host record
   if (std::string(name) == "debug_sync") { b2t_set_debug_sync(value); return B2T_OK; }
   if (std::string(name) == "dwconv_ring") { g_dwconv_ring = value != 0; return B2T_OK; }

@@ -95,8 +95,10 @@ add_layernorm_kernel(float* __restrict__ x, const ActT* __restrict__ d, float al
     }
   }
   if constexpr (!kChain) {
+    if (d != nullptr) {                      // d == NULL: the producing GEMM's epilogue has already updated x
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xr[lane + 32 * j] = v[j];
+      for (int j = 0; j < 8; ++j) xr[lane + 32 * j] = v[j];
+    }
   }
   auto normalise = [&](const float* w, const float* b) {
     float sum = 0.f;

@@ -90,6 +90,11 @@ extern "C" int b2t_debug_stage_sums(unsigned long long* buf, int capacity) {
 }
 extern "C" int b2t_debug_stage_count(void) { return g_sums_n; }
 
+// b2t_set_option("ffn_resid_epilogue", 0/1): the two K = 4096 feed-forward GEMMs of a layer update the fp32 stream in their
+// epilogue (read-modify-write hidden under 32 k-steps per tile) and the LayerNorm that follows reads x alone: same
+// bytes in total, but 6 KB (resp. 2 KB) per row leave the stand-alone HBM-bound LayerNorm kernel.  Same arithmetic.
+bool g_ffn_resid_epilogue = false;  // measured: LayerNorm -20 ms / step, GEMM +26 ms (the K = 4096 epilogues are not free): off
+
 struct b2t_semantic_model {
   int n_layers;
   int codebook_size;
@@ -241,6 +246,12 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
     return b2t_add_layernorm(w.x, w.d, alpha, rr, (const float*)w1, (const float*)b1, (const float*)w2, (const float*)b2, rv,
                              out, M, prec, stream);
   };
+  // the same with the residual update already done by the producing GEMM's epilogue (delta = NULL: x is only read)
+  auto add_ln_x = [&](const void* w1, const void* b1, const void* w2, const void* b2, const uint8_t* rv, void* out) -> int {
+    Scope sc(PC_LN, st);
+    return b2t_add_layernorm(w.x, nullptr, 0.f, 0, (const float*)w1, (const float*)b1, (const float*)w2, (const float*)b2, rv,
+                             out, M, prec, stream);
+  };
   if (m->n_layers > 0) {
     const void* lw = T("L0.ffn1.ln.w"); const void* lb = T("L0.ffn1.ln.b");
     NEED();
@@ -255,8 +266,13 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
       const void* nlw = T(L + "attn.ln.w"); const void* nlb = T(L + "attn.ln.b");
       NEED();
       RUN(gemm(w.ln_out, 1024, w1, b1, w.big, 4096, nullptr, 4096, 1024, B2T_EPI_BIAS_SWISH, 1.f, 0));
-      RUN(gemm(w.big, 4096, w2, b2, w.d, 1024, nullptr, 1024, 4096, B2T_EPI_BIAS, 1.f, 0));
-      RUN(add_ln(0.5f, rr, nlw, nlb, nullptr, nullptr, nullptr, w.ln_out));
+      if (bf && g_ffn_resid_epilogue) {
+        RUN(gemm(w.big, 4096, w2, b2, nullptr, 0, w.x, 1024, 4096, B2T_EPI_RESID, 0.5f, rr));
+        RUN(add_ln_x(nlw, nlb, nullptr, nullptr, nullptr, w.ln_out));
+      } else {
+        RUN(gemm(w.big, 4096, w2, b2, w.d, 1024, nullptr, 1024, 4096, B2T_EPI_BIAS, 1.f, 0));
+        RUN(add_ln(0.5f, rr, nlw, nlb, nullptr, nullptr, nullptr, w.ln_out));
+      }
     }
     // ---- self attention
     {
@@ -289,8 +305,13 @@ extern "C" int b2t_semantic_encode(const b2t_semantic_model* m, const float* wav
       const void* nlw = last ? nullptr : T(N + "ffn1.ln.w"); const void* nlb = last ? nullptr : T(N + "ffn1.ln.b");
       NEED();
       RUN(gemm(w.ln_out, 1024, w1, b1, w.big, 4096, nullptr, 4096, 1024, B2T_EPI_BIAS_SWISH, 1.f, 0));
-      RUN(gemm(w.big, 4096, w2, b2, w.d, 1024, nullptr, 1024, 4096, B2T_EPI_BIAS, 1.f, 0));
-      RUN(add_ln(0.5f, rr, flw, flb, nlw, nlb, nullptr, last ? nullptr : w.ln_out));
+      if (bf && g_ffn_resid_epilogue) {
+        RUN(gemm(w.big, 4096, w2, b2, nullptr, 0, w.x, 1024, 4096, B2T_EPI_RESID, 0.5f, rr));
+        RUN(add_ln_x(flw, flb, nlw, nlb, nullptr, last ? nullptr : w.ln_out));
+      } else {
+        RUN(gemm(w.big, 4096, w2, b2, w.d, 1024, nullptr, 1024, 4096, B2T_EPI_BIAS, 1.f, 0));
+        RUN(add_ln(0.5f, rr, flw, flb, nlw, nlb, nullptr, last ? nullptr : w.ln_out));
+      }
     }
     if (tap_layer == i + 1 && tap_out)
       B2T_CUDA(cudaMemcpyAsync(tap_out, w.x, (size_t)M * 4096, cudaMemcpyDeviceToDevice, st));

@@ -91,6 +91,12 @@ B2T_DEVICE uint32_t mapa_rank0(uint32_t addr) {
 B2T_DEVICE void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
+// The same without memory ordering.  A release at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR: the arriving warp
+// waits until every global store it has in flight is acknowledged.  Where the hand-over is about TENSOR memory whose
+// reads have already completed (tcgen05.wait::ld, then tcgen05.fence::before_thread_sync) no memory needs publishing.
+B2T_DEVICE void mbar_arrive_cluster_relaxed(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 B2T_DEVICE void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -136,6 +142,64 @@ B2T_DEVICE void tmem_alloc_pair(uint32_t smem_dst, uint32_t cols) {
 B2T_DEVICE void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// 2^x on the FMA / ALU pipes (Cody-Waite: x = n + f, |f| <= 1/2, 2^f by a degree-3 minimax polynomial, n added to the
+// exponent field): relative error 1e-4, far below the bf16 rounding of P.  x <= 127; anything below -126 flushes to 0.
+B2T_DEVICE float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xr = x + 12582912.0f;                 // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
+  const float f = x - (xr - 12582912.0f);
+  float p = fmaf(f, 0.05550410866f, 0.24022650696f);
+  p = fmaf(p, f, 0.69314718056f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(xr) << 23));
+}
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): two results per issue slot
+B2T_DEVICE float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+B2T_DEVICE float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// 2^x for a pair on the FMA / ALU pipes (see ex2_poly): 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair.  x <= 127;
+// anything below -126 (masked keys: -inf) gives 2^-126 = 1e-38 instead of 0 — below every quantity it is added to.
+B2T_DEVICE float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f); x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 xr = fadd2(x, magic);                // the integer nearest to x lands in the low mantissa bits
+  const float2 n = fadd2(xr, nmagic);
+  const float2 f = fadd2(x, make_float2(-n.x, -n.y));
+  float2 p = ffma2(f, make_float2(0.05550410866f, 0.05550410866f), make_float2(0.24022650696f, 0.24022650696f));
+  p = ffma2(p, f, make_float2(0.69314718056f, 0.69314718056f));
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xr.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xr.y) << 23)));
+}
+// swish(v) = v / (1 + e^-v) for a pair with ONE special-function op per element: e^-v = 2^(-v log2 e) by the packed
+// polynomial above (argument clamped to +-126: v < -87 gives v * 2^-126, i.e. -0 after the bf16 rounding), then MUFU.RCP.
+// The MUFU.EX2 + MUFU.RCP form made the N = 4096 swish GEMM's epilogue XU-bound (XU pipe 49 % over the whole kernel with
+// the F2F / F2FP conversions on the same pipe).  Relative error 1e-4, far below the bf16 rounding of the result.
+B2T_DEVICE float2 swish2(float2 v) {
+  float2 x = make_float2(v.x * -1.4426950408889634f, v.y * -1.4426950408889634f);
+  x.x = fminf(x.x, 126.0f); x.y = fminf(x.y, 126.0f);
+  const float2 e = ex2_poly2(x);
+  float ra, rb;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(e.x + 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(e.y + 1.0f));
+  return make_float2(v.x * ra, v.y * rb);
+}
+
 B2T_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 B2T_DEVICE void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
