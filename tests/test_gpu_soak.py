@@ -129,3 +129,29 @@ def test_acoustic_is_deterministic_at_production_size(cuda_device):
             assert int(first.min()) >= 0 and int(first.max()) < 1024
         else:
             assert torch.equal(first, codes), f'iteration {it}: {int((first != codes).sum())} codes differ'
+
+
+def test_device_trap_record_reaches_the_host():
+    """The register-critical kernels (single-pass attention) report a protocol time-out by storing {site, a, b, block,
+    thread} into mapped host memory before they trap (no printf ABI call inside setmaxnreg regions).  The trap poisons
+    the CUDA context, so this runs in a child process: b2t_set_option('test_trap', 2) -> the synchronisation fails and
+    b2t_last_device_trap returns the record the test kernel wrote."""
+    code = (
+        "import ctypes as C, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from audiotoken_b200 import lib as L\n"
+        "import torch\n"
+        "torch.zeros(1, device='cuda:0')\n"
+        "lib = L.load()\n"
+        "assert L.device_trap_text() == ''\n"
+        "rc = lib.b2t_set_option(b'test_trap', 2)\n"
+        "rec = (C.c_uint32 * 6)()\n"
+        "got = lib.b2t_last_device_trap(rec)\n"
+        "print('RC', rc, 'GOT', got, 'REC', list(rec), 'TEXT', L.device_trap_text(), 'ERR', lib.b2t_last_error().decode())\n"
+        "import os; os._exit(0)\n" % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    out = r.stdout
+    assert 'RC' in out, (r.stdout[-2000:], r.stderr[-2000:])
+    assert 'GOT 1' in out and 'REC [32343, 43981, 7, 0, 0, 0]' in out, out        # 0x7e57, 0xabcd, 7, block (0,0), thread 0
+    assert 'RC 0' not in out                                                     # the launch's synchronisation reported the fault
+    assert 'device trap record: site 0x7e57' in out
