@@ -312,13 +312,15 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
                     write_futs.append((s_.file_name, writers.submit(write, s_.file_name, self.per_file.pop(s_.file_name))))
                     stats['files'] += 1
 
-    def prepare(window):
-        """window: list of (path, sr, pcm) -> WindowState (PCM decode + resampling on the device, segment rules)."""
+    def prepare(window, raws=None):
+        """window: list of (path, sr, pcm) -> WindowState (PCM decode + resampling on the device, segment rules);
+        raws[i] = the payload of file i already on the device (prepare_async) or None."""
         segs, nbytes = [], 0
-        for path, sr, pcm in window:
+        for wi, (path, sr, pcm) in enumerate(window):
             try:
                 nbytes += pcm.nbytes
-                for ci, wave in enumerate(aio.convert_chunks(sr, pcm, sample_rate, chunk_size, device if on_gpu else None)):
+                for ci, wave in enumerate(aio.convert_chunks(sr, pcm, sample_rate, chunk_size, device if on_gpu else None,
+                                                             raw=raws[wi] if raws else None)):
                     for s_ in aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size):
                         s_.chunk_index = ci                # one segment per streamed chunk (datasets.py:88-105)
                         segs.append(s_)
@@ -331,15 +333,31 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
         stats['windows'] += 1
         return WindowState(segs, rows)
 
-    ingest_stream = torch.cuda.Stream(device=device) if on_gpu else None
+    # side streams of the NEXT window: uploads on a copy-only stream (a pageable copy blocks the host until its stream
+    # has drained, so no kernel may sit in front of it), decode / resampling kernels on a high-priority stream (a few
+    # small CTAs that take the first SM the encoder's persistent kernels release)
+    upload_stream = torch.cuda.Stream(device=device) if on_gpu else None
+    ingest_stream = torch.cuda.Stream(device=device, priority=-1) if on_gpu else None
 
     def prepare_async(window):
-        """prepare() on a side stream: the PCM upload and the decode / resampling kernels of the NEXT window run while
+        """prepare() on side streams: the PCM upload and the decode / resampling kernels of the NEXT window run while
         the compute stream is busy with the batches of the current one"""
         if not on_gpu:
             return prepare(window), None
+        with torch.cuda.stream(upload_stream):
+            raws = []
+            for _, _, pcm in window:
+                try:
+                    raws.append(aio.upload_pcm(pcm, device))
+                except Exception:  # noqa: BLE001 -- prepare() meets the same error and reports it for the file
+                    raws.append(None)
+            uploaded = upload_stream.record_event()
         with torch.cuda.stream(ingest_stream):
-            st_ = prepare(window)
+            ingest_stream.wait_event(uploaded)
+            for r in raws:
+                if r is not None:
+                    r.record_stream(ingest_stream)
+            st_ = prepare(window, raws)
             ready = ingest_stream.record_event()
         return st_, ready
 

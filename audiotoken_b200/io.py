@@ -150,7 +150,19 @@ def read_wav_raw(path) -> Tuple[int, np.ndarray]:
     return int(sr), data
 
 
-def convert_chunks(sr: int, data: np.ndarray, model_sample_rate: int, chunk_size: int, device=None) -> List[torch.Tensor]:
+def upload_pcm(data: np.ndarray, device) -> Optional[torch.Tensor]:
+    """PCM16 / float32 payload of one file -> device tensor [1, n] (None for the encodings the device path does not take).
+    The streaming file loop calls this for every file of a window on a copy-only stream BEFORE any ingest kernel of the
+    window is queued: a pageable host->device copy blocks the calling thread until everything queued before it on its
+    stream has run, and an ingest kernel queued between two copies runs only when the encoder's persistent kernels let
+    go of an SM (0.3-1 ms) — per file, that serialised the host behind the device."""
+    if data.dtype not in (np.int16, np.float32):
+        return None
+    return torch.from_numpy(np.ascontiguousarray(data).reshape(1, -1)).to(device, non_blocking=True)
+
+
+def convert_chunks(sr: int, data: np.ndarray, model_sample_rate: int, chunk_size: int, device=None,
+                   raw: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
     """Second half of the reference's batch reader (utils.py:82-101): the PCM stream is cut into chunks of `chunk_size`
     seconds AT ITS OWN sample rate and every chunk is resampled on its own — so a file whose rate differs from the
     model's has filter edges at every chunk boundary.  Returns fp32 [1, L_i] chunks; on a CUDA `device` PCM decode and
@@ -158,7 +170,8 @@ def convert_chunks(sr: int, data: np.ndarray, model_sample_rate: int, chunk_size
     on_gpu = device is not None and torch.device(device).type == 'cuda' and data.dtype in (np.int16, np.float32)
     if on_gpu:
         from . import ingest
-        raw = torch.from_numpy(np.ascontiguousarray(data).reshape(1, -1)).to(device, non_blocking=True)
+        if raw is None:                                    # `raw`: the payload already uploaded by upload_pcm
+            raw = upload_pcm(data, device)
     else:
         if data.dtype == np.int16:
             x = data.astype(np.float32) / 32768.0
