@@ -345,9 +345,221 @@ dwconv_ring_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   }
 }
 
+
+// ---- round 2: the same ring, half the instructions ---------------------------------------------------------------
+// dwconv_ring_kernel spends 1 723 warp instructions per 16-row sub-tile of which 496 are the packed FMAs (ncu: issue
+// slots 61 % busy, 5 block barriers per sub-tile).  This version keeps the ring protocol and the tap loop (same FMA
+// order => the same conv values) and rebuilds everything behind it:
+//   * every value stays a packed f32x2 (64-bit register pair) from the tap loop to the store: rounding to bf16 is one
+//     cvt.rn.bf16x2 + two unpack ops per row, LayerNorm scale/offset and swish are fma.rn.f32x2 / mul.f32x2;
+//   * row statistics in ONE pass: per thread (sum a, sum a^2) of its two channels for 16 rows = 32 values, reduced over
+//     the warp by a halving butterfly that leaves value l in lane l (31 shuffles), one shared-memory write per lane, ONE
+//     block barrier per sub-tile (partials double-buffered by sub-tile parity), then every warp adds the 16 partial
+//     vectors itself (lane l = value l): no second barrier, no 16-thread serial stage;
+//   * y/2 = a * (rstd * g/2) + (b/2 - mean * rstd * g/2) and swish(y) = y/2 + y/2 * tanh(y/2): 3 packed FMAs + 2 MUFU
+//     per row, stores predicated instead of branched.
+// var = E[a^2] - mean^2 in fp32 (a is bf16-valued, 1024 channels): the result is rounded to bf16 again, the
+// difference to the two-pass form is far below that rounding.
+B2T_DEVICE uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+B2T_DEVICE float2 up2(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+B2T_DEVICE uint64_t fma2p(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+B2T_DEVICE uint64_t mul2p(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// packed bf16x2 word (low half = channel c, high half = channel c + 1) -> f32x2
+B2T_DEVICE uint64_t bf2_to_f2(uint32_t raw) {
+  uint64_t r;
+  asm("{\n\t.reg .b32 lo, hi;\n\tshl.b32 lo, %1, 16;\n\tand.b32 hi, %1, 0xffff0000;\n\tmov.b64 %0, {lo, hi};\n\t}" : "=l"(r) : "r"(raw));
+  return r;
+}
+B2T_DEVICE uint32_t f2_to_bf2(uint64_t v) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.bf16x2.f32 %0, hi, lo;\n\t}" : "=r"(r) : "l"(v));
+  return r;
+}
+
+// kVar: bit 0 = tap loop on scalar FFMA instead of FFMA2; bits 1, 2 = measurement only (no LayerNorm tail / no tap loop)
+template <int kVar>
+__global__ void __launch_bounds__(kThreads, 1)
+dwconv_ring2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w_dw,
+                    const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                    const int32_t* __restrict__ row_off, const int32_t* __restrict__ ctile_clip,
+                    const int32_t* __restrict__ ctile_t0, int n_items, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ float s_part[2][16][32];                  // [sub-tile parity][warp][value]: value t = sum a, 16 + t = sum a^2 of row t
+  __shared__ float2 s_ab[16][kTT];                     // per warp: (rstd, -mean * rstd) of the 16 rows
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t bar_pro = ring_s + kRing * kRowBytes, bar_in0 = bar_pro + 8, bar_in1 = bar_pro + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = tid * 2;
+  if (tid == 0) {
+    mbar_init_(bar_pro, 1); mbar_init_(bar_in0, 1); mbar_init_(bar_in1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint64_t wv[kK];
+#pragma unroll
+  for (int k = 0; k < kK; ++k) {
+    const float2 wk = __ldg(reinterpret_cast<const float2*>(w_dw + (size_t)k * kC + c));
+    wv[k] = pk2(bf16_round(wk.x), bf16_round(wk.y));
+  }
+  const uint64_t gh = pk2(0.5f * __ldg(ln_w + c), 0.5f * __ldg(ln_w + c + 1));     // g / 2
+  const uint64_t bh = pk2(0.5f * __ldg(ln_b + c), 0.5f * __ldg(ln_b + c + 1));     // b / 2
+  const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4, up2_ = lane & 2, up1 = lane & 1;
+  __syncthreads();
+
+  const int per = (n_items + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(n_items, i0 + per);
+  int prev_clip = -1, prev_t0 = -1;
+  uint32_t n_pro = 0, n_issued = 0, n_waited = 0, n_sub = 0;      // barrier use counts (identical in every thread)
+#pragma unroll 1
+  for (int item = i0; item < i1; ++item) {
+    const int clip = ctile_clip[item], tile0 = ctile_t0[item];
+    const int r0 = row_off[clip], rows = row_off[clip + 1] - r0;
+    const bool chained = (clip == prev_clip && tile0 == prev_t0 + kSub * kTT);
+    const bool next_chained = (item + 1 < i1) && ctile_clip[item + 1] == clip;
+    prev_clip = clip; prev_t0 = tile0;
+    if (!chained) {
+      __syncthreads();                                   // nobody still reads the ring
+      if (tid == 0) {
+        const int first = max(0, tile0 - (kK - 1)), last = min(rows, tile0 + kTT);
+        const uint32_t bytes = (uint32_t)(last - first) * kRowBytes;
+        mbar_expect_(bar_pro, bytes);
+        bulk_g2s(ring_s + (uint32_t)((first - tile0 + 32) & (kRing - 1)) * kRowBytes, x + (size_t)(r0 + first) * kC, bytes, bar_pro);
+      }
+      if (tile0 == 0) {
+        uint4* z = reinterpret_cast<uint4*>(ring + 2 * kRowBytes);
+        for (int i = tid; i < 30 * kRowBytes / 16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+      }
+      mbar_wait_(bar_pro, n_pro & 1u);
+      ++n_pro;
+    }
+#pragma unroll 1
+    for (int sub = 0; sub < kSub; ++sub) {
+      const int T = tile0 + sub * kTT;
+      if (T >= rows) break;
+      // prefetch the 16 rows the next sub-tile adds (also across a chained item boundary); every thread is past the
+      // block barrier of the previous sub-tile, i.e. past its last read of the slots this overwrites
+      const bool want_next = (T + kTT < rows) && (sub + 1 < kSub || next_chained);
+      if (want_next && tid == 0) {
+        const int n = min(kTT, rows - (T + kTT));
+        const uint32_t bar = (n_issued & 1u) ? bar_in1 : bar_in0;
+        mbar_expect_(bar, (uint32_t)n * kRowBytes);
+        bulk_g2s(ring_s + (uint32_t)((sub * kTT + kTT + 32) & (kRing - 1)) * kRowBytes, x + (size_t)(r0 + T + kTT) * kC,
+                 (uint32_t)n * kRowBytes, bar);
+      }
+      if (sub > 0 || chained) {                          // rows T..T+15 arrived with the chunk issued one step ago
+        mbar_wait_((n_waited & 1u) ? bar_in1 : bar_in0, (n_waited >> 1) & 1u);
+        ++n_waited;
+      }
+      if (want_next) ++n_issued;
+
+      uint64_t av[kTT];
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) av[t] = 0ull;
+      // input row (T - 30 + j), j = 0..45, contributes to output t with tap k = j - t  (0 <= k <= 30)
+#pragma unroll
+      for (int j = 0; j < kTT + kK - 1; ++j) {
+        const uint32_t slot = (uint32_t)((sub * kTT + 2 + j) & (kRing - 1));
+        const uint64_t v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(ring + slot * kRowBytes + tid * 4));
+        if (kVar & 4) {
+          if (j == 0) av[0] = v;
+          continue;
+        }
+#pragma unroll
+        for (int t = 0; t < kTT; ++t) {
+          const int k = j - t;
+          if (k >= 0 && k < kK) {
+            if (kVar & 1) {
+              const float2 a = up2(av[t]), w = up2(wv[k]), vv = up2(v);
+              av[t] = pk2(fmaf(w.x, vv.x, a.x), fmaf(w.y, vv.y, a.y));
+            } else {
+              av[t] = fma2p(wv[k], v, av[t]);
+            }
+          }
+        }
+      }
+      if (kVar & 2) {
+        __nv_bfloat16* orow = out + (size_t)(r0 + T) * kC + c;
+#pragma unroll
+        for (int t = 0; t < kTT; ++t)
+          if (t < rows - T) *reinterpret_cast<uint32_t*>(orow + (size_t)t * kC) = f2_to_bf2(av[t]);
+        __syncthreads();
+        continue;
+      }
+      // conv output rounded to bf16 (the value LayerNorm sees under autocast), statistics, first butterfly step fused:
+      // lanes 0..15 keep the sums, lanes 16..31 the sums of squares of the 16 rows
+      float w16[16];
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) {
+        av[t] = bf2_to_f2(f2_to_bf2(av[t]));
+        const float2 a = up2(av[t]);
+        const float s1 = a.x + a.y, s2 = fmaf(a.y, a.y, a.x * a.x);
+        w16[t] = (up16 ? s2 : s1) + __shfl_xor_sync(0xffffffffu, up16 ? s1 : s2, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        w16[i] = (up8 ? w16[i + 8] : w16[i]) + __shfl_xor_sync(0xffffffffu, up8 ? w16[i] : w16[i + 8], 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        w16[i] = (up4 ? w16[i + 4] : w16[i]) + __shfl_xor_sync(0xffffffffu, up4 ? w16[i] : w16[i + 4], 4);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        w16[i] = (up2_ ? w16[i + 2] : w16[i]) + __shfl_xor_sync(0xffffffffu, up2_ ? w16[i] : w16[i + 2], 2);
+      const float mine = (up1 ? w16[1] : w16[0]) + __shfl_xor_sync(0xffffffffu, up1 ? w16[0] : w16[1], 1);
+      // lane l now holds the warp's total of value l (l < 16: sum a of row l, l >= 16: sum a^2 of row l - 16)
+      const uint32_t par = n_sub & 1u;
+      ++n_sub;
+      s_part[par][warp][lane] = mine;
+      __syncthreads();                                   // the only block barrier of the sub-tile
+      float tot = 0.f;
+#pragma unroll
+      for (int wi = 0; wi < 16; ++wi) tot += s_part[par][wi][lane];
+      const float sq = __shfl_down_sync(0xffffffffu, tot, 16);
+      if (lane < kTT) {
+        const float mean = tot * (1.0f / kC);
+        const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / kC)), 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        s_ab[warp][lane] = make_float2(rstd, -mean * rstd);
+      }
+      __syncwarp();
+      __nv_bfloat16* orow = out + (size_t)(r0 + T) * kC + c;
+      const int nvalid = rows - T;
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) {
+        const float2 ab = s_ab[warp][t];
+        const uint64_t scale = mul2p(pk2(ab.x, ab.x), gh);           // rstd * g / 2
+        const uint64_t off = fma2p(pk2(ab.y, ab.y), gh, bh);         // b / 2 - mean * rstd * g / 2
+        const uint64_t h = fma2p(av[t], scale, off);                 // y / 2
+        const float2 hf = up2(h);
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(hf.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(hf.y));
+        const uint32_t o = f2_to_bf2(fma2p(h, pk2(t0, t1), h));      // swish(y) = y/2 + y/2 * tanh(y/2)
+        if (t < nvalid) *reinterpret_cast<uint32_t*>(orow + (size_t)t * kC) = o;
+      }
+      // s_ab[warp] is rewritten only behind the next sub-tile's block barrier
+    }
+  }
+}
+
 }  // namespace
 
-bool g_dwconv_ring = true;   // b2t_set_option("dwconv_ring", 0/1)
+int g_dwconv_ring = 2;   // b2t_set_option("dwconv_ring", 0 = direct loads, 1 = round-1 ring kernel, 2 = ring + lean LayerNorm tail)
 
 extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float* ln_weight,
                                    const float* ln_bias, const b2t_batch* b, void* out,
@@ -357,7 +569,25 @@ extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float
   if (rc != B2T_OK) return rc;
   if (b->n_ctiles <= 0) return B2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == B2T_PREC_BF16 && g_dwconv_ring) {
+  if (precision == B2T_PREC_BF16 && g_dwconv_ring >= 2) {
+    int grid = b2t_num_sms();
+    if (b->n_ctiles < grid) grid = b->n_ctiles;
+#define B2T_RING2(V)                                                                                                  \
+  do {                                                                                                                \
+    B2T_SMEM_OPT_IN(kRingSmem, dwconv_ring2_kernel<V>);                                                               \
+    dwconv_ring2_kernel<V><<<grid, kThreads, kRingSmem, st>>>((const __nv_bfloat16*)x, w_dw, ln_weight, ln_bias,      \
+        b->row_off, b->ctile_clip, b->ctile_t0, b->n_ctiles, (__nv_bfloat16*)out);                                    \
+  } while (0)
+    switch (g_dwconv_ring) {
+      case 2: B2T_RING2(0); break;
+      case 3: B2T_RING2(1); break;
+      case 4: B2T_RING2(2); break;      // measurement variants: wrong results by construction
+      case 5: B2T_RING2(3); break;
+      case 6: B2T_RING2(4); break;
+      default: B2T_REQUIRE(false, B2T_ERR_ARG, "dwconv_ring: unknown variant");
+    }
+#undef B2T_RING2
+  } else if (precision == B2T_PREC_BF16 && g_dwconv_ring) {
     B2T_SMEM_OPT_IN(kRingSmem, dwconv_ring_kernel);
     int grid = b2t_num_sms();
     if (b->n_ctiles < grid) grid = b->n_ctiles;

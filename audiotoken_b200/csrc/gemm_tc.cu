@@ -507,7 +507,7 @@ void b2t_seanet_set_sub_frames(int n);   // seanet_tc.cu
 void b2t_seanet_set_lstm_pdl(int on);
 void b2t_seanet_set_lstm_overlap(int on);
 void b2t_seanet_set_l0_fused(int on);
-extern bool g_dwconv_ring;         // dwconv.cu
+extern int g_dwconv_ring;          // dwconv.cu
 extern bool g_ffn_resid_epilogue;  // pipeline.cu
 
 extern "C" int b2t_set_option(const char* name, int value) {
@@ -516,7 +516,7 @@ extern "C" int b2t_set_option(const char* name, int value) {
   if (std::string(name) == "ffn_resid_epilogue") { g_ffn_resid_epilogue = value != 0; return B2T_OK; }
   if (std::string(name) == "test_trap") { return value ? b2t_test_trap(value == 2) : B2T_OK; }   // 2: through the mapped host record
   if (std::string(name) == "debug_sync") { b2t_set_debug_sync(value); return B2T_OK; }
-  if (std::string(name) == "dwconv_ring") { g_dwconv_ring = value != 0; return B2T_OK; }
+  if (std::string(name) == "dwconv_ring") { g_dwconv_ring = value; return B2T_OK; }
   if (std::string(name) == "seanet_l0_fused") { b2t_seanet_set_l0_fused(value); return B2T_OK; }
   if (std::string(name) == "lstm_pdl") { b2t_seanet_set_lstm_pdl(value); return B2T_OK; }
   if (std::string(name) == "lstm_overlap") { b2t_seanet_set_lstm_overlap(value); return B2T_OK; }

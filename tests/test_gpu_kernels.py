@@ -335,6 +335,49 @@ def test_dwconv_ln_swish(cuda_device, precision):
     assert rel_err(out.float(), bf(ref) if emu else ref) < (1e-2 if emu else 2e-5)
 
 
+@pytest.mark.parametrize('dc', [0.0, 6.0])
+def test_dwconv_ring_variants_agree(cuda_device, dc):
+    """The three bf16 implementations (direct loads, round-1 ring, round-2 ring with the one-pass LayerNorm tail) against an
+    fp64 evaluation of the formula: a clip longer than several 64-row items (chained ring), clips that start inside a
+    sub-tile's halo, a 1-row clip; `dc` adds a per-row offset of 6 standard deviations (mean^2 >> variance is the worst case
+    for var = E[a^2] - mean^2)."""
+    rows = [700, 16, 33, 1, 130, 64, 65]
+    plan = _attn_plan(rows, rows)
+    g = torch.Generator().manual_seed(11)
+    M = sum(rows)
+    x = bf(torch.randn(M, 1024, generator=g) + dc * torch.randn(M, 1, generator=g))
+    wd = torch.randn(1024, 31, generator=g) * 0.25
+    lw, lb = torch.randn(1024, generator=g) * 0.1 + 1, torch.randn(1024, generator=g) * 0.1
+    outs, off = [], 0
+    for T in rows:
+        h = x[off:off + T].double().t().unsqueeze(0)
+        c = torch.nn.functional.conv1d(torch.nn.functional.pad(h, (30, 0)), bf(wd).double().unsqueeze(1), groups=1024)[0].t()
+        y = torch.nn.functional.layer_norm(bf(c.float()).double(), (1024,), lw.double(), lb.double(), 1e-5)
+        outs.append(y * torch.sigmoid(y))
+        off += T
+    ref = torch.cat(outs, 0)
+    lib = L.load()
+    got = {}
+    try:
+        for mode in (0, 1, 2):
+            L.check(lib.b2t_set_option(b'dwconv_ring', mode), 'dwconv_ring')
+            got[mode] = ops.dwconv_ln_swish(x.to(cuda_device, torch.bfloat16), wd.t().contiguous().to(cuda_device), lw.to(cuda_device),
+                                            lb.to(cuda_device), plan, 'bf16').double().cpu()
+    finally:
+        L.check(lib.b2t_set_option(b'dwconv_ring', 2), 'dwconv_ring')
+    refb = bf(ref.float()).double()
+    for mode, o in got.items():
+        # an output is the bf16 rounding of a value within fp32 rounding of the formula — except where the fp32 conv sum sits
+        # on a bf16 rounding boundary and the LayerNorm input moves by one ulp (a few outputs in 10^4)
+        err = ((o - ref).abs() / (ref.abs() + 2e-2)).max().item()
+        assert err < 4e-2, (mode, err)
+        assert (o != refb).float().mean().item() < 2e-3, mode
+    for mode in (0, 2):
+        differ = (got[mode] != got[1]).float().mean().item()
+        assert differ < 2e-3, (mode, differ)                     # one bf16 ulp on a few outputs at most
+        assert (got[mode] - got[1]).abs().max().item() <= 4e-2 * max(1.0, ref.abs().max().item() / 4)
+
+
 # ---------------------------------------------------------------------------------------------- VQ
 @pytest.mark.parametrize('impl', [L.IMPL_SIMT, L.IMPL_TENSOR])
 @pytest.mark.parametrize('M,D,K', [(1000, 1024, 2048), (777, 1024, 1000), (300, 128, 1024), (64, 256, 1), (50, 64, 3),
