@@ -559,7 +559,14 @@ dwconv_ring2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 
 }  // namespace
 
-int g_dwconv_ring = 2;   // b2t_set_option("dwconv_ring", 0 = direct loads, 1 = round-1 ring kernel, 2 = ring + lean LayerNorm tail)
+int b2t_dwconv_mma_launch(const void* x, const float* w_dw, const float* ln_w, const float* ln_b, const b2t_batch* b, void* out,
+                          int variant, cudaStream_t st);   // dwconv_mma.cu
+
+// b2t_set_option("dwconv_ring", v): 0 = direct loads, 1 = round-1 ring kernel, 2 = ring + lean LayerNorm tail (default),
+// 3 = the same on scalar FFMA, 4-6 = measurement variants (no tail / no taps: wrong results by construction),
+// 7 / 8 = tensor-core formulation (dwconv_mma.cu: m16n8k16 / m16n8k8 steps).  Measured per 64 806-row launch, stand-alone:
+// 259 / 171 / 162 / 167 us and 149 / 145 us; in the power-capped pipeline the step time is the same with 2 and 8.
+int g_dwconv_ring = 2;
 
 extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float* ln_weight,
                                    const float* ln_bias, const b2t_batch* b, void* out,
@@ -569,6 +576,8 @@ extern "C" int b2t_dwconv_ln_swish(const void* x, const float* w_dw, const float
   if (rc != B2T_OK) return rc;
   if (b->n_ctiles <= 0) return B2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == B2T_PREC_BF16 && (g_dwconv_ring == 7 || g_dwconv_ring == 8))
+    return b2t_dwconv_mma_launch(x, w_dw, ln_weight, ln_bias, b, out, g_dwconv_ring - 7, st);
   if (precision == B2T_PREC_BF16 && g_dwconv_ring >= 2) {
     int grid = b2t_num_sms();
     if (b->n_ctiles < grid) grid = b->n_ctiles;

@@ -69,7 +69,9 @@ int b2t_device_check(int device);
  *                           5 = two-pass with the row sums on the tensor core as well, 2 = single pass with lazily
  *                           rescaled split accumulators, 3 = the same, persistent over (query tile, head) items
  *   "attn_ctas" n           cap the persistent attention kernel's grid (tests; 0 = 2 CTAs per SM)
- *   "dwconv_ring" 0/1, "seanet_l0_fused" 0/1, "lstm_pdl" 0/1, "lstm_overlap" 0/1 (layer 2 on a side stream one chunk
+ *   "dwconv_ring" 0 = direct loads, 1 = round-1 shared-memory ring, 2 = ring + lean LayerNorm tail (default), 7 / 8 = tensor-core
+ *                 formulation (mma.sync over time, csrc/dwconv_mma.cu); 3-6 are measurement variants
+ *   "seanet_l0_fused" 0/1, "lstm_pdl" 0/1, "lstm_overlap" 0/1 (layer 2 on a side stream one chunk
  *   behind layer 1), "seanet_sub_frames" n, "rvq_tensor" 0/1                                                         */
 int b2t_set_option(const char* name, int value);
 /* Device-side protocol time-outs of the register-critical kernels (single-pass attention) do not printf: they store

@@ -359,7 +359,7 @@ def test_dwconv_ring_variants_agree(cuda_device, dc):
     lib = L.load()
     got = {}
     try:
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 7, 8):
             L.check(lib.b2t_set_option(b'dwconv_ring', mode), 'dwconv_ring')
             got[mode] = ops.dwconv_ln_swish(x.to(cuda_device, torch.bfloat16), wd.t().contiguous().to(cuda_device), lw.to(cuda_device),
                                             lb.to(cuda_device), plan, 'bf16').double().cpu()
@@ -372,7 +372,7 @@ def test_dwconv_ring_variants_agree(cuda_device, dc):
         err = ((o - ref).abs() / (ref.abs() + 2e-2)).max().item()
         assert err < 4e-2, (mode, err)
         assert (o != refb).float().mean().item() < 2e-3, mode
-    for mode in (0, 2):
+    for mode in (0, 2, 7, 8):
         differ = (got[mode] != got[1]).float().mean().item()
         assert differ < 2e-3, (mode, differ)                     # one bf16 ulp on a few outputs at most
         assert (got[mode] - got[1]).abs().max().item() <= 4e-2 * max(1.0, ref.abs().max().item() / 4)
