@@ -335,20 +335,27 @@ def run_workload(ctx: Ctx, workload: str, steps: int, warmup: int, instrument: b
             enc.encode_plan(w, plan)
             launches[0] += enc.last_launches
 
-    copy_stream = torch.cuda.Stream(device=device)
+    # end to end: uploads and token read-backs on their own streams (two copy engines), two staging buffers that alternate
+    # over the batches of ALL steps — the upload of the next batch (of this step or the next one) runs under the encode of
+    # the current one, as in the file loop (audiotoken_b200/core.py).  One stream for both directions would queue every
+    # upload behind the previous batch's read-back, i.e. behind its encode: no overlap at all (acoustic: one batch per step).
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
     max_samples = max(w.numel() for w in dev_waves)
     stage = [torch.empty(max_samples, dtype=torch.float32, device=device) for _ in range(2)]
+    free_ev = [None, None]
+    seq = [0]
 
     def step_e2e():
         comp = torch.cuda.current_stream()
-        free_ev = [None, None]
-        for i, (idx, hw, ht) in enumerate(zip(batches, host_waves, host_tokens)):
-            buf = stage[i % 2][:hw.numel()]
-            with torch.cuda.stream(copy_stream):
-                if free_ev[i % 2] is not None:
-                    copy_stream.wait_event(free_ev[i % 2])
+        for idx, hw, ht in zip(batches, host_waves, host_tokens):
+            k = seq[0] % 2
+            seq[0] += 1
+            buf = stage[k][:hw.numel()]
+            with torch.cuda.stream(h2d_stream):
+                if free_ev[k] is not None:
+                    h2d_stream.wait_event(free_ev[k])                            # the encode that last read this buffer
                 buf.copy_(hw, non_blocking=True)
-                ready = copy_stream.record_event()
+                ready = h2d_stream.record_event()
             ln = lengths[idx]
             offs = np.zeros(len(idx), dtype=np.int64)
             offs[1:] = np.cumsum(ln)[:-1]
@@ -357,12 +364,12 @@ def run_workload(ctx: Ctx, workload: str, steps: int, warmup: int, instrument: b
             tokens, _ = enc.encode_plan(buf, plan)
             tokens = tokens.view(-1)
             done = comp.record_event()
-            free_ev[i % 2] = done
-            tokens.record_stream(copy_stream)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done)
+            free_ev[k] = done
+            tokens.record_stream(d2h_stream)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
                 ht.copy_(tokens, non_blocking=True)
-        comp.wait_stream(copy_stream)
+        comp.wait_stream(d2h_stream)            # the step's tokens are on the host before the step (and the timed region) ends
 
     def timed(fn, n):
         ctx.barrier()
