@@ -295,6 +295,12 @@ dwconv_mma_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restr
   }
 }
 
+// Measured and rejected in the same session (profiles/r02_dwconv_ab.txt): a 1024-thread version that stores the un-normalised
+// rows to `out` right after the MMAs, keeps nothing in registers (64 per thread, 8 warps per scheduler) and normalises in a
+// second phase from L2 — 177 us.  The formulation moves 1.2 MB of A fragments and 0.6 MB of B fragments through shared
+// memory per 64-row item (every window word is read by nine k-steps), about 14 000 wavefronts per item whoever issues
+// them; twice the warps only queue up behind the same shared-memory pipe.
+
 }  // namespace
 
 // bf16 tensor-core path of b2t_dwconv_ln_swish (dwconv.cu dispatches here for dwconv_ring = 7)
