@@ -312,15 +312,17 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
                     write_futs.append((s_.file_name, writers.submit(write, s_.file_name, self.per_file.pop(s_.file_name))))
                     stats['files'] += 1
 
-    def prepare(window, raws=None):
+    def prepare(window, raws=None, out_alloc=None):
         """window: list of (path, sr, pcm) -> WindowState (PCM decode + resampling on the device, segment rules);
-        raws[i] = the payload of file i already on the device (prepare_async) or None."""
+        raws[i] = the payload of file i already on the device (prepare_async) or None; out_alloc = bump allocator over
+        the window's waveform buffer."""
         segs, nbytes = [], 0
         for wi, (path, sr, pcm) in enumerate(window):
             try:
                 nbytes += pcm.nbytes
                 for ci, wave in enumerate(aio.convert_chunks(sr, pcm, sample_rate, chunk_size, device if on_gpu else None,
-                                                             raw=raws[wi] if raws else None)):
+                                                             raw=raws[wi] if raws else None,
+                                                             out_alloc=out_alloc if raws and raws[wi] is not None else None)):
                     for s_ in aio.iter_segments(wave, path, sample_rate, token_rate, chunk_size):
                         s_.chunk_index = ci                # one segment per streamed chunk (datasets.py:88-105)
                         segs.append(s_)
@@ -344,20 +346,37 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
         the compute stream is busy with the batches of the current one"""
         if not on_gpu:
             return prepare(window), None
+        # ONE device buffer per window for the PCM payloads and one for the decoded waveforms: per-file tensors would be
+        # per-file cudaMallocs whenever the side streams' allocator pools are cold (measured: 2.3 s of 3.3 s for 1250 files)
+        ok = [pcm.dtype in (np.int16, np.float32) and pcm.ndim <= 2 for _, _, pcm in window]
+        offs, total = [], 0
+        for (_, _, pcm), good in zip(window, ok):
+            offs.append(total)
+            if good:
+                total += (pcm.nbytes + 15) // 16 * 16
+        n_out = sum(sum((n + 3) // 4 * 4 for n in aio.chunk_output_lengths(sr, int(pcm.shape[0]), sample_rate, chunk_size))
+                    for (_, sr, pcm), good in zip(window, ok) if good)
         with torch.cuda.stream(upload_stream):
+            raw_all = torch.empty(max(total, 16), dtype=torch.uint8, device=device)
             raws = []
-            for _, _, pcm in window:
+            for (_, _, pcm), good, off in zip(window, ok, offs):
                 try:
-                    raws.append(aio.upload_pcm(pcm, device))
+                    raws.append(aio.upload_pcm(pcm, device, raw_all[off:off + pcm.nbytes]) if good else None)
                 except Exception:  # noqa: BLE001 -- prepare() meets the same error and reports it for the file
                     raws.append(None)
             uploaded = upload_stream.record_event()
         with torch.cuda.stream(ingest_stream):
             ingest_stream.wait_event(uploaded)
-            for r in raws:
-                if r is not None:
-                    r.record_stream(ingest_stream)
-            st_ = prepare(window, raws)
+            raw_all.record_stream(ingest_stream)
+            wave_all = torch.empty(max(n_out, 1), dtype=torch.float32, device=device)
+            cursor = [0]
+
+            def out_alloc(n):
+                a = cursor[0]
+                cursor[0] = a + (n + 3) // 4 * 4                    # every chunk starts 16-byte aligned
+                return wave_all[a:a + n].view(1, n)
+
+            st_ = prepare(window, raws, out_alloc)
             ready = ingest_stream.record_event()
         return st_, ready
 

@@ -8,7 +8,7 @@ on the host in float64 -> float32, strips them to their non-zero support and kee
 from __future__ import annotations
 
 import math
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -57,14 +57,18 @@ class GpuResampler:
     def out_len(self, length: int) -> int:
         return int(math.ceil(self.new * length / self.orig))
 
-    def __call__(self, audio: torch.Tensor) -> torch.Tensor:
+    def __call__(self, audio: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """audio [C, L] (any strides, e.g. the transposed view of an interleaved PCM buffer), int16 or float32, on
-        the device -> float32 [1, L'] on the device."""
+        the device -> float32 [1, L'] on the device (`out`: caller-owned contiguous [1, L'] destination, e.g. a slice of
+        one buffer per window of files — the streaming loop must not allocate per file, see core.encode_files)."""
         assert audio.is_cuda and audio.dim() == 2 and audio.dtype in (torch.int16, torch.float32)
         c, length = audio.shape
         if c not in (1, 2):
             raise RuntimeError('Only mono or stereo audio is supported')
-        out = torch.empty(1, self.out_len(length), dtype=torch.float32, device=audio.device)
+        if out is None:
+            out = torch.empty(1, self.out_len(length), dtype=torch.float32, device=audio.device)
+        elif tuple(out.shape) != (1, self.out_len(length)) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f'out must be a contiguous float32 [1, {self.out_len(length)}] tensor')
         if out.numel() == 0:
             return out
         with torch.cuda.device(audio.device):
@@ -79,13 +83,19 @@ class GpuResampler:
 _CACHE: Dict[Tuple[int, int, str], GpuResampler] = {}
 
 
-def convert_audio(audio: torch.Tensor, sample_rate: int, target_sample_rate: int, device='cuda:0') -> torch.Tensor:
-    """[C, L] int16 PCM or float32 -> mono float32 [1, L'] at the target rate, on `device` (reference utils.py:26-44).
-    Equal rates run the same kernel with the identity filter (decode + mix-down only)."""
+def resampler(sample_rate: int, target_sample_rate: int, device='cuda:0') -> GpuResampler:
     dev = torch.device(device)
     key = (int(sample_rate), int(target_sample_rate), str(dev))
     if key not in _CACHE:
         _CACHE[key] = GpuResampler(sample_rate, target_sample_rate, dev)
+    return _CACHE[key]
+
+
+def convert_audio(audio: torch.Tensor, sample_rate: int, target_sample_rate: int, device='cuda:0',
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[C, L] int16 PCM or float32 -> mono float32 [1, L'] at the target rate, on `device` (reference utils.py:26-44).
+    Equal rates run the same kernel with the identity filter (decode + mix-down only)."""
+    dev = torch.device(device)
     if audio.shape[0] not in (1, 2):
         raise RuntimeError('Only mono or stereo audio is supported')
-    return _CACHE[key](audio.to(dev, non_blocking=True))
+    return resampler(sample_rate, target_sample_rate, dev)(audio.to(dev, non_blocking=True), out)

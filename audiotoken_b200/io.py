@@ -150,19 +150,33 @@ def read_wav_raw(path) -> Tuple[int, np.ndarray]:
     return int(sr), data
 
 
-def upload_pcm(data: np.ndarray, device) -> Optional[torch.Tensor]:
+def upload_pcm(data: np.ndarray, device, dst: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """PCM16 / float32 payload of one file -> device tensor [1, n] (None for the encodings the device path does not take).
     The streaming file loop calls this for every file of a window on a copy-only stream BEFORE any ingest kernel of the
     window is queued: a pageable host->device copy blocks the calling thread until everything queued before it on its
     stream has run, and an ingest kernel queued between two copies runs only when the encoder's persistent kernels let
-    go of an SM (0.3-1 ms) — per file, that serialised the host behind the device."""
+    go of an SM (0.3-1 ms) — per file, that serialised the host behind the device.  `dst`: a uint8 device slice of at
+    least data.nbytes (16-byte aligned) to copy into instead of allocating."""
     if data.dtype not in (np.int16, np.float32):
         return None
-    return torch.from_numpy(np.ascontiguousarray(data).reshape(1, -1)).to(device, non_blocking=True)
+    src = torch.from_numpy(np.ascontiguousarray(data).reshape(1, -1))
+    if dst is None:
+        return src.to(device, non_blocking=True)
+    view = dst[:src.numel() * src.element_size()].view(src.dtype).view(1, -1)
+    view.copy_(src, non_blocking=True)
+    return view
+
+
+def chunk_output_lengths(sr: int, n_samples: int, model_sample_rate: int, chunk_size: int) -> List[int]:
+    """Samples each streamed chunk of a file has after resampling (what convert_chunks will return)."""
+    g = math.gcd(int(sr), int(model_sample_rate))
+    orig, new = int(sr) // g, int(model_sample_rate) // g
+    step = int(chunk_size * sr)
+    return [int(math.ceil(new * min(step, n_samples - a) / orig)) for a in range(0, n_samples, step)]
 
 
 def convert_chunks(sr: int, data: np.ndarray, model_sample_rate: int, chunk_size: int, device=None,
-                   raw: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+                   raw: Optional[torch.Tensor] = None, out_alloc=None) -> List[torch.Tensor]:
     """Second half of the reference's batch reader (utils.py:82-101): the PCM stream is cut into chunks of `chunk_size`
     seconds AT ITS OWN sample rate and every chunk is resampled on its own — so a file whose rate differs from the
     model's has filter edges at every chunk boundary.  Returns fp32 [1, L_i] chunks; on a CUDA `device` PCM decode and
@@ -186,8 +200,12 @@ def convert_chunks(sr: int, data: np.ndarray, model_sample_rate: int, chunk_size
     out = []
     for a in range(0, raw.shape[1], step):
         piece = raw[:, a:a + step]
-        out.append(ingest.convert_audio(piece, sr, model_sample_rate, device) if on_gpu
-                   else convert_audio(piece, sr, model_sample_rate))
+        if on_gpu:
+            # out_alloc(n) -> contiguous float32 [1, n] device tensor (a slice of the window's buffer in the file loop)
+            dst = out_alloc(ingest.resampler(sr, model_sample_rate, device).out_len(piece.shape[1])) if out_alloc else None
+            out.append(ingest.convert_audio(piece, sr, model_sample_rate, device, out=dst))
+        else:
+            out.append(convert_audio(piece, sr, model_sample_rate))
     return out
 
 
