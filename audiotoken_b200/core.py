@@ -411,8 +411,9 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
 
             carry = []
 
-            def next_window():
-                """whole files up to window_rows token rows (None at the end); the readers keep prefetching"""
+            def next_window(limit=None):
+                """whole files up to `limit` (default window_rows) token rows (None at the end); the readers keep prefetching"""
+                limit = window_rows if limit is None else limit
                 window, w_rows = list(carry), sum(est_rows(sr, pcm) for _, sr, pcm in carry)
                 carry.clear()
                 top_up()
@@ -425,7 +426,7 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
                         continue
                     sr, pcm = res
                     r = est_rows(sr, pcm)
-                    if window and w_rows + r > window_rows:
+                    if window and w_rows + r > limit:
                         carry.append((path, sr, pcm))
                         return window
                     window.append((path, sr, pcm))
@@ -440,7 +441,8 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
                 stats[key] += time.perf_counter() - t
                 return r
 
-            w0 = timed('t_read_wait', next_window)
+            # the first window is one batch: the device starts after a quarter of the read + decode latency of a full window
+            w0 = timed('t_read_wait', next_window, min(window_rows, row_budget))
             cur = timed('t_prepare', prepare_async, w0) if w0 else None
             while cur is not None:
                 st_, ready = cur
