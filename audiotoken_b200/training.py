@@ -98,3 +98,70 @@ class CodebookTrainer:
         elif quant is not None:
             raise NotImplementedError('return_quantized is only provided by the training step')
         return (quant.reshape(*lead, D) if quant is not None else None), i32.long().reshape(lead), loss
+
+
+
+def iter_embeddings(encoder, files, chunk_size: int = 30, max_rows: int = 65536, layer: Optional[int] = None,
+                    padded_rows: bool = False):
+    """LayerNormed hidden states of `layer` (default: the encoder's output layer) for a list of audio files, one fp32
+    device tensor [rows, 1024] per ragged batch of at most `max_rows` token rows: the feature stream the clustering script
+    trains on (``get_features_batch``, cluster_tokens.py:83-136: affine-free LayerNorm of ``encoded_audio[l]``, reshaped to
+    ``[B*T, D]``).  The reference pads every segment to ``chunk_size`` seconds and trains on the padded rows as well;
+    `padded_rows=True` reproduces that (T rows per segment), the default feeds only the rows that become tokens.
+    `encoder` is a Wav2VecBertEncoder; files are read, decoded and resampled on its device (io.read_audio_chunks)."""
+    from . import io as aio
+    from .packing import bucket_by_rows, length_tokens, plan_semantic
+    sr, rate = encoder.config.model_sample_rate, encoder.config.model_token_rate
+    layer = encoder.n_layers if layer is None else int(layer)
+    pad = int(chunk_size * sr)
+    pend, pend_rows = [], []                       # segments waiting for a batch
+
+    def flush():
+        for idx in bucket_by_rows(pend_rows, max_rows):
+            clips = [pend[i] for i in idx]
+            lengths = [int(c.numel()) for c in clips]
+            offs = [0]
+            for n in lengths[:-1]:
+                offs.append(offs[-1] + n)
+            plan = plan_semantic(lengths, offs, pad, None if padded_rows else [pend_rows[i] for i in idx])
+            wave = torch.cat([c.reshape(-1) for c in clips]).to(encoder.device, torch.float32)
+            _, hidden = encoder.encode_plan(wave, plan, tap_layer=layer)
+            yield torch.nn.functional.layer_norm(hidden, (hidden.shape[-1],))
+        pend.clear()
+        pend_rows.clear()
+
+    for path in files:
+        for wave in aio.read_audio_chunks(path, sr, chunk_size, encoder.device):
+            for seg in aio.iter_segments(wave, str(path), sr, rate, chunk_size):
+                n = int(seg.wave.numel())
+                pend.append(seg.wave)
+                pend_rows.append(encoder.rows_for(pad) if padded_rows
+                                 else encoder.rows_for_tokens(length_tokens(n, sr, rate), pad))
+        if sum(pend_rows) >= max_rows:
+            yield from flush()
+    if pend:
+        yield from flush()
+
+
+def train_codebook(trainer: CodebookTrainer, batches, outdir: Optional[str] = None, save_freq: int = 10, layer: int = 19,
+                   log=None) -> Dict[str, float]:
+    """The clustering script's training loop (cluster_tokens.py:293-320): one EMA step of `trainer` per batch of
+    embeddings (``_, indices, commit_loss = quantizer(x)``), the commitment loss and the share of active codes reported per
+    batch, a checkpoint ``quantizer__L{layer}_C{K}_ckpt{idx}.pkl`` (``torch.save(state_dict())``) every `save_freq` batches.
+    `batches`: any iterable of fp32 device tensors [rows, D], e.g. iter_embeddings(...)."""
+    import os
+    trainer.train()
+    stats = {'batches': 0, 'rows': 0, 'commit_loss': float('nan'), 'active_fraction': float('nan')}
+    for idx, x in enumerate(batches):
+        _, indices, loss = trainer(x)
+        stats['batches'] += 1
+        stats['rows'] += int(x.shape[0])
+        stats['commit_loss'] = float(loss.item())
+        stats['active_fraction'] = indices.unique().numel() / trainer.codebook_size
+        if log is not None:
+            log(f"batch {idx}: rows {int(x.shape[0])}, commitment loss {stats['commit_loss']:.3f}, "
+                f"active {100 * stats['active_fraction']:.3f} %")
+        if outdir is not None and idx % save_freq == 0:
+            os.makedirs(outdir, exist_ok=True)
+            torch.save(trainer.state_dict(), os.path.join(outdir, f'quantizer__L{layer}_C{trainer.codebook_size}_ckpt{idx}.pkl'))
+    return stats

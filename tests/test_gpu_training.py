@@ -86,3 +86,54 @@ def test_eval_mode_leaves_state_untouched(cuda_device):
     assert torch.equal(tr.embed.cpu(), embed)
     ref, tie = quantize.nearest_centroid(x.reshape(-1, 128), embed)
     assert torch.equal(idx.cpu().reshape(-1)[~tie], ref[~tie])
+
+
+def test_codebook_training_loop_over_files(cuda_device, tmp_path):
+    """The clustering script's loop (cluster_tokens.py:83-136, 293-320) end to end on the device: WAV files -> LayerNormed
+    hidden states of the tapped layer in ragged batches (iter_embeddings) -> one EMA step per batch (train_codebook) ->
+    checkpoints with the reference's names and keys.  The streamed features equal the tap of a direct encoder call, and the
+    loop leaves the same state as calling the trainer on those batches by hand."""
+    import os
+    from audiotoken_b200 import io as aio
+    from audiotoken_b200.encoder import Wav2VecBertEncoder
+    from audiotoken_b200.training import iter_embeddings, train_codebook
+    from audiotoken_b200.packing import plan_semantic
+    from audiotoken_b200.weights import synthetic_waveform
+    SR = 16000
+    files = []
+    for i, n in enumerate([52000, 16000, 33333, 90000]):          # the last one spans two 5 s chunks
+        p = tmp_path / f'train{i}.wav'
+        aio.write_wav(str(p), synthetic_waveform(300 + i, n, SR), SR)
+        files.append(str(p))
+    enc = Wav2VecBertEncoder(device=cuda_device, precision='fp32', n_layers=2)
+    batches = [b.clone() for b in iter_embeddings(enc, files, chunk_size=5, max_rows=300, layer=2)]
+    rows = sum(b.shape[0] for b in batches)
+    assert len(batches) >= 2 and rows == 163 + 50 + 105 + 250 + 32 and all(b.shape[1] == 1024 and b.is_cuda for b in batches)
+    # one of the files, alone, through the operator: same LayerNormed rows somewhere in the stream
+    wave = aio.read_audio_chunks(files[1], SR, 5, cuda_device)[0].reshape(-1)
+    plan = plan_semantic([wave.numel()], [0], 5 * SR, [50])
+    _, tap = enc.encode_plan(wave.contiguous(), plan, tap_layer=2)
+    want = torch.nn.functional.layer_norm(tap, (1024,))
+    allrows = torch.cat(batches)
+    d = torch.cdist(want[:5].double(), allrows.double()).min(dim=1).values
+    assert float(d.max()) < 1e-3 * float(want[:5].double().norm(dim=1).mean())
+
+    K = 64
+    g = torch.Generator().manual_seed(3)
+    init = allrows[torch.randperm(rows, generator=g)[:K].to(allrows.device)].cpu()
+    sd = {'_codebook.embed': init.unsqueeze(0), '_codebook.embed_avg': init.unsqueeze(0).clone(),
+          '_codebook.cluster_size': torch.ones(1, K), '_codebook.initted': torch.tensor([True])}
+    a = CodebookTrainer(1024, K, device=cuda_device); a.load_state_dict(sd)
+    b = CodebookTrainer(1024, K, device=cuda_device); b.load_state_dict(sd)
+    logs = []
+    st = train_codebook(a, iter(batches), outdir=str(tmp_path / 'ckpt'), save_freq=2, layer=2, log=logs.append)
+    for x in batches:
+        b(x)
+    assert st['batches'] == len(batches) and st['rows'] == rows and 0 < st['active_fraction'] <= 1 and len(logs) == len(batches)
+    assert torch.equal(a.embed, b.embed) and torch.equal(a.cluster_size, b.cluster_size)
+    assert not torch.equal(a.embed.cpu(), init)
+    names = sorted(os.listdir(tmp_path / 'ckpt'))
+    assert names[0] == f'quantizer__L2_C{K}_ckpt0.pkl' and len(names) == (len(batches) + 1) // 2
+    ck = torch.load(tmp_path / 'ckpt' / names[-1])
+    assert set(ck) == {'_codebook.initted', '_codebook.cluster_size', '_codebook.embed_avg', '_codebook.embed'}
+    assert tuple(ck['_codebook.embed'].shape) == (1, K, 1024)
