@@ -386,7 +386,8 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
         if ready is not None:
             comp.wait_event(ready)
             for s_ in st_.segs:
-                s_.wave.record_stream(comp)
+                if s_.wave.is_cuda:                      # 8-bit / 32-bit PCM is decoded on the host (io.convert_chunks)
+                    s_.wave.record_stream(comp)
         out = []
         for idx in bucket_by_rows(st_.rows, row_budget):
             out.append((*launch([st_.segs[i].wave for i in idx], [st_.rows[i] for i in idx]), idx))

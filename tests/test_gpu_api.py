@@ -87,3 +87,29 @@ def test_encode_single_inputs(cuda_device, tmp_path):
         tok.encode(123)
     with pytest.raises(AssertionError):
         AudioToken('semantic_m', device='cuda:0', num_codebooks=3)
+
+
+def test_file_loop_mixed_pcm_encodings(cuda_device, tmp_path):
+    """One corpus with PCM16 and float32 payloads (decoded on the device) next to 32-bit and 8-bit PCM (decoded on the
+    host, io.convert_chunks) and a stereo file (rejected, logged, skipped): the same audio gives the same tokens whatever
+    its container encoding.  Samples are multiples of 256, so s / 32768 is exact in all four encodings."""
+    from scipy.io import wavfile
+    g = np.random.default_rng(5)
+    n = SR * 4 + 777
+    s16 = (np.round(8000 * np.sin(np.arange(n) * 0.05) + 1500 * g.standard_normal(n)) // 256 * 256).clip(-32768, 32512).astype(np.int16)
+    indir = tmp_path / 'in'
+    indir.mkdir()
+    wavfile.write(indir / 'p16.wav', SR, s16)
+    wavfile.write(indir / 'p32.wav', SR, s16.astype(np.int32) * 65536)
+    wavfile.write(indir / 'p8.wav', SR, (s16.astype(np.int32) // 256 + 128).astype(np.uint8))
+    wavfile.write(indir / 'f32.wav', SR, (s16.astype(np.float32) / 32768.0))
+    wavfile.write(indir / 'stereo.wav', SR, np.stack([s16, s16], axis=1))
+    tok = AudioToken(tokenizer=Tokenizers.semantic_m, device='cuda:0', n_layers=2, synthetic_weights=True)
+    out = tmp_path / 'out'
+    tok.encode_batch_files(batch_size=4, outdir=str(out), chunk_size=3, audio_dir=str(indir), num_workers=2)
+    ref = np.load(out / 'p16.npy')
+    assert ref.shape == (1, math.ceil(n / SR * 50))
+    for name in ('p32', 'p8', 'f32'):
+        assert np.array_equal(np.load(out / f'{name}.npy'), ref), name
+    assert not (out / 'stereo.npy').exists()
+    assert tok.last_stats['files'] == 4 and len(tok.last_stats['errors']) == 1
