@@ -1,8 +1,8 @@
 // Conformer convolution-module middle on the tensor cores (bf16 production path of b2t_dwconv_ln_swish):
 //   causal depthwise conv1d (k = 31, per clip) -> LayerNorm(1024) -> swish        (HF modeling_wav2vec2_bert.py:213-221)
 //
-// Why: the CUDA-core tap loop of dwconv.cu is bound by register-file bandwidth, not by HBM — every FMA reads a weight, an
-// input and an accumulator that all differ from the previous instruction's (measured on B200, tools/micro/fma_rate.cu and
+// Why: the CUDA-core tap loop of dwconv.cu is bound by register-file bandwidth, not by HBM — every FMA reads a weight and an
+// accumulator that differ from the previous instruction's (only the input is served by the operand reuse cache) (measured on B200, tools/micro/fma_rate.cu and
 // tools/dwconv_ab.py: scalar FFMA 2.2 clk, FFMA2 3.8 clk per warp instruction and SM sub-partition; the tap loop alone is
 // 108 us of the 162 us launch, against an HBM floor of 41 us).  A depthwise conv has no shared operand to build a GEMM
 // from — except along time: for ONE channel pair (2i, 2i+1) and one 64-row item starting at clip row T0
