@@ -56,7 +56,7 @@ res = {'note': f'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram_
 for key, pred, alg, what in (
         ('add_layernorm', lambda k: 'add_layernorm_kernel<__nv_bfloat16, 0>' in k or 'add_layernorm_kernel<__nv_bfloat16, false>' in k, M * 12288,
          'fp32 x read + written (8 KB/row), bf16 d read (2 KB), bf16 LN output written (2 KB)'),
-        ('dwconv_ring', lambda k: 'dwconv_ring_kernel' in k, M * 4096, 'bf16 GLU output read (2 KB/row) + bf16 output written (2 KB/row)'),
+        ('dwconv_ring', lambda k: 'dwconv_ring' in k or 'dwconv_mma' in k, M * 4096, 'bf16 GLU output read (2 KB/row) + bf16 output written (2 KB/row)'),
         ('attention', lambda k: 'attention_tc' in k, M * 8192,
          'bf16 qkv read once (6 KB/row) + bf16 output written (2 KB/row); K/V re-reads by the query tiles of a clip hit L2')):
     c = cls(pred)
