@@ -207,3 +207,15 @@ def test_streaming_file_loop_windows_writes_and_errors(tmp_path, caplog):
         assert got.dtype == np.int16 and got.shape == want.shape and np.array_equal(got, want), f
     with pytest.raises(Exception):
         encode_files(_FakeEncoder(), [str(bad)], aio.sanitize_path(out), sr, 50, chunk, 4, 2, None, on_error='raise')
+
+
+def test_chunk_output_lengths_match_the_host_resampler():
+    """The streaming loop sizes one waveform buffer per window from chunk_output_lengths: it must predict exactly what
+    convert_chunks returns (reference utils.py:82-101: chunks cut at the source rate, each resampled on its own)."""
+    import numpy as np
+    from audiotoken_b200 import io as aio
+    for sr, n, chunk in [(16000, 16000 * 7 + 123, 3), (22050, 22050 * 4 + 17, 3), (8000, 8000 * 2 + 1, 1), (44100, 100000, 30),
+                         (24000, 24000 * 5, 5), (48000, 48001, 1)]:
+        pcm = (np.arange(n) % 200 - 100).astype(np.int16)
+        got = [int(w.shape[-1]) for w in aio.convert_chunks(sr, pcm, 16000, chunk)]
+        assert got == aio.chunk_output_lengths(sr, n, 16000, chunk), (sr, n, chunk, got)
