@@ -30,6 +30,21 @@ from .packing import bucket_by_rows, length_tokens, padded_rows
 
 logger = logging.getLogger('audiotoken_b200')
 
+# side streams of the file loop, one set per device for the life of the process: the caching allocator keeps a pool per
+# stream, so fresh streams per call would meet cold pools (a cudaMalloc per window buffer) on every call
+_SIDE_STREAMS: Dict[str, tuple] = {}
+
+
+def _side_streams(device):
+    """(token read-back, upload, ingest): uploads go on a copy-only stream (a pageable copy blocks the host until its
+    stream has drained, so no kernel may sit in front of it), decode / resampling kernels on a high-priority stream (a
+    few small CTAs that take the first SM the encoder's persistent kernels release)."""
+    key = str(torch.device(device))
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device),
+                              torch.cuda.Stream(device=device, priority=-1))
+    return _SIDE_STREAMS[key]
+
 
 class AudioToken:
     def __init__(self, tokenizer: Union[Tokenizers, str], device: str = "cuda:0", compile: bool = False, **kwargs):
@@ -255,7 +270,7 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
         except Exception as e:  # noqa: BLE001
             return e
 
-    copy_stream = torch.cuda.Stream(device=device) if on_gpu else None
+    copy_stream, upload_stream, ingest_stream = _side_streams(device) if on_gpu else (None, None, None)
     writers = ThreadPoolExecutor(max(1, min(4, num_workers)))
     write_futs = []
 
@@ -334,12 +349,6 @@ def encode_files(encoder, files: Sequence[str], outdir: str, sample_rate: int, t
         stats['segments'] += len(segs)
         stats['windows'] += 1
         return WindowState(segs, rows)
-
-    # side streams of the NEXT window: uploads on a copy-only stream (a pageable copy blocks the host until its stream
-    # has drained, so no kernel may sit in front of it), decode / resampling kernels on a high-priority stream (a few
-    # small CTAs that take the first SM the encoder's persistent kernels release)
-    upload_stream = torch.cuda.Stream(device=device) if on_gpu else None
-    ingest_stream = torch.cuda.Stream(device=device, priority=-1) if on_gpu else None
 
     def prepare_async(window):
         """prepare() on side streams: the PCM upload and the decode / resampling kernels of the NEXT window run while

@@ -449,7 +449,7 @@ def run_files_e2e(ctx: Ctx, n_files: int) -> dict:
         del wave
         tok = AudioToken('semantic_m', device=str(ctx.device), synthetic_weights=True, precision='bf16')
         tok.load_encoder()
-        warm = sorted(os.path.join(indir, f) for f in os.listdir(indir))[:16]
+        warm = sorted(os.path.join(indir, f) for f in os.listdir(indir))[:400]     # more than one window: allocator pools and pinned buffers at their working size
         tok.encode_batch_files(batch_size=ROW_BUDGET // 1500, outdir=os.path.join(root, 'warm'), chunk_size=CHUNK_S, audio_files=warm,
                                num_workers=min(16, os.cpu_count() or 1))
         ctx.barrier()
