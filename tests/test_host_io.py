@@ -219,3 +219,66 @@ def test_chunk_output_lengths_match_the_host_resampler():
         pcm = (np.arange(n) % 200 - 100).astype(np.int16)
         got = [int(w.shape[-1]) for w in aio.convert_chunks(sr, pcm, 16000, chunk)]
         assert got == aio.chunk_output_lengths(sr, n, 16000, chunk), (sr, n, chunk, got)
+
+
+def test_training_feature_stream_batching_on_a_host_stand_in(tmp_path):
+    """iter_embeddings / train_codebook host logic without a GPU: segments are cut by the reference's chunk rules, batches
+    respect the row budget, `padded_rows` switches between the rows that become tokens and the T rows per padded segment
+    the reference trains on (cluster_tokens.py:83-136); the loop reports per batch and writes reference-named checkpoints."""
+    import types
+    import numpy as np
+    import torch
+    from audiotoken_b200 import io as aio
+    from audiotoken_b200 import training
+    from audiotoken_b200.packing import padded_rows
+    from audiotoken_b200.weights import synthetic_waveform
+    SR = 16000
+    files = []
+    for i, n in enumerate([52000, 16000, 33333, 90000]):
+        p = tmp_path / f't{i}.wav'
+        aio.write_wav(str(p), synthetic_waveform(i, n, SR), SR)
+        files.append(str(p))
+
+    class Enc:
+        device = torch.device('cpu')
+        config = types.SimpleNamespace(model_sample_rate=SR, model_token_rate=50)
+        n_layers = 19
+        seen = []
+
+        def rows_for(self, pad):
+            return padded_rows(pad)
+
+        def rows_for_tokens(self, n_tokens, pad):
+            return max(1, min(n_tokens, self.rows_for(pad)))
+
+        def encode_plan(self, wave, plan, tap_layer=-1):
+            assert tap_layer == 19
+            self.seen.append(int(plan.total_rows))
+            return None, torch.arange(plan.total_rows * 8, dtype=torch.float32).reshape(plan.total_rows, 8)
+
+    enc = Enc()
+    got = list(training.iter_embeddings(enc, files, chunk_size=5, max_rows=300))
+    assert sum(b.shape[0] for b in got) == 163 + 50 + 105 + 250 + 32 and max(b.shape[0] for b in got) <= 300
+    assert all(abs(float(b.mean())) < 1e-4 for b in got)                      # affine-free LayerNorm was applied
+    enc.seen.clear()
+    padded = list(training.iter_embeddings(enc, files, chunk_size=5, max_rows=600, padded_rows=True))
+    assert sum(b.shape[0] for b in padded) == 5 * padded_rows(5 * SR) and enc.seen == [b.shape[0] for b in padded]
+
+    class Trainer:
+        codebook_size = 4
+        calls = 0
+
+        def train(self):
+            return self
+
+        def __call__(self, x):
+            self.calls += 1
+            return None, torch.arange(x.shape[0]) % 3, torch.tensor([0.25])
+
+        def state_dict(self):
+            return {'_codebook.embed': torch.zeros(1, 4, 8)}
+
+    tr = Trainer()
+    st = training.train_codebook(tr, iter(got), outdir=str(tmp_path / 'ck'), save_freq=2, layer=19)
+    assert tr.calls == len(got) and st['batches'] == len(got) and st['active_fraction'] == 0.75 and st['commit_loss'] == 0.25
+    assert sorted(os.listdir(tmp_path / 'ck'))[0] == 'quantizer__L19_C4_ckpt0.pkl'
